@@ -1,0 +1,430 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   D[M,N] = epilogue( A[M,K] * W[N,K]^T )           bf16 in, fp32 accumulate in TMEM, bf16 out
+//
+// One kernel, two A-operand producers:
+//   GEMM mode : A is a row-major [M,K] matrix, tiles fetched with 2-D TMA boxes {64, 128}.
+//   CONV mode : A is an NHWC activation [B,H,W,C]; the 128 rows of an M tile are a pixel box
+//               {TB,TH,TW}; for each of the 9 taps the producer issues a 4-D TMA box shifted by
+//               (kh-1, kw-1). Out-of-bounds rows/columns are zero-filled by the TMA unit, which is
+//               exactly conv2d's zero padding -> no im2col buffer is ever materialised.
+//               Up to two extra 1x1 sources are accumulated into the same tile (ResnetBlock's
+//               conv_shortcut over the un-normalised input / the skip-concat halves).
+//
+// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer (one elected
+// lane), warps 2..5 = epilogue (TMEM -> registers -> bias/temb/residual/GEGLU -> global).
+// Two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
+//
+// Replaces the reference's library calls: nn.Conv2d inside InflatedConv3d
+// (animatediff/models/resnet.py:19-27), nn.Linear / LoRACompatibleLinear everywhere
+// (diffusers/models/lora.py:368), GEGLU (diffusers/models/activations.py:93-122).
+#include "common.cuh"
+#include "tmap.h"
+
+namespace i360 {
+
+struct GemmConvParams {
+  // problem
+  int M, N, K;        // GEMM mode (conv: M = padded pixel count, K unused)
+  int conv;           // 0 = GEMM, 1 = CONV3x3
+  // conv geometry (input dims include any materialised halo)
+  int B, H, W;
+  int TW, TH, TB;     // pixel box, TW*TH*TB == 128
+  int n_wt, n_ht, n_bt;
+  int Cin, C2, C3;    // channels of the 3x3 source and of up to two extra 1x1 sources
+  int crop;           // output columns cropped on each side (pano halo)
+  int Hout, Wout;
+  // tiling
+  int m_tiles, n_tiles;
+  int k_iters;        // 64-wide K blocks per tile
+  // epilogue
+  bf16* D; long long ldd;
+  const bf16* bias;                 // [N] (GEGLU: [2*N_out], values then gates like the weight)
+  const bf16* resid; long long ldr; // same row mapping as D
+  const float* rowvec; int rowvec_div; int rowvec_ld;  // += rowvec[(img_or_row / div) * ld + col]
+  int act;            // 0 none, 1 GEGLU (tile = [values | gates]), 2 GELU(erf), 3 SiLU
+  float out_scale;
+  int n_out;          // logical output columns (GEGLU: N/2)
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+
+template <int BN> struct Cfg {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                   : (2 * BN <= 256) ? 256 : 512;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW,
+                 const GemmConvParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full = bars;                       // [kStages]
+  uint64_t* empty = bars + C::kStages;         // [kStages]
+  uint64_t* tfull = bars + 2 * C::kStages;     // [2]
+  uint64_t* tempty = bars + 2 * C::kStages + 2;// [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW);
+    if (p.C2 > 0) tma_prefetch_desc(&tmA2);
+    if (p.C3 > 0) tma_prefetch_desc(&tmA3);
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, C::kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
+        const int n0 = n_blk * BN;
+        int w0 = 0, h0 = 0, b0 = 0;
+        if (p.conv) {
+          w0 = (m_blk % p.n_wt) * p.TW;
+          h0 = ((m_blk / p.n_wt) % p.n_ht) * p.TH;
+          b0 = (m_blk / (p.n_wt * p.n_ht)) * p.TB;
+        }
+        auto issue = [&](const CUtensorMap* ma, int c0, int dw, int dh, int kcoord) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kABytes;
+          mbar_expect_tx(&full[stage], C::kStageBytes);
+          if (p.conv) tma_load_4d(sa, ma, &full[stage], c0, w0 + dw, h0 + dh, b0);
+          else        tma_load_2d(sa, ma, &full[stage], c0, m_blk * BM);
+          tma_load_2d(sb, &tmW, &full[stage], kcoord, n0);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        };
+        if (!p.conv) {
+          for (int kb = 0; kb < p.k_iters; ++kb) issue(&tmA, kb * BK, 0, 0, kb * BK);
+        } else {
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+            for (int c0 = 0; c0 < p.Cin; c0 += BK) issue(&tmA, c0, dw, dh, tap * p.Cin + c0);
+          }
+          for (int c0 = 0; c0 < p.C2; c0 += BK) issue(&tmA2, c0, 0, 0, 9 * p.Cin + c0);
+          for (int c0 = 0; c0 < p.C3; c0 += BK) issue(&tmA3, c0, 0, 0, 9 * p.Cin + p.C2 + c0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.k_iters; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * C::kStageBytes;
+          const uint32_t sb = sa + C::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * 32, 1024, 16, SWZ_128B);
+            const uint64_t db = make_smem_desc(sb + k * 32, 1024, 16, SWZ_128B);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);   // frees the smem slot once these MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[as]);        // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 2..5) ===============================
+    const int ew = warp & 3;                 // TMEM lane quarter this warp may read
+    const int row = ew * 32 + lane;          // row inside the 128-row tile
+    int as = 0; uint32_t aphase = 0;
+    constexpr int NOUT = BN;                 // accumulator columns
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
+      // ---- row mapping ----
+      bool valid; long long orow; int vec_idx;
+      if (p.conv) {
+        const int tw = row % p.TW, th = (row / p.TW) % p.TH, tb = row / (p.TW * p.TH);
+        const int w = (m_blk % p.n_wt) * p.TW + tw;
+        const int h = ((m_blk / p.n_wt) % p.n_ht) * p.TH + th;
+        const int b = (m_blk / (p.n_wt * p.n_ht)) * p.TB + tb;
+        valid = (b < p.B) && (h < p.H) && (w >= p.crop) && (w < p.W - p.crop);
+        orow = (static_cast<long long>(b) * p.Hout + h) * p.Wout + (w - p.crop);
+        vec_idx = b;
+      } else {
+        const int r = m_blk * BM + row;
+        valid = r < p.M; orow = r; vec_idx = r;
+      }
+      const float* rv = (p.rowvec != nullptr)
+                            ? p.rowvec + static_cast<long long>(vec_idx / p.rowvec_div) * p.rowvec_ld
+                            : nullptr;
+      bf16* drow = p.D + orow * p.ldd;
+      const bf16* rrow = (p.resid != nullptr) ? p.resid + orow * p.ldr : nullptr;
+
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+
+      if (p.act == 1) {
+        // GEGLU: accumulator columns [0,BN/2) are values, [BN/2,BN) the matching gates
+        constexpr int HALF = NOUT / 2;
+        const int oc0 = n_blk * HALF;
+#pragma unroll 1
+        for (int c = 0; c < HALF; c += 16) {
+          uint32_t va[16], vg[16];
+          tmem_ld_x16(t_acc + c, va);
+          tmem_ld_x16(t_acc + HALF + c, vg);
+          tmem_ld_wait();
+          const int col = oc0 + c;
+          if (valid && col < p.n_out) {
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              float a0 = __uint_as_float(va[j]), a1 = __uint_as_float(va[j + 1]);
+              float g0 = __uint_as_float(vg[j]), g1 = __uint_as_float(vg[j + 1]);
+              if (p.bias) {
+                a0 += __bfloat162float(p.bias[n_blk * BN + c + j]);
+                a1 += __bfloat162float(p.bias[n_blk * BN + c + j + 1]);
+                g0 += __bfloat162float(p.bias[n_blk * BN + HALF + c + j]);
+                g1 += __bfloat162float(p.bias[n_blk * BN + HALF + c + j + 1]);
+              }
+              o[j / 2] = pack_bf16x2(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
+            }
+            uint4* dst = reinterpret_cast<uint4*>(drow + col);
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      } else {
+        const int oc0 = n_blk * BN;
+#pragma unroll 1
+        for (int c = 0; c < NOUT; c += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(t_acc + c, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = oc0 + c + g * 8;
+              if (col < p.N) {   // N is a multiple of 8 (checked on the host)
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+                if (p.bias) {
+                  const uint4 bb = *reinterpret_cast<const uint4*>(p.bias + col);
+                  float2 t0 = unpack_bf16x2(bb.x), t1 = unpack_bf16x2(bb.y);
+                  float2 t2 = unpack_bf16x2(bb.z), t3 = unpack_bf16x2(bb.w);
+                  f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
+                  f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
+                }
+                if (rv) {
+                  const float4 r0 = *reinterpret_cast<const float4*>(rv + col);
+                  const float4 r1 = *reinterpret_cast<const float4*>(rv + col + 4);
+                  f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                  f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+                }
+                if (p.act == 2) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
+                } else if (p.act == 3) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = silu(f[j]);
+                }
+                if (rrow) {
+                  const uint4 rr = *reinterpret_cast<const uint4*>(rrow + col);
+                  float2 t0 = unpack_bf16x2(rr.x), t1 = unpack_bf16x2(rr.y);
+                  float2 t2 = unpack_bf16x2(rr.z), t3 = unpack_bf16x2(rr.w);
+                  f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
+                  f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
+                }
+                if (p.out_scale != 1.0f) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] *= p.out_scale;
+                }
+                *reinterpret_cast<uint4*>(drow + col) =
+                    make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                               pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, C::kTmemCols); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3,
+                  const CUtensorMap& w, const GemmConvParams& p, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             C::kSmemBytes) != cudaSuccess)
+      return I360_ERR_CUDA;
+    attr_set = true;
+  }
+  int grid = p.m_tiles * p.n_tiles;
+  if (grid > num_sms()) grid = num_sms();
+  if (grid <= 0) return I360_OK;
+  gemm_conv_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(a, a2, a3, w, p);
+  I360_CUDA_CHECK_LAUNCH();
+  return I360_OK;
+}
+
+static int pick_bn(int N, int act) {
+  // GEGLU tiles need value/gate halves -> 256 (128 out cols) unless the problem is tiny
+  if (act == 1) return (N % 256 == 0) ? 256 : ((N % 160 == 0) ? 160 : ((N % 128 == 0) ? 128 : 64));
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  // minimise padded columns; prefer the wider tile on ties (better smem traffic per FLOP)
+  int best = 256; long best_waste = ((N + 255) / 256) * 256L - N;
+  const int cands[3] = {160, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    long w = ((N + cands[i] - 1) / cands[i]) * (long)cands[i] - N;
+    if (w < best_waste) { best_waste = w; best = cands[i]; }
+  }
+  return best;
+}
+
+static int dispatch(int bn, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3,
+                    const CUtensorMap& w, const GemmConvParams& p, cudaStream_t st) {
+  switch (bn) {
+    case 64: return launch<64>(a, a2, a3, w, p, st);
+    case 128: return launch<128>(a, a2, a3, w, p, st);
+    case 160: return launch<160>(a, a2, a3, w, p, st);
+    case 256: return launch<256>(a, a2, a3, w, p, st);
+  }
+  return I360_ERR_ARG;
+}
+
+}  // namespace i360
+
+using namespace i360;
+
+// GEGLU packing contract: the caller packs W (and bias) so that each BN-row block holds BN/2 value
+// rows followed by the BN/2 matching gate rows; i360_gemm_geglu_block(N) returns that BN.
+extern "C" int i360_gemm_geglu_block(int n_total) { return pick_bn(n_total, 1); }
+
+extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* D,
+                              long long ldd, int M, int N, int K, const void* bias,
+                              const void* resid, long long ldr, const float* rowvec, int rowvec_div,
+                              int rowvec_ld, int act, float out_scale, void* stream) {
+  if (!A || !W || !D || M <= 0 || N <= 0 || K <= 0) return I360_ERR_ARG;
+  if ((K % 8) || (lda % 8) || (ldw % 8) || (ldd % 8) || (N % 8)) return I360_ERR_ARG;
+  if (resid && (ldr % 8)) return I360_ERR_ARG;
+  if (act == 1 && (N % 2)) return I360_ERR_ARG;
+  const int bn = pick_bn(N, act);
+  if (act == 1 && (N % bn)) return I360_ERR_ARG;
+  GemmConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K; p.conv = 0;
+  p.m_tiles = (M + BM - 1) / BM; p.n_tiles = (N + bn - 1) / bn; p.k_iters = (K + BK - 1) / BK;
+  p.D = static_cast<bf16*>(D); p.ldd = ldd;
+  p.bias = static_cast<const bf16*>(bias);
+  p.resid = static_cast<const bf16*>(resid); p.ldr = ldr;
+  p.rowvec = rowvec; p.rowvec_div = rowvec_div > 0 ? rowvec_div : 1; p.rowvec_ld = rowvec_ld;
+  p.act = act; p.out_scale = out_scale; p.n_out = (act == 1) ? N / 2 : N;
+  CUtensorMap ta, tw;
+  uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}; uint64_t sA[1] = {(uint64_t)lda * 2};
+  uint32_t bA[2] = {BK, BM};
+  uint64_t dW[2] = {(uint64_t)K, (uint64_t)N}; uint64_t sW[1] = {(uint64_t)ldw * 2};
+  uint32_t bW[2] = {BK, (uint32_t)bn};
+  int r = get_tmap_bf16(&ta, A, 2, dA, sA, bA, 3); if (r) return r;
+  r = get_tmap_bf16(&tw, W, 2, dW, sW, bW, 3); if (r) return r;
+  return dispatch(bn, ta, ta, ta, tw, p, static_cast<cudaStream_t>(stream));
+}
+
+// x: NHWC [B,H,W,Cin] (H,W include any materialised halo); Wt: [Cout, 9*Cin + C2 + C3] with the
+// 3x3 part ordered (kh, kw, cin). x2/x3: optional NHWC [B,H,W,C2|C3] sources for a fused 1x1.
+// Output NHWC [B, H, W-2*crop, Cout].
+extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, const void* x2, int C2,
+                                 const void* x3, int C3, const void* Wt, int Cout, void* D,
+                                 int crop, const void* bias, const void* resid,
+                                 const float* rowvec, int rowvec_div, int rowvec_ld,
+                                 float out_scale, void* stream) {
+  if (!x || !Wt || !D || B <= 0 || H <= 0 || W <= 0) return I360_ERR_ARG;
+  if ((Cin % 8) || (Cout % 8) || (C2 % 8) || (C3 % 8) || crop < 0 || 2 * crop >= W)
+    return I360_ERR_ARG;
+  if ((C2 > 0 && !x2) || (C3 > 0 && !x3)) return I360_ERR_ARG;
+  if ((C2 % 64 && C3 > 0) || (Cin % 64 && (C2 > 0))) return I360_ERR_ARG;  // K segments must align
+  // choose the pixel box minimising padded work
+  int bestTW = 16, bestTH = 8, bestTB = 1; double bestw = 1e30;
+  for (int tw = 1; tw <= 128; tw *= 2)
+    for (int th = 1; tw * th <= 128; th *= 2) {
+      const int tb = 128 / (tw * th);
+      if (tw > 1 && tw / 2 >= W) continue;
+      if (th > 1 && th / 2 >= H) continue;
+      const double waste = (double)((W + tw - 1) / tw * tw) * ((H + th - 1) / th * th) *
+                           ((B + tb - 1) / tb * tb) / ((double)W * H * B);
+      const double score = waste - 1e-6 * tw;  // ties -> wider rows
+      if (score < bestw) { bestw = score; bestTW = tw; bestTH = th; bestTB = tb; }
+    }
+  GemmConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.conv = 1; p.B = B; p.H = H; p.W = W; p.TW = bestTW; p.TH = bestTH; p.TB = bestTB;
+  p.n_wt = (W + p.TW - 1) / p.TW; p.n_ht = (H + p.TH - 1) / p.TH; p.n_bt = (B + p.TB - 1) / p.TB;
+  p.Cin = Cin; p.C2 = C2; p.C3 = C3; p.crop = crop; p.Hout = H; p.Wout = W - 2 * crop;
+  p.N = Cout; p.M = p.n_wt * p.n_ht * p.n_bt * BM;
+  const int bn = pick_bn(Cout, 0);
+  p.m_tiles = p.n_wt * p.n_ht * p.n_bt; p.n_tiles = (Cout + bn - 1) / bn;
+  p.k_iters = 9 * ((Cin + BK - 1) / BK) + (C2 + BK - 1) / BK + (C3 + BK - 1) / BK;
+  p.D = static_cast<bf16*>(D); p.ldd = Cout;
+  p.bias = static_cast<const bf16*>(bias);
+  p.resid = static_cast<const bf16*>(resid); p.ldr = Cout;
+  p.rowvec = rowvec; p.rowvec_div = rowvec_div > 0 ? rowvec_div : 1; p.rowvec_ld = rowvec_ld;
+  p.act = 0; p.out_scale = out_scale; p.n_out = Cout;
+  const long long Ktot = 9LL * Cin + C2 + C3;
+  CUtensorMap ta, ta2, ta3, tw;
+  auto act_map = [&](CUtensorMap* m, const void* ptr, int C) {
+    uint64_t d[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t s[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t b[4] = {BK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
+    return get_tmap_bf16(m, ptr, 4, d, s, b, 3);
+  };
+  int r = act_map(&ta, x, Cin); if (r) return r;
+  ta2 = ta; ta3 = ta;
+  if (C2 > 0) { r = act_map(&ta2, x2, C2); if (r) return r; }
+  if (C3 > 0) { r = act_map(&ta3, x3, C3); if (r) return r; }
+  uint64_t dW[2] = {(uint64_t)Ktot, (uint64_t)Cout}; uint64_t sW[1] = {(uint64_t)Ktot * 2};
+  uint32_t bW[2] = {BK, (uint32_t)bn};
+  r = get_tmap_bf16(&tw, Wt, 2, dW, sW, bW, 3); if (r) return r;
+  return dispatch(bn, ta, ta2, ta3, tw, p, static_cast<cudaStream_t>(stream));
+}

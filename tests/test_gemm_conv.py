@@ -1,0 +1,112 @@
+"""GPU parity of the tcgen05 GEMM / implicit-GEMM conv engine against fp32 torch math.
+
+These are floating-point kernels, so the checker is a plain fp32 torch evaluation of the same op on
+the same bf16 inputs (the CPU oracle modules are compared at block level in test_blocks_gpu.py).
+Tolerance: bf16 output rounding (2^-8 relative) on top of fp32 accumulation-order noise.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(out, ref, what, rtol=1.0 / 128, atol_scale=2e-3):
+    out = out.float()
+    ref = ref.float()
+    atol = atol_scale * ref.abs().max().item() + 1e-6
+    err = (out - ref).abs()
+    bad = err > (atol + rtol * ref.abs())
+    assert not bad.any(), f"{what}: {bad.sum().item()} / {bad.numel()} mismatches, max err {err.max().item():.4g}, ref max {ref.abs().max().item():.4g}"
+
+
+@pytest.mark.parametrize("M,N,K", [
+    (128, 64, 64), (256, 128, 128), (300, 320, 320), (1000, 640, 320), (4096, 1280, 1280),
+    (77, 320, 1024), (2, 1280, 320), (5000, 960, 320), (513, 2560, 1280), (640, 1920, 640),
+    (130, 1024, 4096), (128, 72, 200),
+])
+def test_gemm_plain(M, N, K):
+    from imagine360_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    out = ops.gemm(a, w)
+    _close(out, a.float() @ w.float().t(), f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_epilogues():
+    from imagine360_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    M, N, K = 1500, 640, 320
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g).bfloat16()
+    resid = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    rowvec = torch.randn(M // 100, N, device="cuda", generator=g)
+    ref = a.float() @ w.float().t() + bias.float()
+    _close(ops.gemm(a, w, bias=bias), ref, "bias")
+    _close(ops.gemm(a, w, bias=bias, resid=resid), ref + resid.float(), "bias+resid")
+    _close(ops.gemm(a, w, bias=bias, act=ops.ACT_GELU), F.gelu(ref), "gelu")
+    _close(ops.gemm(a, w, bias=bias, act=ops.ACT_SILU), F.silu(ref), "silu")
+    rv = rowvec.repeat_interleave(100, dim=0)
+    _close(ops.gemm(a, w, bias=bias, rowvec=rowvec, rowvec_div=100, out_scale=0.5), (ref + rv) * 0.5, "rowvec+scale")
+    # strided A view and strided output view
+    big = torch.randn(M, 2 * K, device="cuda", generator=g).bfloat16()
+    outbig = torch.zeros(M, 2 * N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(big[:, K:], w, out=outbig[:, N:])
+    _close(outbig[:, N:], big[:, K:].float() @ w.float().t(), "strided views")
+    assert outbig[:, :N].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("C", [320, 640, 1280])
+def test_gemm_geglu(C):
+    from imagine360_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(C)
+    M = 777
+    a = torch.randn(M, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(8 * C, C, device="cuda", generator=g) / C ** 0.5).bfloat16()
+    b = torch.randn(8 * C, device="cuda", generator=g).bfloat16()
+    wp, bp = ops.pack_geglu(w, b)
+    out = ops.gemm(a, wp, bias=bp, act=ops.ACT_GEGLU)
+    h = a.float() @ w.float().t() + b.float()
+    val, gate = h.chunk(2, dim=-1)
+    _close(out, val * F.gelu(gate), f"geglu {C}")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [
+    (2, 16, 16, 64, 64), (3, 32, 32, 320, 320), (5, 8, 8, 640, 1280), (9, 4, 4, 1280, 1280),
+    (2, 64, 132, 320, 320), (2, 32, 68, 960, 640), (2, 8, 20, 2560, 1280), (1, 24, 40, 128, 256),
+    (2, 16, 36, 64, 8),
+])
+def test_conv3x3(B, H, W, Cin, Cout):
+    from imagine360_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B * 131 + H * 17 + Cin + Cout)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda", generator=g).bfloat16()
+    out = ops.conv3x3(x, ops.pack_conv3x3(w), bias=bias)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias.float(), padding=1).permute(0, 2, 3, 1)
+    _close(out, ref, f"conv {B}x{H}x{W} {Cin}->{Cout}")
+
+
+def test_conv3x3_fused_shortcut_temb_crop():
+    """conv2 of a pano ResnetBlock3D: 3x3 on the padded domain + 1x1 shortcut over two concatenated
+    sources + temb + crop of the circular halo (MVGenModel.py:276-281, resnet.py:246-251)."""
+    from imagine360_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, H, W, Cin, Cout, C2, C3, crop, F_ = 4, 16, 36, 128, 192, 64, 128, 2, 2
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).bfloat16()
+    x2 = torch.randn(B, H, W, C2, device="cuda", generator=g).bfloat16()
+    x3 = torch.randn(B, H, W, C3, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    ws = (torch.randn(Cout, C2 + C3, 1, 1, device="cuda", generator=g) / (C2 + C3) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda", generator=g).bfloat16()
+    temb = torch.randn(B // F_, Cout, device="cuda", generator=g)
+    resid = torch.randn(B, H, W - 2 * crop, Cout, device="cuda", generator=g).bfloat16()
+    out = ops.conv3x3(x, ops.pack_conv3x3(w, ws), bias=bias, x2=x2, x3=x3, resid=resid, rowvec=temb,
+                      rowvec_div=F_, crop=crop)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias.float(), padding=1)
+    ref = ref + F.conv2d(torch.cat([x2, x3], -1).float().permute(0, 3, 1, 2), ws.float())
+    ref = ref + temb.repeat_interleave(F_, 0)[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1)[:, :, crop:-crop] + resid.float()
+    _close(out, ref, "fused conv")
