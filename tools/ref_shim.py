@@ -136,6 +136,9 @@ def install():
         assert diffusers.__file__.startswith(REF), diffusers.__file__
     finally:
         importlib.util.find_spec = real_find_spec
+    import diffusers.models.attention_processor as _ap
+
+    _ap.xformers = sys.modules["xformers"]   # module-level `xformers = None` when the wheel is absent
     import src.modules.utils as smu
 
     smu.flush = lambda: None
@@ -181,7 +184,7 @@ def tiny_unet_kwargs(c0=32, heads=(1, 2, 2, 2), cross_dim=64, img_hidden=16, num
     kw["image_cross_attention_dim"] = cross_dim
     kw["image_hidden_size"] = img_hidden
     kw["num_tokens"] = num_tokens
-    kw["norm_num_groups"] = 8
+    kw["norm_num_groups"] = 32
     mk = dict(kw["motion_module_kwargs"])
     mk["num_attention_heads"] = mm_heads
     kw["motion_module_kwargs"] = mk
