@@ -1,0 +1,270 @@
+// Channels-last normalisation kernels (HBM-bound: one coalesced 16-byte-vector read per element,
+// fp32 statistics, bf16 out).
+//
+//  * GroupNorm (per-image statistics = InflatedGroupNorm, animatediff/models/resnet.py:9-17, and the
+//    plain nn.GroupNorm of Transformer3DModel / TemporalTransformer3DModel / the VAE), split into
+//      gn_stats : sum / sum-of-squares per (image, group), accumulated in fp64 atomics
+//      gn_apply : (x - mean) * rstd * gamma + beta  [-> SiLU], written as a dense NHWC tensor.
+//    Both read a VIRTUAL tensor: the channel concatenation of up to two sources (UNet skip concat,
+//    MVGenModel.py:399) circularly padded by `pad` columns (pad_pano, src/utils/pano.py:75-92), so the
+//    statistics are those of the padded tensor exactly as in the reference (SURVEY.md trap 1) while the
+//    concat / pad copies are never materialised on their own.
+//  * LayerNorm over the last dim with optional additive tables before (WarpAttn query PE,
+//    src/modules/transformer.py:155-159) and after (temporal sinusoidal PE, motion_module.py:350).
+#include "common.cuh"
+#include "tmap.h"
+
+namespace i360 {
+
+struct GnSrc {
+  const bf16* x1; const bf16* x2;
+  int C1, C2;       // channels of each source (C2 = 0 when unused); both multiples of 8
+  int H, Wsrc, pad; // virtual width = Wsrc + 2*pad, column wv reads (wv - pad) mod Wsrc
+};
+
+__device__ __forceinline__ uint4 gn_load(const GnSrc& s, int b, long long pix, int v, int Wv) {
+  const int h = static_cast<int>(pix / Wv);
+  int w = static_cast<int>(pix - static_cast<long long>(h) * Wv) - s.pad;
+  w = (w % s.Wsrc + s.Wsrc) % s.Wsrc;
+  const long long p = (static_cast<long long>(b) * s.H + h) * s.Wsrc + w;
+  const int nv1 = s.C1 >> 3;
+  const bf16* ptr = (v < nv1) ? s.x1 + p * s.C1 + v * 8 : s.x2 + p * s.C2 + (v - nv1) * 8;
+  return *reinterpret_cast<const uint4*>(ptr);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// grid (chunks, B); block = R * nvec threads; dynamic smem = R*C*2 floats
+__global__ void gn_stats_kernel(GnSrc s, int groups, int chunk_pixels, double* __restrict__ stats) {
+  extern __shared__ float sm[];
+  const int C = s.C1 + s.C2, nvec = C >> 3, R = blockDim.x / nvec;
+  const int Wv = s.Wsrc + 2 * s.pad;
+  const long long npix = static_cast<long long>(s.H) * Wv;
+  const int b = blockIdx.y;
+  const int r = threadIdx.x / nvec, v = threadIdx.x % nvec;
+  const long long p0 = static_cast<long long>(blockIdx.x) * chunk_pixels;
+  long long p1 = p0 + chunk_pixels; if (p1 > npix) p1 = npix;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  if (r < R) {
+    for (long long p = p0 + r; p < p1; p += R) {
+      float f[8];
+      unpack8(gn_load(s, b, p, v, Wv), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] += f[j] * f[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sm[(r * C + v * 8 + j) * 2] = s1[j];
+      sm[(r * C + v * 8 + j) * 2 + 1] = s2[j];
+    }
+  }
+  __syncthreads();
+  const int gs = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double a = 0.0, q = 0.0;
+    for (int rr = 0; rr < R; ++rr)
+      for (int c = g * gs; c < (g + 1) * gs; ++c) { a += sm[(rr * C + c) * 2]; q += sm[(rr * C + c) * 2 + 1]; }
+    atomicAdd(&stats[(static_cast<long long>(b) * groups + g) * 2], a);
+    atomicAdd(&stats[(static_cast<long long>(b) * groups + g) * 2 + 1], q);
+  }
+}
+
+// grid (chunks, B); block = R * nvec; dynamic smem = 2*C floats (scale, shift)
+__global__ void gn_apply_kernel(GnSrc s, int groups, int chunk_pixels, const double* __restrict__ stats,
+                                const bf16* __restrict__ gamma, const bf16* __restrict__ beta, float eps,
+                                int do_silu, double count, bf16* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int C = s.C1 + s.C2, nvec = C >> 3, R = blockDim.x / nvec;
+  const int Wv = s.Wsrc + 2 * s.pad;
+  const long long npix = static_cast<long long>(s.H) * Wv;
+  const int b = blockIdx.y;
+  const int gs = C / groups;
+  const double n = count > 0.0 ? count : static_cast<double>(npix) * gs;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / gs;
+    const double m = stats[(static_cast<long long>(b) * groups + g) * 2] / n;
+    double var = stats[(static_cast<long long>(b) * groups + g) * 2 + 1] / n - m * m;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float a = rstd * __bfloat162float(gamma[c]);
+    sm[c] = a;
+    sm[C + c] = __bfloat162float(beta[c]) - static_cast<float>(m) * a;
+  }
+  __syncthreads();
+  const int r = threadIdx.x / nvec, v = threadIdx.x % nvec;
+  if (r >= R) return;
+  const long long p0 = static_cast<long long>(blockIdx.x) * chunk_pixels;
+  long long p1 = p0 + chunk_pixels; if (p1 > npix) p1 = npix;
+  float a[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a[j] = sm[v * 8 + j]; sh[j] = sm[C + v * 8 + j]; }
+  for (long long p = p0 + r; p < p1; p += R) {
+    float f[8];
+    unpack8(gn_load(s, b, p, v, Wv), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = f[j] * a[j] + sh[j];
+      if (do_silu) f[j] = silu(f[j]);
+    }
+    *reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * npix + p) * C + v * 8) =
+        make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                   pack_bf16x2(f[6], f[7]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row kept in registers (C <= 8*32*MAXV)
+// ---------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                                 long long M, int C, const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
+                                 float eps, const bf16* __restrict__ pre_add, int pre_div_a, int pre_mod_a,
+                                 int pre_mul_a, int pre_mod_b,
+                                 const float* __restrict__ post_add, int post_div, int post_mod) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31, nvec = C >> 3;
+  float f[MAXV][8];
+  float sum = 0.f;
+  const bf16* xr = x + row * ldx;
+  // pre-add table row = ((row / div_a) % mod_a) * mul_a + row % mod_b   (view-major PE of WarpAttn's pers tokens)
+  const bf16* pr = pre_add ? pre_add + (((row / pre_div_a) % pre_mod_a) * pre_mul_a + row % pre_mod_b) * C : nullptr;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f[i]);
+      if (pr) {
+        float g[8];
+        unpack8(*reinterpret_cast<const uint4*>(pr + v * 8), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[i][j] = __bfloat162float(__float2bfloat16(f[i][j] + g[j]));  // bf16 add like the reference
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; var += d * d; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / C + eps);
+  const float* po = post_add ? post_add + static_cast<long long>((row / post_div) % post_mod) * C : nullptr;
+  bf16* yr = y + row * ldy;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float g[8], bb[8], o[8];
+      unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), g);
+      unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = (f[i][j] - mean) * rstd * g[j] + bb[j];
+        if (po) o[j] = __bfloat162float(__float2bfloat16(o[j])) + po[v * 8 + j];
+      }
+      *reinterpret_cast<uint4*>(yr + v * 8) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                         pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+  }
+}
+
+}  // namespace i360
+
+using namespace i360;
+
+static int gn_geometry(int C, int B, long long npix, int* block, int* chunk, int* chunks) {
+  const int nvec = C / 8;
+  if (nvec <= 0 || nvec > 1024) return I360_ERR_ARG;
+  int R = 384 / nvec; if (R < 1) R = 1;
+  *block = R * nvec;
+  long long target = (static_cast<long long>(num_sms()) * 4 + B - 1) / B;  // CTAs per image for ~4 waves
+  if (target < 1) target = 1;
+  long long cp = (npix + target - 1) / target;
+  const long long minp = static_cast<long long>(R) * 4;
+  if (cp < minp) cp = minp;
+  *chunk = static_cast<int>(cp);
+  *chunks = static_cast<int>((npix + cp - 1) / cp);
+  return I360_OK;
+}
+
+// stats: [B, groups, 2] fp64, zeroed here.  x2/C2 optional second concat source.
+extern "C" int i360_groupnorm_stats(const void* x1, int C1, const void* x2, int C2, int B, int H, int Wsrc,
+                                    int pad, int groups, double* stats, void* stream) {
+  const int C = C1 + C2;
+  if (!x1 || !stats || (C1 % 8) || (C2 % 8) || C <= 0 || (C % groups) || B <= 0 || pad < 0 || pad > Wsrc)
+    return I360_ERR_ARG;
+  if (C2 > 0 && !x2) return I360_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * groups, st) != cudaSuccess) return I360_ERR_CUDA;
+  GnSrc s{static_cast<const bf16*>(x1), static_cast<const bf16*>(x2), C1, C2, H, Wsrc, pad};
+  int block, chunk, chunks;
+  const long long npix = static_cast<long long>(H) * (Wsrc + 2 * pad);
+  int r = gn_geometry(C, B, npix, &block, &chunk, &chunks); if (r) return r;
+  const size_t smem = static_cast<size_t>(block) * 8 * 2 * sizeof(float);
+  if (smem > 48 * 1024) return I360_ERR_ARG;
+  gn_stats_kernel<<<dim3(chunks, B), block, smem, st>>>(s, groups, chunk, stats);
+  I360_CUDA_CHECK_LAUNCH();
+  return I360_OK;
+}
+
+// out: dense [B, H, Wsrc+2*pad, C1+C2].  stats_count: elements per (image, group) the statistics were taken
+// over; pass 0 when they were taken over this same virtual tensor (conv_norm_out normalises BEFORE the
+// circular pad, MVGenModel.py:472-475, so there stats use pad 0 while the output is written with pad 1).
+extern "C" int i360_groupnorm_apply(const void* x1, int C1, const void* x2, int C2, int B, int H, int Wsrc,
+                                    int pad, int groups, const double* stats, double stats_count, const void* gamma,
+                                    const void* beta, float eps, int do_silu, void* out, void* stream) {
+  const int C = C1 + C2;
+  if (!x1 || !stats || !gamma || !beta || !out || (C1 % 8) || (C2 % 8) || (C % groups)) return I360_ERR_ARG;
+  GnSrc s{static_cast<const bf16*>(x1), static_cast<const bf16*>(x2), C1, C2, H, Wsrc, pad};
+  int block, chunk, chunks;
+  const long long npix = static_cast<long long>(H) * (Wsrc + 2 * pad);
+  int r = gn_geometry(C, B, npix, &block, &chunk, &chunks); if (r) return r;
+  const size_t smem = static_cast<size_t>(C) * 2 * sizeof(float);
+  gn_apply_kernel<<<dim3(chunks, B), block, smem, static_cast<cudaStream_t>(stream)>>>(
+      s, groups, chunk, stats, static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), eps, do_silu,
+      stats_count, static_cast<bf16*>(out));
+  I360_CUDA_CHECK_LAUNCH();
+  return I360_OK;
+}
+
+extern "C" int i360_layernorm(const void* x, long long ldx, void* y, long long ldy, long long M, int C,
+                              const void* gamma, const void* beta, float eps, const void* pre_add, int pre_div_a,
+                              int pre_mod_a, int pre_mul_a, int pre_mod_b, const float* post_add, int post_div,
+                              int post_mod, void* stream) {
+  if (!x || !y || !gamma || !beta || M <= 0 || C <= 0 || (C % 8) || (ldx % 8) || (ldy % 8)) return I360_ERR_ARG;
+  if (pre_add && (pre_div_a <= 0 || pre_mod_a <= 0 || pre_mod_b <= 0)) return I360_ERR_ARG;
+  if (post_add && (post_div <= 0 || post_mod <= 0)) return I360_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int warps = 8;
+  const unsigned grid = static_cast<unsigned>((M + warps - 1) / warps);
+  const bf16 *xx = static_cast<const bf16*>(x), *g = static_cast<const bf16*>(gamma), *b = static_cast<const bf16*>(beta);
+  const bf16* pa = static_cast<const bf16*>(pre_add);
+  bf16* yy = static_cast<bf16*>(y);
+  const int nvec = C / 8;
+  if (nvec <= 32 * 2)
+    layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(xx, ldx, yy, ldy, M, C, g, b, eps, pa, pre_div_a, pre_mod_a, pre_mul_a, pre_mod_b, post_add, post_div, post_mod);
+  else if (nvec <= 32 * 5)
+    layernorm_kernel<5><<<grid, warps * 32, 0, st>>>(xx, ldx, yy, ldy, M, C, g, b, eps, pa, pre_div_a, pre_mod_a, pre_mul_a, pre_mod_b, post_add, post_div, post_mod);
+  else if (nvec <= 32 * 16)
+    layernorm_kernel<16><<<grid, warps * 32, 0, st>>>(xx, ldx, yy, ldy, M, C, g, b, eps, pa, pre_div_a, pre_mod_a, pre_mul_a, pre_mod_b, post_add, post_div, post_mod);
+  else
+    return I360_ERR_UNSUPPORTED;
+  I360_CUDA_CHECK_LAUNCH();
+  return I360_OK;
+}

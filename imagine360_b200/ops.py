@@ -118,3 +118,164 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias=None, x2=None, x3=None
         c_float(out_scale), _stream())
     check(rc, "i360_conv3x3_bf16")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation
+# ------------------------------------------------------------------------------------------------
+def groupnorm(x1: torch.Tensor, gamma, beta, groups: int, eps: float, silu: bool, x2=None, pad: int = 0,
+              stats_pad: int | None = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) over the channel concat of NHWC ``x1`` (and ``x2``), circularly padded by ``pad`` columns.
+    Statistics are per image over the padded tensor (``stats_pad`` overrides the pad used for statistics)."""
+    _chk_bf16(x1, x2, gamma, beta)
+    assert x1.dim() == 4 and x1.is_contiguous() and (x2 is None or (x2.is_contiguous() and x2.shape[:3] == x1.shape[:3]))
+    B, H, W, C1 = x1.shape
+    C2 = x2.shape[-1] if x2 is not None else 0
+    C = C1 + C2
+    sp = pad if stats_pad is None else stats_pad
+    stats = torch.empty((B, groups, 2), dtype=torch.float64, device=x1.device)
+    rc = lib().i360_groupnorm_stats(_p(x1), c_int(C1), _p(x2), c_int(C2), c_int(B), c_int(H), c_int(W), c_int(sp),
+                                    c_int(groups), _p(stats), _stream())
+    check(rc, "i360_groupnorm_stats")
+    out = torch.empty((B, H, W + 2 * pad, C), dtype=BF16, device=x1.device)
+    count = float(H * (W + 2 * sp) * (C // groups)) if sp != pad else 0.0
+    rc = lib().i360_groupnorm_apply(_p(x1), c_int(C1), _p(x2), c_int(C2), c_int(B), c_int(H), c_int(W), c_int(pad),
+                                    c_int(groups), _p(stats), ctypes.c_double(count), _p(gamma), _p(beta),
+                                    c_float(eps), c_int(1 if silu else 0), _p(out), _stream())
+    check(rc, "i360_groupnorm_apply")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma, beta, eps: float = 1e-5, pre_add=None, pre_index=(1, 1, 0, 1), post_add=None,
+              post_div: int = 1, post_mod: int = 1, out=None) -> torch.Tensor:
+    """LayerNorm over the last dim of 2-D ``x`` [M, C] (row-strided views allowed).
+    ``pre_add`` bf16 [*, C] is added first at row ((r // a) % b) * c + r % d with (a, b, c, d) = pre_index;
+    ``post_add`` fp32 [post_mod, C] is added last at row (r // post_div) % post_mod."""
+    _chk_bf16(x, gamma, beta, pre_add, out)
+    assert x.dim() == 2 and x.stride(1) == 1
+    M, C = x.shape
+    if out is None:
+        out = torch.empty((M, C), dtype=BF16, device=x.device)
+    if post_add is not None:
+        assert post_add.dtype == torch.float32 and post_add.is_contiguous() and post_add.shape[-1] == C
+    if pre_add is not None:
+        assert pre_add.is_contiguous() and pre_add.shape[-1] == C
+    a, b, c, d = pre_index
+    rc = lib().i360_layernorm(_p(x), c_longlong(x.stride(0)), _p(out), c_longlong(out.stride(0)), c_longlong(M), c_int(C),
+                              _p(gamma), _p(beta), c_float(eps), _p(pre_add), c_int(a), c_int(b), c_int(c), c_int(d),
+                              _p(post_add), c_int(post_div), c_int(post_mod), _stream())
+    check(rc, "i360_layernorm")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+class TokenView(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("channels", c_int), ("col0", c_int), ("d1", c_int), ("d2", c_int), ("d3", c_int),
+                ("s1", c_longlong), ("s2", c_longlong), ("s3", c_longlong), ("A", c_int), ("Bdiv", c_int),
+                ("mul", c_int), ("ext3", c_int)]
+
+
+def seq_view(t: torch.Tensor, n_seq: int, n_tok: int, col0: int = 0, share_div: int = 1) -> TokenView:
+    """Rows of 2-D ``t`` are ``n_seq`` consecutive sequences of ``n_tok`` tokens; batch item bi uses sequence
+    bi // share_div (share_div = frames when K/V are shared by all frames of a clip)."""
+    assert t.dim() == 2 and t.stride(1) == 1
+    ld = t.stride(0)
+    return TokenView(t.data_ptr(), t.shape[1], col0, n_tok, n_seq, 1, ld, ld * n_tok, ld * n_tok * n_seq, 0, share_div,
+                     0, 1)
+
+
+def multiview_view(t: torch.Tensor, n_clip: int, n_view: int, n_frame: int, n_tok: int, col0: int = 0) -> TokenView:
+    """Rows of ``t`` are ordered (clip, view, frame, token); batch item bi = clip * n_frame + frame attends over
+    the (view, token) axis of its frame (WarpAttn's '(b m) c f h w -> (b f) (m h w) c')."""
+    assert t.dim() == 2 and t.stride(1) == 1
+    ld = t.stride(0)
+    return TokenView(t.data_ptr(), t.shape[1], col0, n_tok, n_frame, n_clip * n_view, ld, ld * n_tok,
+                     ld * n_tok * n_frame, n_frame, 1, n_view, n_view)
+
+
+def attention(q: TokenView, k: TokenView, v: TokenView, o: TokenView, heads: int, head_dim: int, batch: int,
+              scale: float | None = None, bias: torch.Tensor | None = None, accumulate: bool = False) -> None:
+    if bias is not None:
+        _chk_bf16(bias)
+        assert bias.dim() == 2 and bias.is_contiguous()
+    rc = lib().i360_attention_bf16(ctypes.byref(q), ctypes.byref(k), ctypes.byref(v), ctypes.byref(o), c_int(heads),
+                                   c_int(head_dim), c_int(batch), c_float(scale if scale is not None else head_dim ** -0.5),
+                                   _p(bias), c_int(bias.shape[0] if bias is not None else 0),
+                                   c_int(bias.shape[1] if bias is not None else 0), c_int(1 if accumulate else 0), _stream())
+    check(rc, "i360_attention_bf16")
+
+
+def temporal_attention(q, k, v, out, B: int, F: int, D: int, heads: int, head_dim: int) -> None:
+    """q/k/v/out: 2-D bf16 views with rows ordered (b, f, d) and heads*head_dim columns."""
+    _chk_bf16(q, k, v, out)
+    rc = lib().i360_temporal_attention_bf16(_p(q), c_longlong(q.stride(0)), _p(k), c_longlong(k.stride(0)), _p(v),
+                                            c_longlong(v.stride(0)), _p(out), c_longlong(out.stride(0)), c_int(B),
+                                            c_int(F), c_int(D), c_int(heads), c_int(head_dim),
+                                            c_float(head_dim ** -0.5), _stream())
+    check(rc, "i360_temporal_attention_bf16")
+
+
+# ------------------------------------------------------------------------------------------------
+# data movement / elementwise
+# ------------------------------------------------------------------------------------------------
+def upsample2x(x: torch.Tensor, pad_in: int = 0) -> torch.Tensor:
+    _chk_bf16(x)
+    B, H, W, C = x.shape
+    out = torch.empty((B, 2 * H, 2 * (W + 2 * pad_in), C), dtype=BF16, device=x.device)
+    check(lib().i360_upsample2x_nhwc(_p(x), _p(out), c_int(B), c_int(H), c_int(W), c_int(C), c_int(pad_in), _stream()),
+          "i360_upsample2x_nhwc")
+    return out
+
+
+def im2col_s2(x: torch.Tensor, circular: bool) -> torch.Tensor:
+    _chk_bf16(x)
+    B, H, W, C = x.shape
+    out = torch.empty((B * (H // 2) * (W // 2), 9 * C), dtype=BF16, device=x.device)
+    check(lib().i360_im2col3x3_s2_nhwc(_p(x), _p(out), c_int(B), c_int(H), c_int(W), c_int(C), c_int(1 if circular else 0),
+                                       _stream()), "i360_im2col3x3_s2_nhwc")
+    return out
+
+
+def axpby(x: torch.Tensor, y: torch.Tensor | None, a: float, b: float) -> torch.Tensor:
+    _chk_bf16(x, y)
+    assert x.is_contiguous() and (y is None or (y.is_contiguous() and y.shape == x.shape))
+    out = torch.empty_like(x)
+    check(lib().i360_axpby_bf16(_p(x), _p(y), _p(out), c_float(a), c_float(b), c_longlong(x.numel()), _stream()),
+          "i360_axpby_bf16")
+    return out
+
+
+def cfg_ddim_step(latent, pred_uncond, pred_cond, guidance: float, sa: float, sb: float, sap: float, sbp: float):
+    _chk_bf16(latent, pred_uncond, pred_cond)
+    assert latent.is_contiguous() and pred_uncond.is_contiguous() and pred_cond.is_contiguous()
+    assert latent.shape == pred_uncond.shape == pred_cond.shape
+    out = torch.empty_like(latent)
+    check(lib().i360_cfg_ddim_step_bf16(_p(latent), _p(pred_uncond), _p(pred_cond), _p(out), c_float(guidance), c_float(sa),
+                                        c_float(sb), c_float(sap), c_float(sbp), c_longlong(latent.numel()), _stream()),
+          "i360_cfg_ddim_step_bf16")
+    return out
+
+
+def avgpool_frames4(x: torch.Tensor) -> torch.Tensor:
+    """[B, F, D, C] -> [B, F // 4, D, C]"""
+    _chk_bf16(x)
+    assert x.is_contiguous() and x.dim() == 4
+    B, F, D, C = x.shape
+    out = torch.empty((B, F // 4, D, C), dtype=BF16, device=x.device)
+    check(lib().i360_avgpool_frames4_bf16(_p(x), _p(out), c_int(B), c_int(F), c_longlong(D * C), _stream()),
+          "i360_avgpool_frames4_bf16")
+    return out
+
+
+def grid_sample(img: torch.Tensor, grid: torch.Tensor, nearest: bool = False) -> torch.Tensor:
+    """img [N, C, Hi, Wi] fp32, grid [N, Ho, Wo, 2] fp32 normalised (x, y), align_corners=True, zeros padding."""
+    assert img.dtype == torch.float32 and grid.dtype == torch.float32 and img.is_cuda and grid.is_cuda
+    img, grid = img.contiguous(), grid.contiguous()
+    N, C, Hi, Wi = img.shape
+    Ho, Wo = grid.shape[1:3]
+    out = torch.empty((N, C, Ho, Wo), dtype=torch.float32, device=img.device)
+    check(lib().i360_grid_sample_f32(_p(img), _p(grid), _p(out), c_int(N), c_int(C), c_int(Hi), c_int(Wi), c_int(Ho),
+                                     c_int(Wo), c_int(1 if nearest else 0), _stream()), "i360_grid_sample_f32")
+    return out

@@ -1,0 +1,129 @@
+/* imagine360_b200 -- C ABI of the B200-native (sm_100a) kernels behind Imagine360's dual-branch
+ * denoising hot path.
+ *
+ * The reference (3DTopia/Imagine360) is pure Python: it has no FFI of its own, its "operator
+ * interface" for this path is the set of torch / xformers / kornia library calls inventoried in
+ * SURVEY.md section 2.1.  Each entry point below replaces one of those call sites (cited as
+ * reference file:line) and is what a binding from the reference's Python modules would call
+ * (see INTEGRATION.md for the ctypes stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching allocator); the library
+ *     borrows it for the duration of the call, never frees it and allocates no device memory itself;
+ *   - activations are bf16, channels-last: images [N, H, W, C], tokens [rows, C]; weights bf16 [out, in];
+ *   - `stream` is a cudaStream_t; all work is enqueued on it, nothing synchronises;
+ *   - return value: 0 on success, negative I360_ERR_* otherwise (never throws, never aborts).
+ */
+#ifndef IMAGINE360_B200_H
+#define IMAGINE360_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define I360_OK 0
+#define I360_ERR_ARG (-1)
+#define I360_ERR_CUDA (-2)
+#define I360_ERR_TMAP (-3)
+#define I360_ERR_UNSUPPORTED (-4)
+
+/* epilogue activations of i360_gemm_bf16 */
+#define I360_ACT_NONE 0
+#define I360_ACT_GEGLU 1 /* tile = [values | gates] -> values * gelu_erf(gates)  (diffusers/models/activations.py:93-122) */
+#define I360_ACT_GELU 2  /* nn.GELU (animatediff/models/resampler.py:19) */
+#define I360_ACT_SILU 3  /* TimestepEmbedding.act (diffusers/models/embeddings.py:210) */
+
+/* D[M,N] = act(A[M,K] W[N,K]^T + bias[N] + rowvec[(row/rowvec_div), N]) + resid[M,N], then * out_scale.
+ * Replaces nn.Linear / LoRACompatibleLinear (diffusers/models/lora.py:368) at every call site of the path:
+ * attention projections (attention_processor.py:1244-1262), FeedForward (attention_lora.py:540-547),
+ * proj_in/proj_out (animatediff/models/attention.py:271,:289), time embeddings, the adapter.
+ * tcgen05 tensor cores, TMA-fed, persistent, fp32 accumulation in TMEM.  lda/ldw/ldd/ldr in elements. */
+int i360_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* D, long long ldd, int M, int N,
+                   int K, const void* bias, const void* resid, long long ldr, const float* rowvec, int rowvec_div,
+                   int rowvec_ld, int act, float out_scale, void* stream);
+
+/* Row-block size the GEGLU weight must be packed with ([block/2 value rows | block/2 gate rows] repeating). */
+int i360_gemm_geglu_block(int n_total);
+
+/* 3x3 / stride 1 / zero-pad 1 convolution as an im2col-free implicit GEMM over NHWC x[B,H,W,Cin], with up to
+ * two fused 1x1 sources x2/x3 (ResnetBlock3D.conv_shortcut over the [hidden | skip] concat), per-image
+ * rowvec (time embedding), residual, and `crop` halo columns dropped from the output (pano circular pad).
+ * Replaces nn.Conv2d inside InflatedConv3d (animatediff/models/resnet.py:19-27, call sites :227,:246,:249)
+ * and the VAE's convs (diffusers/models/resnet.py:454-496).  Wt: [Cout, 9*Cin + C2 + C3], taps (kh,kw,cin). */
+int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, const void* x2, int C2, const void* x3, int C3,
+                      const void* Wt, int Cout, void* D, int crop, const void* bias, const void* resid,
+                      const float* rowvec, int rowvec_div, int rowvec_ld, float out_scale, void* stream);
+
+/* GroupNorm statistics / application over a virtual tensor = concat(x1, x2) along C, circularly padded by `pad`
+ * columns.  Replaces InflatedGroupNorm / nn.GroupNorm (+ SiLU) (animatediff/models/resnet.py:9-17,:224-225,:243)
+ * together with torch.cat (MVGenModel.py:399) and pad_pano (src/utils/pano.py:75-92).  stats: [B, groups, 2] fp64. */
+int i360_groupnorm_stats(const void* x1, int C1, const void* x2, int C2, int B, int H, int Wsrc, int pad, int groups,
+                         double* stats, void* stream);
+int i360_groupnorm_apply(const void* x1, int C1, const void* x2, int C2, int B, int H, int Wsrc, int pad, int groups,
+                         const double* stats, double stats_count, const void* gamma, const void* beta, float eps,
+                         int do_silu, void* out, void* stream);
+
+/* LayerNorm over the last dim; optional bf16 table added before (spherical PE of WarpAttn,
+ * src/modules/transformer.py:155-161) and fp32 table added after (temporal PE, motion_module.py:350).
+ * Replaces nn.LayerNorm (animatediff/models/attention.py:463,:474,:505; motion_module.py:248,:256). */
+int i360_layernorm(const void* x, long long ldx, void* y, long long ldy, long long M, int C, const void* gamma,
+                   const void* beta, float eps, const void* pre_add, int pre_div_a, int pre_mod_a, int pre_mul_a,
+                   int pre_mod_b, const float* post_add, int post_div, int post_mod, void* stream);
+
+/* A strided 4-D token view [channels | d1, d2, d3] (strides in elements, channel stride 1).
+ * Batch item bi selects c2 = (bi % A) / Bdiv and c3 in [(bi / A) * mul, +ext3); a sequence is the d1 tokens of
+ * those ext3 dim-3 entries. */
+typedef struct I360TokenView {
+  const void* ptr;
+  int channels;
+  int col0;
+  int d1, d2, d3;
+  long long s1, s2, s3;
+  int A, Bdiv, mul;
+  int ext3;
+} I360TokenView;
+
+/* O = softmax(Q K^T * scale + bias) V per (batch item, head); head_dim 32 or 64; optional dense bf16 bias
+ * [bias_rows, bias_cols] shared by all batch items and heads; accumulate != 0: O_out = bf16(O_out + bf16(O)).
+ * Replaces xformers.ops.memory_efficient_attention (diffusers/models/attention_processor.py:1264,:641;
+ * src/modules/transformer.py:72) and F.scaled_dot_product_attention (attention_processor.py:1351). */
+int i360_attention_bf16(const I360TokenView* q, const I360TokenView* k, const I360TokenView* v,
+                        const I360TokenView* o, int heads, int head_dim, int batch, float scale, const void* bias,
+                        int bias_rows, int bias_cols, int accumulate, void* stream);
+
+/* Attention over the frame axis (F <= 32) for every (clip b, pixel d, head), rows ordered (b, f, d).
+ * Replaces the baddbmm/softmax/bmm math path of VersatileAttention (animatediff/models/motion_module.py:343-429,
+ * diffusers/models/attention_processor.py:562-591) and of TemporalProjection.attn_temp (resampler.py:246,:259). */
+int i360_temporal_attention_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                                 long long ldv, void* o, long long ldo, int B, int F, int D, int heads, int head_dim,
+                                 float scale, void* stream);
+
+/* nearest x2 upsample, out [B, 2H, 2(W+2*pad_in), C] (Upsample3D, animatediff/models/resnet.py:86-110, with the
+ * pano halo of MVGenModel.py:449-452 folded in). */
+int i360_upsample2x_nhwc(const void* x, void* out, int B, int H, int W, int C, int pad_in, void* stream);
+
+/* im2col for the stride-2 downsample convs (Downsample3D, resnet.py:117-140; circular = pano halo of
+ * MVGenModel.py:305-314).  out [B*(H/2)*(W/2), 9*C]. */
+int i360_im2col3x3_s2_nhwc(const void* x, void* out, int B, int H, int W, int C, int circular, void* stream);
+
+/* out = a*x + bf16(b*y)  (add_noise_to_condition, src/models/MVGenModel.py:11-14). */
+int i360_axpby_bf16(const void* x, const void* y, void* out, float a, float b, long long n, void* stream);
+
+/* Fused classifier-free guidance + DDIM v-prediction step with the reference's bf16 rounding sequence
+ * (pipeline_animation_inference_dual.py:789-800; diffusers/schedulers/scheduling_ddim.py:319-346). */
+int i360_cfg_ddim_step_bf16(const void* latent, const void* pred_uncond, const void* pred_cond, void* out,
+                            float guidance, float sqrt_a_t, float sqrt_1m_a_t, float sqrt_a_prev,
+                            float sqrt_1m_a_prev, long long n, void* stream);
+
+/* mean over groups of 4 frames (F.avg_pool1d(kernel 4), animatediff/models/resampler.py:251,:264). */
+int i360_avgpool_frames4_bf16(const void* x, void* out, int B, int F, long long DC, void* stream);
+
+/* grid_sample(align_corners=True, zeros padding), bilinear or nearest, NCHW fp32 (kornia.geometry.transform.remap
+ * as called by e2p.py:77 / p2e.py:70; init_noise pipeline_animation_inference_dual.py:376-379). */
+int i360_grid_sample_f32(const float* img, const float* grid, float* out, int N, int C, int Hi, int Wi, int Ho, int Wo,
+                         int nearest, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMAGINE360_B200_H */
