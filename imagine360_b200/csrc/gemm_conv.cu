@@ -33,6 +33,7 @@ struct GemmConvParams {
   int n_wt, n_ht, n_bt;
   int Cin, C2, C3;    // channels of the 3x3 source and of up to two extra 1x1 sources
   int crop;           // output columns cropped on each side (pano halo)
+  int xoff;           // column offset applied to the extra 1x1 sources (= -crop: they are stored un-padded)
   int Hout, Wout;
   // tiling
   int m_tiles, n_tiles;
@@ -126,8 +127,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int dh = tap / 3 - 1, dw = tap % 3 - 1;
             for (int c0 = 0; c0 < p.Cin; c0 += BK) issue(&tmA, c0, dw, dh, tap * p.Cin + c0);
           }
-          for (int c0 = 0; c0 < p.C2; c0 += BK) issue(&tmA2, c0, 0, 0, 9 * p.Cin + c0);
-          for (int c0 = 0; c0 < p.C3; c0 += BK) issue(&tmA3, c0, 0, 0, 9 * p.Cin + p.C2 + c0);
+          for (int c0 = 0; c0 < p.C2; c0 += BK) issue(&tmA2, c0, p.xoff, 0, 9 * p.Cin + c0);
+          for (int c0 = 0; c0 < p.C3; c0 += BK) issue(&tmA3, c0, p.xoff, 0, 9 * p.Cin + p.C2 + c0);
         }
       }
     }
@@ -373,8 +374,8 @@ extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long 
 }
 
 // x: NHWC [B,H,W,Cin] (H,W include any materialised halo); Wt: [Cout, 9*Cin + C2 + C3] with the
-// 3x3 part ordered (kh, kw, cin). x2/x3: optional NHWC [B,H,W,C2|C3] sources for a fused 1x1.
-// Output NHWC [B, H, W-2*crop, Cout].
+// 3x3 part ordered (kh, kw, cin). x2/x3: optional NHWC [B,H,W-2*crop,C2|C3] sources for a fused 1x1
+// (stored WITHOUT the halo, i.e. aligned with the output). Output NHWC [B, H, W-2*crop, Cout].
 extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, const void* x2, int C2,
                                  const void* x3, int C3, const void* Wt, int Cout, void* D,
                                  int crop, const void* bias, const void* resid,
@@ -384,7 +385,8 @@ extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, co
   if ((Cin % 8) || (Cout % 8) || (C2 % 8) || (C3 % 8) || crop < 0 || 2 * crop >= W)
     return I360_ERR_ARG;
   if ((C2 > 0 && !x2) || (C3 > 0 && !x3)) return I360_ERR_ARG;
-  if ((C2 % 64 && C3 > 0) || (Cin % 64 && (C2 > 0))) return I360_ERR_ARG;  // K segments must align
+  // K segments need no 64-alignment: channels past a source's extent are zero-filled by TMA, so whatever
+  // weight columns a partial K block overlaps are multiplied by zeros.
   // choose the pixel box minimising padded work
   int bestTW = 16, bestTH = 8, bestTB = 1; double bestw = 1e30;
   for (int tw = 1; tw <= 128; tw *= 2)
@@ -401,7 +403,7 @@ extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, co
   memset(&p, 0, sizeof(p));
   p.conv = 1; p.B = B; p.H = H; p.W = W; p.TW = bestTW; p.TH = bestTH; p.TB = bestTB;
   p.n_wt = (W + p.TW - 1) / p.TW; p.n_ht = (H + p.TH - 1) / p.TH; p.n_bt = (B + p.TB - 1) / p.TB;
-  p.Cin = Cin; p.C2 = C2; p.C3 = C3; p.crop = crop; p.Hout = H; p.Wout = W - 2 * crop;
+  p.Cin = Cin; p.C2 = C2; p.C3 = C3; p.crop = crop; p.xoff = -crop; p.Hout = H; p.Wout = W - 2 * crop;
   p.N = Cout; p.M = p.n_wt * p.n_ht * p.n_bt * BM;
   const int bn = pick_bn(Cout, 0);
   p.m_tiles = p.n_wt * p.n_ht * p.n_bt; p.n_tiles = (Cout + bn - 1) / bn;
@@ -413,16 +415,16 @@ extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, co
   p.act = 0; p.out_scale = out_scale; p.n_out = Cout;
   const long long Ktot = 9LL * Cin + C2 + C3;
   CUtensorMap ta, ta2, ta3, tw;
-  auto act_map = [&](CUtensorMap* m, const void* ptr, int C) {
-    uint64_t d[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    uint64_t s[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  auto act_map = [&](CUtensorMap* m, const void* ptr, int C, int Wt_) {
+    uint64_t d[4] = {(uint64_t)C, (uint64_t)Wt_, (uint64_t)H, (uint64_t)B};
+    uint64_t s[3] = {(uint64_t)C * 2, (uint64_t)Wt_ * C * 2, (uint64_t)H * Wt_ * C * 2};
     uint32_t b[4] = {BK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
     return get_tmap_bf16(m, ptr, 4, d, s, b, 3);
   };
-  int r = act_map(&ta, x, Cin); if (r) return r;
+  int r = act_map(&ta, x, Cin, W); if (r) return r;
   ta2 = ta; ta3 = ta;
-  if (C2 > 0) { r = act_map(&ta2, x2, C2); if (r) return r; }
-  if (C3 > 0) { r = act_map(&ta3, x3, C3); if (r) return r; }
+  if (C2 > 0) { r = act_map(&ta2, x2, C2, W - 2 * crop); if (r) return r; }
+  if (C3 > 0) { r = act_map(&ta3, x3, C3, W - 2 * crop); if (r) return r; }
   uint64_t dW[2] = {(uint64_t)Ktot, (uint64_t)Cout}; uint64_t sW[1] = {(uint64_t)Ktot * 2};
   uint32_t bW[2] = {BK, (uint32_t)bn};
   r = get_tmap_bf16(&tw, Wt, 2, dW, sW, bW, 3); if (r) return r;

@@ -1,0 +1,269 @@
+"""Native forward passes of the UNet3D blocks: every tensor op is a call into ``libimagine360_b200.so``.
+
+Activations are channels-last bf16 ``[images, H, W, C]`` with images ordered (batch, frame); the same memory is the
+token matrix ``[(b f h w), C]`` of the transformer blocks, so no permute/reshape copy exists between convolutions,
+spatial attention and temporal attention (the reference does one per block boundary: attention.py:266,:297;
+motion_module.py:166-181,:348,:427).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+from .unet3d import BF16, cached, conv_w, fused_w, geglu_w, lin_w, pad8
+
+
+# ------------------------------------------------------------------------------------------------------
+# layout glue for the 4/9-channel latents at the model boundary (tiny tensors; torch is plumbing here)
+# ------------------------------------------------------------------------------------------------------
+def latents_to_nhwc(x, circular_pad: int = 0):
+    """[b, c, f, h, w] -> [(b f), h, w(+2p), pad8(c)] bf16, optionally circularly padded on w (pad_pano)."""
+    b, c, f, h, w = x.shape
+    y = x.permute(0, 2, 3, 4, 1).reshape(b * f, h, w, c).to(BF16)
+    if circular_pad:
+        y = torch.cat([y[:, :, -circular_pad:], y, y[:, :, :circular_pad]], dim=2)
+    if pad8(c) != c:
+        y = F.pad(y, (0, pad8(c) - c))
+    return y.contiguous()
+
+
+def nhwc_to_latents(y, b, c):
+    """[(b f), h, w, >=c] -> [b, c, f, h, w]"""
+    n, h, w, _ = y.shape
+    return y[..., :c].reshape(b, n // b, h, w, c).permute(0, 4, 1, 2, 3).contiguous()
+
+
+def tokens(x):
+    return x.view(-1, x.shape[-1])
+
+
+# ------------------------------------------------------------------------------------------------------
+# time embedding (unet.py:718-744; MVGenModel.py:104-133)
+# ------------------------------------------------------------------------------------------------------
+def _mlp(t_emb, te):
+    w1, b1 = lin_w(te.linear_1)
+    w2, b2 = lin_w(te.linear_2)
+    h = ops.gemm(t_emb, w1, bias=b1, act=ops.ACT_SILU)
+    return ops.gemm(h, w2, bias=b2)
+
+
+def time_embedding(unet, timesteps, fps=None):
+    """-> silu(emb) [B, 4*C0] bf16, the only form the ResnetBlocks consume (resnet.py:231)."""
+    emb = _mlp(unet.time_proj(timesteps).to(BF16), unet.time_embedding)
+    if fps is not None:
+        emb = emb + _mlp(unet.time_proj(fps).to(BF16), unet.fps_embedding)
+    return F.silu(emb)
+
+
+def all_temb_projections(unet, silu_emb):
+    """time_emb_proj of every ResnetBlock3D of a UNet in ONE GEMM (they share the input); returns
+    {resnet module: fp32 [B, Cout]} ready to be added per image inside the conv epilogue."""
+    resnets = [m for m in unet.modules() if m.__class__.__name__ == "ResnetBlock3D"]
+
+    def build():
+        w = torch.cat([r.time_emb_proj.weight.to(BF16) for r in resnets], 0).contiguous()
+        b = torch.cat([r.time_emb_proj.bias.to(BF16) for r in resnets], 0).contiguous()
+        return w, b
+
+    params = [p for r in resnets for p in (r.time_emb_proj.weight, r.time_emb_proj.bias)]
+    w, b = cached(unet, "temb_all", params, build)
+    out = ops.gemm(silu_emb, w, bias=b).float()
+    res, o = {}, 0
+    for r in resnets:
+        n = r.out_channels
+        res[r] = out[:, o:o + n].contiguous()
+        o += n
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------
+# ResnetBlock3D (resnet.py:221-254), optionally on the pano circular halo (MVGenModel.py:276-281)
+# ------------------------------------------------------------------------------------------------------
+def resnet_block(x, r, temb, frames: int, groups: int, skip=None, halo: int = 0):
+    """x [N,H,W,C1] (+ skip [N,H,W,C2] = the torch.cat of the up path) -> [N,H,W,Cout].
+    halo > 0: pad_pano(halo) -> block -> unpad_pano(halo): the GroupNorm statistics are taken over the padded tensor
+    (norm2 even over conv1's zero-padded outer columns) exactly as the reference does."""
+    eps = r.norm1.eps
+    h = ops.groupnorm(x, r.norm1.weight, r.norm1.bias, groups, eps, True, x2=skip, pad=halo)
+    w1, b1 = conv_w(r.conv1)
+    h = ops.conv3x3(h, w1, bias=b1, rowvec=temb, rowvec_div=frames)
+    h = ops.groupnorm(h, r.norm2.weight, r.norm2.bias, groups, eps, True)
+    if r.conv_shortcut is not None:
+        w2, b2 = conv_w(r.conv2, shortcut=r.conv_shortcut)
+        return ops.conv3x3(h, w2, bias=b2, x2=x, x3=skip, crop=halo, out_scale=1.0 / r.output_scale_factor)
+    assert skip is None
+    w2, b2 = conv_w(r.conv2)
+    return ops.conv3x3(h, w2, bias=b2, resid=x, crop=halo, out_scale=1.0 / r.output_scale_factor)
+
+
+def downsample(x, d, circular: bool):
+    """Downsample3D (resnet.py:132-140); circular: pad_pano(2) -> conv -> unpad_pano(1) (MVGenModel.py:305-314)."""
+    n, h, w, c = x.shape
+    wp, b = conv_w(d.conv)
+    y = ops.gemm(ops.im2col_s2(x, circular), wp, bias=b)
+    return y.view(n, h // 2, w // 2, -1)
+
+
+def upsample(x, u, circular: bool):
+    """Upsample3D (resnet.py:86-114); circular: pad_pano(1) -> x2 -> conv -> unpad_pano(2) (MVGenModel.py:449-456)."""
+    wp, b = conv_w(u.conv)
+    if circular:
+        return ops.conv3x3(ops.upsample2x(x, pad_in=1), wp, bias=b, crop=2)
+    return ops.conv3x3(ops.upsample2x(x), wp, bias=b)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Transformer3DModel (attention.py:246-301) with BasicTransformerBlock (:461-508)
+# ------------------------------------------------------------------------------------------------------
+class Context:
+    """Cross-attention context of one branch for one step: text tokens (step-invariant) and image tokens
+    (re-noised every step).  K/V projections are computed once per batch element instead of once per frame
+    (the reference repeats the context ``f`` times, attention.py:257)."""
+
+    def __init__(self, text, ip):
+        self.text, self.ip = text.contiguous(), ip.contiguous()   # [Bc, 77, D], [Bc, n_ip, D]
+        self.n_ctx = text.shape[0]
+
+
+def spatial_transformer(x, t3d, ctx: Context, frames: int):
+    n, h, w, c = x.shape
+    heads, hd = t3d.heads, t3d.dim_head
+    npix = h * w
+    hn = ops.groupnorm(x, t3d.norm.weight, t3d.norm.bias, t3d.groups, 1e-6, False)
+    wi, bi = lin_w(t3d.proj_in)
+    t = ops.gemm(tokens(hn), wi, bias=bi)
+    for blk in t3d.transformer_blocks:
+        # --- attn1: fused QKV projection, flash attention reading q/k/v as column slices ---
+        a1 = blk.attn1
+        nrm = ops.layernorm(t, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
+        qkv = ops.gemm(nrm, fused_w(a1, "qkv", [a1.to_q, a1.to_k, a1.to_v]))
+        o = torch.empty_like(t)
+        ops.attention(ops.seq_view(qkv, n, npix, 0), ops.seq_view(qkv, n, npix, c), ops.seq_view(qkv, n, npix, 2 * c),
+                      ops.seq_view(o, n, npix), heads, hd, n)
+        wo, bo = lin_w(a1.to_out[0])
+        t = ops.gemm(o, wo, bias=bo, resid=t)
+        # --- attn2: text + image-prompt cross attention, outputs summed before to_out (attention.py:148) ---
+        a2 = blk.attn2
+        nrm = ops.layernorm(t, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
+        q = ops.gemm(nrm, lin_w(a2.to_q)[0])
+        nt, ni = ctx.text.shape[1], ctx.ip.shape[1]
+        kv_t = ops.gemm(ctx.text.view(-1, ctx.text.shape[-1]), fused_w(a2, "kv", [a2.to_k, a2.to_v]))
+        ip = ctx.ip[..., : a2.image_cross_attention_dim] if a2.image_cross_attention_dim != a2.cross_attention_dim else ctx.ip
+        kv_i = ops.gemm(ip.reshape(-1, ip.shape[-1]), fused_w(a2, "kv_ip", [a2.to_k_ip, a2.to_v_ip]))
+        o = torch.empty_like(t)
+        qv, ov = ops.seq_view(q, n, npix), ops.seq_view(o, n, npix)
+        ops.attention(qv, ops.seq_view(kv_t, ctx.n_ctx, nt, 0, share_div=frames),
+                      ops.seq_view(kv_t, ctx.n_ctx, nt, c, share_div=frames), ov, heads, hd, n)
+        if a2.ip_scale != 1.0:
+            raise NotImplementedError("ip scale != 1.0")
+        ops.attention(qv, ops.seq_view(kv_i, ctx.n_ctx, ni, 0, share_div=frames),
+                      ops.seq_view(kv_i, ctx.n_ctx, ni, c, share_div=frames), ov, heads, hd, n, accumulate=True)
+        wo, bo = lin_w(a2.to_out[0])
+        t = ops.gemm(o, wo, bias=bo, resid=t)
+        # --- GEGLU feed-forward ---
+        t = feed_forward(t, blk.ff, blk.norm3)
+    wo, bo = lin_w(t3d.proj_out)
+    return ops.gemm(t, wo, bias=bo, resid=tokens(x)).view(n, h, w, c)
+
+
+def feed_forward(t, ff, norm):
+    nrm = ops.layernorm(t, norm.weight, norm.bias, norm.eps)
+    wg, bg = geglu_w(ff)
+    g = ops.gemm(nrm, wg, bias=bg, act=ops.ACT_GEGLU)
+    w2, b2 = lin_w(ff.net[2])
+    return ops.gemm(g, w2, bias=b2, resid=t)
+
+
+# ------------------------------------------------------------------------------------------------------
+# VanillaTemporalModule (motion_module.py:158-185, :247-259, :343-429)
+# ------------------------------------------------------------------------------------------------------
+def _pe_table(att, frames, dtype_like):
+    """pos_encoder.pe[:F] as fp32 values of the (bf16-cast) buffer the reference adds (motion_module.py:350)."""
+    pe = att.pos_encoder.pe
+    return cached(att, f"pe{frames}", [pe], lambda: pe[0, :frames].to(dtype_like).float().contiguous())
+
+
+def temporal_module(x, mm, frames: int):
+    tt = mm.temporal_transformer
+    n, h, w, c = x.shape
+    d = h * w
+    hn = ops.groupnorm(x, tt.norm.weight, tt.norm.bias, tt.groups, 1e-6, False)
+    wi, bi = lin_w(tt.proj_in)
+    t = ops.gemm(tokens(hn), wi, bias=bi)
+    for blk in tt.transformer_blocks:
+        for att, norm in zip(blk.attention_blocks, blk.norms):
+            nrm = ops.layernorm(t, norm.weight, norm.bias, norm.eps, post_add=_pe_table(att, frames, BF16), post_div=d,
+                                post_mod=frames)
+            qkv = ops.gemm(nrm, fused_w(att, "qkv", [att.to_q, att.to_k, att.to_v]))
+            o = torch.empty_like(t)
+            ops.temporal_attention(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], o, n // frames, frames, d, tt.heads, tt.dim_head)
+            wo, bo = lin_w(att.to_out[0])
+            t = ops.gemm(o, wo, bias=bo, resid=t)
+        t = feed_forward(t, blk.ff, blk.ff_norm)
+    wo, bo = lin_w(tt.proj_out)
+    return ops.gemm(t, wo, bias=bo, resid=tokens(x)).view(n, h, w, c)
+
+
+# ------------------------------------------------------------------------------------------------------
+# conv_in / conv_out
+# ------------------------------------------------------------------------------------------------------
+def conv_in(unet, latents, circular: bool):
+    """[b, 9, f, h, w] -> [(b f), h, w, C0]; pano: pad_pano(1) -> conv -> unpad_pano(1) (MVGenModel.py:136-143)."""
+    x = latents_to_nhwc(latents, 1 if circular else 0)
+    wp, b = conv_w(unet.conv_in, cin_pad=x.shape[-1])
+    return ops.conv3x3(x, wp, bias=b, crop=1 if circular else 0)
+
+
+def conv_out(unet, x, batch: int, circular: bool):
+    """GroupNorm -> SiLU -> conv_out; pano: the norm runs BEFORE pad_pano(1) (MVGenModel.py:472-478)."""
+    co = unet.conv_out.out_channels
+    h = ops.groupnorm(x, unet.conv_norm_out.weight, unet.conv_norm_out.bias, unet.groups, unet.conv_norm_out.eps, True,
+                      pad=1 if circular else 0, stats_pad=0)
+    wp, b = conv_w(unet.conv_out, cout_pad=pad8(co))
+    y = ops.conv3x3(h, wp, bias=b, crop=1 if circular else 0)
+    return nhwc_to_latents(y, batch, co)
+
+
+# ------------------------------------------------------------------------------------------------------
+# single-branch forward (unet.py:632-856) -- configs C1 / C2
+# ------------------------------------------------------------------------------------------------------
+def unet_single_forward(unet, sample, timestep, ctx_tokens, fps=None):
+    b, _, frames, _, _ = sample.shape
+    dev = sample.device
+    t = timestep.reshape(-1).to(dev).expand(b)
+    silu_emb = time_embedding(unet, t, None if fps is None else fps.reshape(-1).to(dev).expand(b))
+    temb = all_temb_projections(unet, silu_emb)
+    nt = ctx_tokens.shape[1] - unet.num_tokens
+    ctx = Context(ctx_tokens[:, :nt].to(BF16), ctx_tokens[:, nt:].to(BF16))
+    g = unet.groups
+    x = conv_in(unet, sample, False)
+    skips = [x]
+    for blk in unet.down_blocks:
+        for j, r in enumerate(blk.resnets):
+            x = resnet_block(x, r, temb[r], frames, g)
+            if blk.has_cross_attention:
+                x = spatial_transformer(x, blk.attentions[j], ctx, frames)
+            if blk.motion_modules[j] is not None:      # UNet3DConditionModel.forward runs them in every block
+                x = temporal_module(x, blk.motion_modules[j], frames)
+            skips.append(x)
+        if blk.downsamplers is not None:
+            x = downsample(x, blk.downsamplers[0], False)
+            skips.append(x)
+    mid = unet.mid_block
+    x = resnet_block(x, mid.resnets[0], temb[mid.resnets[0]], frames, g)
+    for i, att in enumerate(mid.attentions):
+        x = spatial_transformer(x, att, ctx, frames)
+        if mid.motion_modules[i] is not None:
+            x = temporal_module(x, mid.motion_modules[i], frames)
+        x = resnet_block(x, mid.resnets[i + 1], temb[mid.resnets[i + 1]], frames, g)
+    for blk in unet.up_blocks:
+        for j, r in enumerate(blk.resnets):
+            x = resnet_block(x, r, temb[r], frames, g, skip=skips.pop())
+            if blk.has_cross_attention:
+                x = spatial_transformer(x, blk.attentions[j], ctx, frames)
+            if blk.motion_modules[j] is not None:
+                x = temporal_module(x, blk.motion_modules[j], frames)
+        if blk.upsamplers is not None:
+            x = upsample(x, blk.upsamplers[0], False)
+    return conv_out(unet, x, b, False)

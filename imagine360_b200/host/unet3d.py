@@ -1,0 +1,515 @@
+"""Host-side mirror of ``animatediff.models.unet.UNet3DConditionModel`` and its blocks.
+
+Same class names, constructor kwargs, sub-module names and parameter shapes as the reference
+(animatediff/models/{unet,unet_blocks,resnet,attention,motion_module,resampler}.py), so checkpoints load with the
+reference's own ``load_state_dict(strict=False)`` / LoRA-merge code (inference_dual_p2e.py:175-250), but the
+modules are only parameter containers: the math runs in the sm_100a kernels of ``libimagine360_b200.so``
+through :mod:`imagine360_b200.ops`, on channels-last bf16 activations ``[images, H, W, C]`` whose flattened rows
+``(b, f, h, w)`` are at once the conv layout and the reference's token layout ``(b f) (h w) c``.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+
+BF16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------------
+# packed-weight cache: derived tensors (fused QKV, tap-major conv weights, GEGLU tiles) are rebuilt only when
+# the source parameters change (load_state_dict / LoRA merge bump Tensor._version or replace storage).
+# ------------------------------------------------------------------------------------------------------
+def _sig(params):
+    return tuple((p.data_ptr(), p._version, p.dtype, p.device) for p in params if p is not None)
+
+
+def cached(mod: nn.Module, key: str, params, build):
+    store = mod.__dict__.setdefault("_i360_cache", {})
+    sig = _sig(params)
+    hit = store.get(key)
+    if hit is None or hit[0] != sig:
+        with torch.no_grad():
+            val = build()
+        store[key] = (sig, val)
+        return val
+    return hit[1]
+
+
+def _b(t):
+    return None if t is None else t.to(BF16)
+
+
+def lin_w(m: nn.Linear):
+    return cached(m, "w", [m.weight, m.bias], lambda: (m.weight.to(BF16).contiguous(), _b(m.bias)))
+
+
+def fused_w(owner: nn.Module, key: str, mods):
+    """Concatenate several bias-free projections sharing their input into one [sum N, K] weight."""
+    return cached(owner, key, [m.weight for m in mods], lambda: torch.cat([m.weight.to(BF16) for m in mods], 0).contiguous())
+
+
+def geglu_w(ff):
+    proj = ff.net[0].proj
+    return cached(ff, "geglu", [proj.weight, proj.bias], lambda: ops.pack_geglu(proj.weight.to(BF16), _b(proj.bias)))
+
+
+def pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def conv_w(conv: nn.Conv2d, shortcut: nn.Conv2d | None = None, cin_pad: int | None = None, cout_pad: int | None = None):
+    """Tap-major packed 3x3 weight [(Cout), 9*Cin (+ shortcut Cin)] and the summed bias."""
+    def build():
+        w = conv.weight.to(BF16)
+        b = conv.bias.to(torch.float32) if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+        if cin_pad is not None and cin_pad != w.shape[1]:
+            w = F.pad(w, (0, 0, 0, 0, 0, cin_pad - w.shape[1]))
+        extra = []
+        if shortcut is not None:
+            extra.append(shortcut.weight.to(BF16))
+            b = b + shortcut.bias.to(torch.float32)
+        wp = ops.pack_conv3x3(w, *extra)
+        if cout_pad is not None and cout_pad != wp.shape[0]:
+            wp = F.pad(wp, (0, 0, 0, cout_pad - wp.shape[0])).contiguous()
+            b = F.pad(b, (0, cout_pad - b.shape[0]))
+        return wp, b.to(BF16)
+    params = [conv.weight, conv.bias] + ([shortcut.weight, shortcut.bias] if shortcut is not None else [])
+    return cached(conv, f"w{cin_pad}_{cout_pad}", params, build)
+
+
+# ------------------------------------------------------------------------------------------------------
+# parameter containers (names == reference)
+# ------------------------------------------------------------------------------------------------------
+class InflatedConv3d(nn.Conv2d):
+    """resnet.py:19-27"""
+
+
+class InflatedGroupNorm(nn.GroupNorm):
+    """resnet.py:9-17"""
+
+
+class TimestepEmbedding(nn.Module):
+    """diffusers/models/embeddings.py:190-236"""
+
+    def __init__(self, in_channels, time_embed_dim, out_dim=None):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_channels, time_embed_dim)
+        self.linear_2 = nn.Linear(time_embed_dim, out_dim or time_embed_dim)
+
+
+class Timesteps(nn.Module):
+    """diffusers/models/embeddings.py:238-252 (no parameters)"""
+
+    def __init__(self, num_channels, flip_sin_to_cos=True, downscale_freq_shift=0):
+        super().__init__()
+        self.num_channels, self.flip_sin_to_cos, self.downscale_freq_shift = num_channels, flip_sin_to_cos, downscale_freq_shift
+
+    def forward(self, timesteps):
+        half = self.num_channels // 2
+        exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32, device=timesteps.device)
+        exponent = exponent / (half - self.downscale_freq_shift)
+        emb = timesteps[:, None].float() * torch.exp(exponent)[None, :]
+        emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
+        if self.flip_sin_to_cos:
+            emb = torch.cat([emb[:, half:], emb[:, :half]], dim=-1)
+        return emb
+
+
+class ResnetBlock3D(nn.Module):
+    """resnet.py:143-254"""
+
+    def __init__(self, *, in_channels, out_channels=None, temb_channels=512, groups=32, eps=1e-6, output_scale_factor=1.0,
+                 use_inflated_groupnorm=True, **_):
+        super().__init__()
+        out_channels = out_channels or in_channels
+        self.in_channels, self.out_channels, self.output_scale_factor = in_channels, out_channels, output_scale_factor
+        gn = InflatedGroupNorm if use_inflated_groupnorm else nn.GroupNorm
+        self.norm1 = gn(groups, in_channels, eps=eps, affine=True)
+        self.conv1 = InflatedConv3d(in_channels, out_channels, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels) if temb_channels is not None else None
+        self.norm2 = gn(groups, out_channels, eps=eps, affine=True)
+        self.conv2 = InflatedConv3d(out_channels, out_channels, 3, padding=1)
+        self.conv_shortcut = InflatedConv3d(in_channels, out_channels, 1) if in_channels != out_channels else None
+
+
+class Downsample3D(nn.Module):
+    def __init__(self, channels, out_channels=None, **_):
+        super().__init__()
+        self.channels, self.out_channels = channels, out_channels or channels
+        self.conv = InflatedConv3d(channels, self.out_channels, 3, stride=2, padding=1)
+
+
+class Upsample3D(nn.Module):
+    def __init__(self, channels, out_channels=None, **_):
+        super().__init__()
+        self.channels, self.out_channels = channels, out_channels or channels
+        self.conv = InflatedConv3d(channels, self.out_channels, 3, padding=1)
+
+
+def _to_out(inner, dim):
+    return nn.ModuleList([nn.Linear(inner, dim), nn.Dropout(0.0)])
+
+
+class Attention(nn.Module):
+    """diffusers Attention / legacy CrossAttention parameter layout (attention_processor.py:38-200)."""
+
+    def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=64, bias=False):
+        super().__init__()
+        inner = heads * dim_head
+        kv = cross_attention_dim or query_dim
+        self.heads, self.dim_head, self.scale = heads, dim_head, dim_head ** -0.5
+        self.to_q = nn.Linear(query_dim, inner, bias=bias)
+        self.to_k = nn.Linear(kv, inner, bias=bias)
+        self.to_v = nn.Linear(kv, inner, bias=bias)
+        self.to_out = _to_out(inner, query_dim)
+
+
+class IPCrossAttention(Attention):
+    """animatediff/models/attention.py:23-63.  NB: the reference overwrites ``self.scale`` with the IP scale (1.0);
+    the production (xformers) path still applies the 1/sqrt(d) softmax scale, which is what runs here."""
+
+    def __init__(self, query_dim, cross_attention_dim, image_cross_attention_dim, heads, dim_head, scale=1.0, num_tokens=4):
+        super().__init__(query_dim, cross_attention_dim, heads, dim_head)
+        self.ip_scale, self.num_tokens = scale, num_tokens
+        self.image_cross_attention_dim, self.cross_attention_dim = image_cross_attention_dim, cross_attention_dim
+        self.to_k_ip = nn.Linear(image_cross_attention_dim or query_dim, query_dim, bias=False)
+        self.to_v_ip = nn.Linear(image_cross_attention_dim or query_dim, query_dim, bias=False)
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+
+class FeedForward(nn.Module):
+    """diffusers/models/attention_lora.py:493-547 (geglu)"""
+
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
+
+
+class BasicTransformerBlock(nn.Module):
+    """animatediff/models/attention.py:323-508"""
+
+    def __init__(self, dim, heads, dim_head, cross_attention_dim, image_cross_attention_dim, scale, num_tokens):
+        super().__init__()
+        self.attn1 = Attention(dim, None, heads, dim_head)
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn2 = IPCrossAttention(dim, cross_attention_dim, image_cross_attention_dim, heads, dim_head, scale, num_tokens)
+        self.norm2 = nn.LayerNorm(dim)
+        self.ff = FeedForward(dim)
+        self.norm3 = nn.LayerNorm(dim)
+
+
+class Transformer3DModel(nn.Module):
+    """animatediff/models/attention.py:170-301 (use_linear_projection=True)"""
+
+    def __init__(self, heads, dim_head, in_channels, cross_attention_dim, norm_num_groups, image_cross_attention_dim, scale,
+                 num_tokens):
+        super().__init__()
+        inner = heads * dim_head
+        self.heads, self.dim_head, self.groups = heads, dim_head, norm_num_groups
+        self.norm = nn.GroupNorm(norm_num_groups, in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Linear(in_channels, inner)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(inner, heads, dim_head, cross_attention_dim,
+                                                                       image_cross_attention_dim, scale, num_tokens)])
+        self.proj_out = nn.Linear(in_channels, inner)
+
+
+class PositionalEncoding(nn.Module):
+    """motion_module.py:262-280"""
+
+    def __init__(self, d_model, max_len=24):
+        super().__init__()
+        position = torch.arange(max_len).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+        pe = torch.zeros(1, max_len, d_model)
+        pe[0, :, 0::2] = torch.sin(position * div_term)
+        pe[0, :, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe)
+
+
+class VersatileAttention(Attention):
+    """motion_module.py:304-341"""
+
+    def __init__(self, query_dim, heads, dim_head, max_len):
+        super().__init__(query_dim, None, heads, dim_head)
+        self.pos_encoder = PositionalEncoding(query_dim, max_len)
+
+
+class TemporalTransformerBlock(nn.Module):
+    def __init__(self, dim, heads, dim_head, n_attn, max_len):
+        super().__init__()
+        self.attention_blocks = nn.ModuleList([VersatileAttention(dim, heads, dim_head, max_len) for _ in range(n_attn)])
+        self.norms = nn.ModuleList([nn.LayerNorm(dim) for _ in range(n_attn)])
+        self.ff = FeedForward(dim)
+        self.ff_norm = nn.LayerNorm(dim)
+
+
+class TemporalTransformer3DModel(nn.Module):
+    """motion_module.py:99-185"""
+
+    def __init__(self, in_channels, heads, dim_head, num_layers, n_attn, max_len, norm_num_groups=32):
+        super().__init__()
+        inner = heads * dim_head
+        self.heads, self.dim_head, self.groups = heads, dim_head, norm_num_groups
+        self.norm = nn.GroupNorm(norm_num_groups, in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Linear(in_channels, inner)
+        self.transformer_blocks = nn.ModuleList([TemporalTransformerBlock(inner, heads, dim_head, n_attn, max_len)
+                                                 for _ in range(num_layers)])
+        self.proj_out = nn.Linear(in_channels, inner)
+
+
+class VanillaTemporalModule(nn.Module):
+    """motion_module.py:52-97"""
+
+    def __init__(self, in_channels, num_attention_heads=8, num_transformer_block=2,
+                 attention_block_types=("Temporal_Self", "Temporal_Self"), temporal_position_encoding=False,
+                 temporal_position_encoding_max_len=24, temporal_attention_dim_div=1, zero_initialize=True, **_):
+        super().__init__()
+        self.temporal_transformer = TemporalTransformer3DModel(
+            in_channels, num_attention_heads, in_channels // num_attention_heads // temporal_attention_dim_div,
+            num_transformer_block, len(attention_block_types), temporal_position_encoding_max_len)
+        if zero_initialize:
+            nn.init.zeros_(self.temporal_transformer.proj_out.weight)
+            nn.init.zeros_(self.temporal_transformer.proj_out.bias)
+
+
+class PerceiverAttention(nn.Module):
+    """resampler.py:36-80"""
+
+    def __init__(self, dim, dim_head=64, heads=8):
+        super().__init__()
+        self.dim_head, self.heads = dim_head, heads
+        inner = dim_head * heads
+        self.norm1, self.norm2 = nn.LayerNorm(dim), nn.LayerNorm(dim)
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_kv = nn.Linear(dim, inner * 2, bias=False)
+        self.to_out = nn.Linear(inner, dim, bias=False)
+
+
+def _plain_ff(dim, mult=4):
+    return nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, dim * mult, bias=False), nn.GELU(), nn.Linear(dim * mult, dim, bias=False))
+
+
+class Resampler(nn.Module):
+    """resampler.py:83-160"""
+
+    def __init__(self, dim=1024, depth=8, dim_head=64, heads=16, num_queries=8, embedding_dim=768, output_dim=1024, ff_mult=4, **_):
+        super().__init__()
+        self.latents = nn.Parameter(torch.randn(1, num_queries, dim) / dim ** 0.5)
+        self.proj_in = nn.Linear(embedding_dim, dim)
+        self.proj_out = nn.Linear(dim, output_dim)
+        self.norm_out = nn.LayerNorm(output_dim)
+        self.layers = nn.ModuleList([nn.ModuleList([PerceiverAttention(dim, dim_head, heads), _plain_ff(dim, ff_mult)])
+                                     for _ in range(depth)])
+
+
+class TemporalProjection(nn.Module):
+    """resampler.py:194-267"""
+
+    def __init__(self, *, dim, dim_head=64, heads=8, compress_video_features=False, kernel_size=4):
+        super().__init__()
+        self.spacial_compress = dim < 1024
+        d = dim * 4 if self.spacial_compress else dim
+        if self.spacial_compress:
+            self.patch_embed = nn.Conv2d(dim, dim * 4, kernel_size=4, stride=4, bias=True)
+        self.attn_temp = Attention(d, None, heads, dim_head)
+        self.norm_temp = nn.LayerNorm(d)
+        self.ff = _plain_ff(d)
+        self.norm1 = nn.LayerNorm(d)
+        self.compress_video_features = compress_video_features
+        if compress_video_features:
+            self.attn_temp_2 = Attention(d, None, heads, dim_head)
+            self.norm_temp_2 = nn.LayerNorm(d)
+            self.ff_2 = _plain_ff(d)
+            self.norm2 = nn.LayerNorm(d)
+
+
+class _Block(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.resnets = nn.ModuleList()
+        self.attentions = None
+        self.motion_modules = nn.ModuleList()
+        self.downsamplers = None
+        self.upsamplers = None
+
+
+# ------------------------------------------------------------------------------------------------------
+# UNet3DConditionModel
+# ------------------------------------------------------------------------------------------------------
+class UNet3DConditionModel(nn.Module):
+    """animatediff/models/unet.py:57-358.  Constructor kwargs are the reference's (SD-2.1 ``unet/config.json`` merged
+    with ``unet_additional_kwargs`` of configs/prompt-dual.yaml:16-45); unknown kwargs are kept in ``config``."""
+
+    def __init__(self, sample_size=None, in_channels=4, out_channels=4, flip_sin_to_cos=True, freq_shift=0,
+                 down_block_types=("CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "DownBlock3D"),
+                 up_block_types=("UpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D"),
+                 block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, norm_num_groups=32, norm_eps=1e-5,
+                 cross_attention_dim=1280, attention_head_dim=8, use_motion_module=False,
+                 motion_module_resolutions=(1, 2, 4, 8), motion_module_mid_block=False, motion_module_kwargs=None,
+                 image_hidden_size=1280, use_ip_plus_cross_attention=False, scale=1.0, num_tokens=4,
+                 use_inflated_groupnorm=False, use_fps_condition=False, use_outpaint=False, use_relative_postions=False,
+                 adapter_cross_attention_dim=1024, image_cross_attention_dim=1024, ip_plus_condition="image",
+                 use_adapter_temporal_projection=False, compress_video_features=False, **extra):
+        super().__init__()
+        self.config = SimpleNamespace(**{k: v for k, v in locals().items() if k not in ("self", "extra", "__class__")}, **extra)
+        mm_kwargs = dict(motion_module_kwargs or {})
+        c0 = block_out_channels[0]
+        time_dim = c0 * 4
+        self.use_relative_postions = use_relative_postions
+        self.image_cross_attention_dim = image_cross_attention_dim
+        self.ip_plus_condition = ip_plus_condition
+        self.num_tokens, self.groups, self.eps = num_tokens, norm_num_groups, norm_eps
+        if isinstance(attention_head_dim, int):
+            attention_head_dim = (attention_head_dim,) * len(down_block_types)
+        self.head_counts = tuple(attention_head_dim)
+        self.conv_in = InflatedConv3d(in_channels * 2 + 1 if use_outpaint else in_channels, c0, 3, padding=1)
+        self.time_proj = Timesteps(c0, flip_sin_to_cos, freq_shift)
+        self.time_embedding = TimestepEmbedding(c0, time_dim)
+        if use_relative_postions == "WithAdapter":
+            self.add_cond_proj = Timesteps(c0, flip_sin_to_cos, freq_shift)
+            self.add_cond_embedding = TimestepEmbedding(c0 * 6, image_cross_attention_dim)
+            self.cond_rp_proj = nn.Linear(image_cross_attention_dim, image_cross_attention_dim // 4 * 3, bias=False)
+            self.add_cond_embedding2 = TimestepEmbedding(c0, image_cross_attention_dim // 4)
+        elif use_relative_postions:
+            raise NotImplementedError("only use_relative_postions='WithAdapter' is on the Imagine360 path")
+        if use_fps_condition:
+            self.fps_embedding = TimestepEmbedding(c0, time_dim)
+            nn.init.zeros_(self.fps_embedding.linear_2.weight)
+            nn.init.zeros_(self.fps_embedding.linear_2.bias)
+        if use_ip_plus_cross_attention:
+            if ip_plus_condition == "video" and use_adapter_temporal_projection:
+                self.temporal_proj = TemporalProjection(dim=image_hidden_size, dim_head=64, heads=8,
+                                                        compress_video_features=compress_video_features)
+                emb_dim = image_hidden_size * 4 if self.temporal_proj.spacial_compress else image_hidden_size
+            else:
+                raise NotImplementedError("the Imagine360 path uses ip_plus_condition='video' with the temporal projection")
+            self.image_proj_model = Resampler(dim=adapter_cross_attention_dim, depth=4, dim_head=64, heads=12,
+                                              num_queries=num_tokens, embedding_dim=emb_dim,
+                                              output_dim=image_cross_attention_dim, ff_mult=4)
+
+        def transformer(ch, heads):
+            return Transformer3DModel(heads, ch // heads, ch, cross_attention_dim, norm_num_groups, image_cross_attention_dim,
+                                      scale, num_tokens)
+
+        def resnet(cin, cout):
+            return ResnetBlock3D(in_channels=cin, out_channels=cout, temb_channels=time_dim, groups=norm_num_groups,
+                                 eps=norm_eps, use_inflated_groupnorm=use_inflated_groupnorm)
+
+        def motion(ch, on):
+            return VanillaTemporalModule(in_channels=ch, **mm_kwargs) if on else None
+
+        self.down_blocks = nn.ModuleList()
+        out_ch = c0
+        for i, btype in enumerate(down_block_types):
+            in_ch, out_ch = out_ch, block_out_channels[i]
+            blk = _Block()
+            blk.has_cross_attention = btype.startswith("CrossAttn")
+            mm_on = use_motion_module and (2 ** i in motion_module_resolutions)
+            if blk.has_cross_attention:
+                blk.attentions = nn.ModuleList()
+            for j in range(layers_per_block):
+                blk.resnets.append(resnet(in_ch if j == 0 else out_ch, out_ch))
+                if blk.has_cross_attention:
+                    blk.attentions.append(transformer(out_ch, attention_head_dim[i]))
+                blk.motion_modules.append(motion(out_ch, mm_on))
+            if i != len(block_out_channels) - 1:
+                blk.downsamplers = nn.ModuleList([Downsample3D(out_ch, out_ch)])
+            self.down_blocks.append(blk)
+
+        mid = _Block()
+        mid.has_cross_attention = True
+        ch = block_out_channels[-1]
+        mid.resnets.append(resnet(ch, ch))
+        mid.attentions = nn.ModuleList([transformer(ch, attention_head_dim[-1])])
+        mid.motion_modules.append(motion(ch, use_motion_module and motion_module_mid_block))
+        mid.resnets.append(resnet(ch, ch))
+        self.mid_block = mid
+
+        self.up_blocks = nn.ModuleList()
+        rev = list(reversed(block_out_channels))
+        rev_heads = list(reversed(attention_head_dim))
+        out_ch = rev[0]
+        for i, btype in enumerate(up_block_types):
+            prev_out, out_ch = out_ch, rev[i]
+            in_ch = rev[min(i + 1, len(block_out_channels) - 1)]
+            blk = _Block()
+            blk.has_cross_attention = btype.startswith("CrossAttn")
+            mm_on = use_motion_module and (2 ** (3 - i) in motion_module_resolutions)
+            if blk.has_cross_attention:
+                blk.attentions = nn.ModuleList()
+            n = layers_per_block + 1
+            for j in range(n):
+                skip = in_ch if j == n - 1 else out_ch
+                rin = prev_out if j == 0 else out_ch
+                blk.resnets.append(resnet(rin + skip, out_ch))
+                if blk.has_cross_attention:
+                    blk.attentions.append(transformer(out_ch, rev_heads[i]))
+                blk.motion_modules.append(motion(out_ch, mm_on))
+            if i != len(block_out_channels) - 1:
+                blk.upsamplers = nn.ModuleList([Upsample3D(out_ch, out_ch)])
+            self.up_blocks.append(blk)
+
+        gn = InflatedGroupNorm if use_inflated_groupnorm else nn.GroupNorm
+        self.conv_norm_out = gn(norm_num_groups, c0, eps=norm_eps)
+        self.conv_act = nn.SiLU()
+        self.conv_out = InflatedConv3d(c0, out_channels, 3, padding=1)
+
+    # -- reference API surface (unet.py:859-909, modeling_utils.py) --------------------------------------
+    @property
+    def dtype(self):
+        return self.conv_in.weight.dtype
+
+    @property
+    def device(self):
+        return self.conv_in.weight.device
+
+    def enable_xformers_memory_efficient_attention(self, *_, **__):
+        return None  # attention always runs in the fused tcgen05 kernel
+
+    @classmethod
+    def from_pretrained_2d(cls, pretrained_model_path, subfolder=None, unet_additional_kwargs=None):
+        path = os.path.join(pretrained_model_path, subfolder) if subfolder else pretrained_model_path
+        with open(os.path.join(path, "config.json")) as f:
+            config = json.load(f)
+        config = {k: v for k, v in config.items() if not k.startswith("_")}
+        config["down_block_types"] = ["CrossAttnDownBlock3D"] * 3 + ["DownBlock3D"]
+        config["up_block_types"] = ["UpBlock3D"] + ["CrossAttnUpBlock3D"] * 3
+        model = cls(**config, **(unet_additional_kwargs or {}))
+        for name in ("diffusion_pytorch_model.bin", "diffusion_pytorch_model.safetensors"):
+            wpath = os.path.join(path, name)
+            if os.path.isfile(wpath):
+                if name.endswith(".bin"):
+                    sd = torch.load(wpath, map_location="cpu")
+                else:
+                    from safetensors.torch import load_file
+                    sd = load_file(wpath)
+                w = sd.get("conv_in.weight")
+                if w is not None and w.shape[1] != model.conv_in.weight.shape[1]:   # unet.py:895-900: zero-extend 4 -> 9
+                    ext = torch.zeros_like(model.conv_in.weight)
+                    ext[:, : w.shape[1]] = w
+                    sd["conv_in.weight"] = ext
+                model.load_state_dict(sd, strict=False)
+                break
+        return model
+
+    def forward(self, sample, timestep, encoder_hidden_states, use_fps_condition=False, fps_tensor=None, **kwargs):
+        """Single-branch forward (unet.py:632-856) with ``encoder_hidden_states`` already holding text + image tokens
+        (``use_ip_plus_cross_attention=False`` path; configs C1/C2)."""
+        if kwargs.get("use_ip_plus_cross_attention"):
+            raise NotImplementedError("single-branch forward with in-graph adapter: use MultiViewBaseModel")
+        from . import forward as Fw
+        return SimpleNamespace(sample=Fw.unet_single_forward(self, sample, timestep, encoder_hidden_states,
+                                                             fps_tensor if use_fps_condition else None))

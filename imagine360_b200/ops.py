@@ -97,8 +97,8 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias=None, x2=None, x3=None
             rowvec=None, rowvec_div: int = 1, crop: int = 0, out_scale: float = 1.0) -> torch.Tensor:
     """3x3 / stride 1 / zero-pad 1 convolution on NHWC ``x`` [B, H, W, Cin] -> [B, H, W-2*crop, Cout].
 
-    ``x2``/``x3`` are optional NHWC sources of a fused 1x1 convolution whose weights are the trailing
-    columns of ``w_packed``; ``rowvec`` [B // rowvec_div, Cout] fp32 is added per image (temb)."""
+    ``x2``/``x3`` are optional NHWC sources [B, H, W-2*crop, C] (no halo) of a fused 1x1 convolution whose
+    weights are the trailing columns of ``w_packed``; ``rowvec`` [B // rowvec_div, Cout] fp32 is added per image (temb)."""
     _chk_bf16(x, w_packed, bias, x2, x3, resid)
     assert x.dim() == 4 and x.is_contiguous()
     B, H, W, Cin = x.shape

@@ -123,16 +123,19 @@ def _cam(cameras, key, i):
 
 
 def remap(img, map_x, map_y, mode):
-    """kornia.geometry.transform.remap(align_corners=True) restated; maps are already in img.dtype."""
+    """kornia.geometry.transform.remap(align_corners=True) restated; the maps arrive in the dtype the reference cast
+    them to (the image dtype -- bf16 in production) and are normalised in that dtype."""
     h, w = img.shape[-2:]
     gx = 2.0 * map_x / (w - 1) - 1.0
     gy = 2.0 * map_y / (h - 1) - 1.0
-    grid = torch.stack([gx, gy], dim=-1).to(img.dtype)
+    grid = torch.stack([gx, gy], dim=-1).to(img.dtype)   # gx/gy were computed in the maps' dtype
     return F.grid_sample(img, grid, mode=mode, padding_mode="zeros", align_corners=True)
 
 
-def e2p(e_img, cameras, out_hw, mode="bilinear"):
-    """e2p for tensors (e2p.py:54-77).  e_img: [m, c, he, we], one camera per batch item."""
+def e2p(e_img, cameras, out_hw, mode="bilinear", grid_dtype=None):
+    """e2p for tensors (e2p.py:54-77).  e_img: [m, c, he, we], one camera per batch item.
+    ``grid_dtype`` (default: the image dtype, as in the reference) lets an fp32 evaluation keep the production
+    path's bf16 quantisation of the sampling grid."""
     m, c, he, we = e_img.shape
     lons, lats = [], []
     for i in range(m):
@@ -140,12 +143,13 @@ def e2p(e_img, cameras, out_hw, mode="bilinear"):
                                     out_hw[0], out_hw[1])
         lons.append(lon)
         lats.append(lat)
-    lons = torch.from_numpy(np.stack(lons)).to(e_img.device).type(e_img.dtype)
-    lats = torch.from_numpy(np.stack(lats)).to(e_img.device).type(e_img.dtype)
+    gd = grid_dtype or e_img.dtype
+    lons = torch.from_numpy(np.stack(lons)).to(e_img.device).type(gd)
+    lats = torch.from_numpy(np.stack(lats)).to(e_img.device).type(gd)
     return remap(e_img, lons, lats, mode)
 
 
-def p2e(p_img, cameras, out_hw, mode="bilinear", theta_offset=0.0):
+def p2e(p_img, cameras, out_hw, mode="bilinear", theta_offset=0.0, grid_dtype=None):
     """p2e for tensors (p2e.py:52-71). Returns (equi, mask)."""
     m, c, hp, wp = p_img.shape
     lons, lats, masks = [], [], []
@@ -155,8 +159,9 @@ def p2e(p_img, cameras, out_hw, mode="bilinear", theta_offset=0.0):
         lons.append(lon)
         lats.append(lat)
         masks.append(mask[None])
-    lons = torch.from_numpy(np.stack(lons)).to(p_img.device).type(p_img.dtype)
-    lats = torch.from_numpy(np.stack(lats)).to(p_img.device).type(p_img.dtype)
+    gd = grid_dtype or p_img.dtype
+    lons = torch.from_numpy(np.stack(lons)).to(p_img.device).type(gd)
+    lats = torch.from_numpy(np.stack(lats)).to(p_img.device).type(gd)
     mask = torch.from_numpy(np.stack(masks)).to(p_img.device)
     return remap(p_img, lons, lats, mode) * mask, mask
 
@@ -202,14 +207,14 @@ def _one_hot_images(m, h, w, dtype, device, shift_w=0):
     return px
 
 
-def raw_masks(ph, pw, eh, ew, cameras, device, dtype, antipodal: bool):
+def raw_masks(ph, pw, eh, ew, cameras, device, dtype, antipodal: bool, grid_dtype=None):
     """get_masks (utils.py:43-89) / get_oppo_masks (:91-142) before blur/normalisation.
     pers_masks [m, eh, ew, ph, pw], equi_masks [m, ph, pw, eh, ew]."""
     m = len(cameras["FoV"])
     pers_px = _one_hot_images(m, ph, pw, dtype, device)
     equi_px = _one_hot_images(m, eh, ew, dtype, device, shift_w=ew // 2 if antipodal else 0)
-    pers_masks = e2p(equi_px, cameras, (ph, pw))
-    equi_masks = p2e(pers_px, cameras, (eh, ew), theta_offset=180.0 if antipodal else 0.0)[0]
+    pers_masks = e2p(equi_px, cameras, (ph, pw), grid_dtype=grid_dtype)
+    equi_masks = p2e(pers_px, cameras, (eh, ew), theta_offset=180.0 if antipodal else 0.0, grid_dtype=grid_dtype)[0]
     pers_masks = pers_masks.reshape(m, eh, ew, ph, pw)
     equi_masks = equi_masks.reshape(m, ph, pw, eh, ew)
     # "fix missing pixels": add the transposed other-direction correspondences, clamp to [0,1]
@@ -227,10 +232,10 @@ def raw_masks(ph, pw, eh, ew, cameras, device, dtype, antipodal: bool):
     return pers_masks, equi_masks
 
 
-def merged_masks(ph, pw, eh, ew, cameras, device, dtype, antipodal: bool):
+def merged_masks(ph, pw, eh, ew, cameras, device, dtype, antipodal: bool, grid_dtype=None):
     """get_merged_masks (utils.py:12-41) for one variant.  The reference computes BOTH variants and picks
     the antipodal one when random.random() < 0.4 (:15-21); the caller owns that draw."""
-    pers_masks, equi_masks = raw_masks(ph, pw, eh, ew, cameras, device, dtype, antipodal)
+    pers_masks, equi_masks = raw_masks(ph, pw, eh, ew, cameras, device, dtype, antipodal, grid_dtype)
     m = pers_masks.shape[0]
     pm = _gaussian_blur5(pers_masks.reshape(m * eh * ew, 1, ph, pw), circular=False)
     em = _gaussian_blur5(equi_masks.reshape(m * ph * pw, 1, eh, ew), circular=True)

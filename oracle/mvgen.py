@@ -35,21 +35,27 @@ def warp_transformer(x, context, mask, query_pe, p: P):
     return linear(val * F.gelu(gate), fp, "net.2") + x
 
 
-def warp_attn(pers_x, equi_x, cameras, p: P, antipodal: bool, mask_dtype=None):
+def warp_attn(pers_x, equi_x, cameras, p: P, antipodal: bool, mask_dtype=None, grid_dtype=None, pe_dtype=None):
     """WarpAttn.forward (attn_perspano.py:22-99).  pers_x [(b m), c, f, ph, pw], equi_x [b, c, f, eh, ew].
-    ``antipodal`` is the outcome of the reference's ``random.random() < 0.4`` draw (utils.py:15-21)."""
+    ``antipodal`` is the outcome of the reference's ``random.random() < 0.4`` draw (utils.py:15-21).
+    ``grid_dtype`` / ``pe_dtype``: dtype in which the sampling grids and the spherical PE are evaluated; the reference
+    uses the activation dtype for both (bf16 in production), which matters: the PE frequencies reach 2^79 and the
+    grids hold pixel coordinates, so an fp32 evaluation of the rest must still quantise these two like production."""
     bm, c, f, ph, pw = pers_x.shape
     b, _, _, eh, ew = equi_x.shape
     m = bm // b
     dt = pers_x.dtype
     mdt = mask_dtype or dt
-    pers_masks, equi_masks = G.merged_masks(ph, pw, eh, ew, cameras, pers_x.device, mdt, antipodal)
-    pers_coords, equi_coords = G.polar_coords(ph, pw, eh, ew, cameras, pers_x.device, dt)
+    pers_masks, equi_masks = G.merged_masks(ph, pw, eh, ew, cameras, pers_x.device, mdt, antipodal, grid_dtype)
+    if grid_dtype is not None:      # production rounds the finished bias to the activation dtype
+        pers_masks, equi_masks = pers_masks.to(grid_dtype).to(mdt), equi_masks.to(grid_dtype).to(mdt)
+    pdt = pe_dtype or dt
+    pers_coords, equi_coords = G.polar_coords(ph, pw, eh, ew, cameras, pers_x.device, pdt)
     fb = p.get("pe.freq_bands")
     if fb is None:
         fb = G.spherical_freqs(c // 4, pers_x.device)
-    pers_pe = G.spherical_pe(pers_coords, fb).to(dt)          # [m, ph, pw, c]
-    equi_pe = G.spherical_pe(equi_coords, fb).to(dt)          # [eh, ew, c]
+    pers_pe = G.spherical_pe(pers_coords, fb.to(pdt)).to(dt)   # [m, ph, pw, c]
+    equi_pe = G.spherical_pe(equi_coords, fb.to(pdt)).to(dt)   # [eh, ew, c]
 
     # tokens: equi '(b f) (h w) c', pers '(b f) (m h w) c'
     def equi_tokens(t):
@@ -109,7 +115,7 @@ def _pano_resnet(x, emb, p, cfg):
 
 def mv_forward(sd, latents, pano_latent, timestep, prompt_embd, pano_prompt_embd, cameras, fps_pano, fps_pers,
                feats_pano, feats_pers, rel_pos, pitch, antipodal_draws, ip_noise_pano, ip_noise_pers, cfg=None,
-               mask_dtype=None):
+               mask_dtype=None, grid_dtype=None, pe_dtype=None):
     """One dual-branch denoise step.
 
     latents [b, m, 9, f, h, w]; pano_latent [b, 9, f, H, W]; timestep [1] int64; prompt_embd [b*m, 77, D];
@@ -163,7 +169,7 @@ def mv_forward(sd, latents, pano_latent, timestep, prompt_embd, pano_prompt_embd
             y = G.unpad_pano(downsample(G.pad_pano(y, 2), bq.sub("downsamplers.0")), 1)
             xs.append(x)
             ys.append(y)
-            x, y = warp_attn(x, y, cameras, P(sd, f"cp_blocks_encoder.{i}."), draws.pop(0), mask_dtype)
+            x, y = warp_attn(x, y, cameras, P(sd, f"cp_blocks_encoder.{i}."), draws.pop(0), mask_dtype, grid_dtype, pe_dtype)
 
     mp, mq = pp.sub("mid_block"), qp.sub("mid_block")
     x = resnet_block(x, emb, mp.sub("resnets.0"), cfg)
@@ -175,7 +181,7 @@ def mv_forward(sd, latents, pano_latent, timestep, prompt_embd, pano_prompt_embd
         y = spatial_transformer(y, pano_ctx, mq.sub(f"attentions.{i}"), heads[-1], cfg)
         y = temporal_module(y, mq.sub(f"motion_modules.{i}"), cfg)
         y = _pano_resnet(y, pano_emb, mq.sub(f"resnets.{i + 1}"), cfg)
-    x, y = warp_attn(x, y, cameras, P(sd, "cp_blocks_mid."), draws.pop(0), mask_dtype)
+    x, y = warp_attn(x, y, cameras, P(sd, "cp_blocks_mid."), draws.pop(0), mask_dtype, grid_dtype, pe_dtype)
 
     nu = qp.count("up_blocks")
     dec = 0
@@ -191,7 +197,7 @@ def mv_forward(sd, latents, pano_latent, timestep, prompt_embd, pano_prompt_embd
                 y = spatial_transformer(y, pano_ctx, bq.sub(f"attentions.{j}"), heads[nu - 1 - i], cfg)
                 y = temporal_module(y, bq.sub(f"motion_modules.{j}"), cfg)
         if bq.has_prefix("upsamplers"):
-            x, y = warp_attn(x, y, cameras, P(sd, f"cp_blocks_decoder.{dec}."), draws.pop(0), mask_dtype)
+            x, y = warp_attn(x, y, cameras, P(sd, f"cp_blocks_decoder.{dec}."), draws.pop(0), mask_dtype, grid_dtype, pe_dtype)
             dec += 1
             x = upsample(x, bp.sub("upsamplers.0"))
             y = G.unpad_pano(upsample(G.pad_pano(y, 1), bq.sub("upsamplers.0")), 2)

@@ -96,8 +96,8 @@ def test_conv3x3_fused_shortcut_temb_crop():
     g = torch.Generator(device="cuda").manual_seed(5)
     B, H, W, Cin, Cout, C2, C3, crop, F_ = 4, 16, 36, 128, 192, 64, 128, 2, 2
     x = torch.randn(B, H, W, Cin, device="cuda", generator=g).bfloat16()
-    x2 = torch.randn(B, H, W, C2, device="cuda", generator=g).bfloat16()
-    x3 = torch.randn(B, H, W, C3, device="cuda", generator=g).bfloat16()
+    x2 = torch.randn(B, H, W - 2 * crop, C2, device="cuda", generator=g).bfloat16()
+    x3 = torch.randn(B, H, W - 2 * crop, C3, device="cuda", generator=g).bfloat16()
     w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (9 * Cin) ** 0.5).bfloat16()
     ws = (torch.randn(Cout, C2 + C3, 1, 1, device="cuda", generator=g) / (C2 + C3) ** 0.5).bfloat16()
     bias = torch.randn(Cout, device="cuda", generator=g).bfloat16()
@@ -105,8 +105,8 @@ def test_conv3x3_fused_shortcut_temb_crop():
     resid = torch.randn(B, H, W - 2 * crop, Cout, device="cuda", generator=g).bfloat16()
     out = ops.conv3x3(x, ops.pack_conv3x3(w, ws), bias=bias, x2=x2, x3=x3, resid=resid, rowvec=temb,
                       rowvec_div=F_, crop=crop)
-    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias.float(), padding=1)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias.float(), padding=1)[..., crop:-crop]
     ref = ref + F.conv2d(torch.cat([x2, x3], -1).float().permute(0, 3, 1, 2), ws.float())
     ref = ref + temb.repeat_interleave(F_, 0)[:, :, None, None]
-    ref = ref.permute(0, 2, 3, 1)[:, :, crop:-crop] + resid.float()
+    ref = ref.permute(0, 2, 3, 1) + resid.float()
     _close(out, ref, "fused conv")
