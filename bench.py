@@ -1,0 +1,375 @@
+"""bench.py -- denoised-frames/sec of Imagine360's dual-branch DDIM loop (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--size c3|c2|tiny]
+
+A "step" is ONE pass of the hot path: one dual-branch ``MultiViewBaseModel.forward`` (CFG batch 2, 20 perspective
+views + panorama, all 16 frames) + the fused CFG/DDIM update of both latents.  The metric is quoted per 50-step clip:
+``value = n_clips * F / (50 * t_step)`` with t_step the mean of exactly K timed steps (CUDA events, barrier +
+synchronize on both sides, max over ranks).  Random-init weights of the SD-2.1 + configs/prompt-dual.yaml topology,
+synthetic inputs of SURVEY.md section 8(d), bf16 (the reference's inference dtype).
+
+Multi-GPU: clips are independent -> rank r denoises its own clip, no collective inside a
+step; one barrier + one max-all-reduce of the timing around the region ("scaling": "weak").
+
+``--impl reference`` times the reference's own algorithm on the host cores: the reference is pure Python over torch
+and cannot travel to the GPU box (no /root/reference there), so this arm runs ``oracle/`` -- the restatement pinned
+against the reference's outputs -- in fp32 with all host threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+STEPS_PER_CLIP = 50
+C3_STEP_FLOPS = 262.61e12          # dual-branch, CFG 2, 16x512x1024
+SIZES = {  # frames, pano (H, W), views
+    "c3": dict(frames=16, pano_hw=(512, 1024), views=20, step_flops=262.61e12),
+    "c2": dict(frames=16, pano_hw=(256, 512), views=20, step_flops=70.21e12),
+    "tiny": dict(frames=16, pano_hw=(128, 256), views=4, step_flops=None),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_native(device, size):
+    from imagine360_b200.host.config import FULL_UNET_KWARGS, SCHEDULER_KWARGS
+    from imagine360_b200.host.ddim import DDIMScheduler
+    from imagine360_b200.host.mvgen import MultiViewBaseModel
+    from imagine360_b200.host.pipeline import AnimationPipeline, random_init_, synthetic_inputs
+    from imagine360_b200.host.unet3d import UNet3DConditionModel
+
+    torch.manual_seed(0)
+    with torch.device(device):
+        pers = UNet3DConditionModel(**FULL_UNET_KWARGS).to(torch.bfloat16)
+        pano = UNet3DConditionModel(**FULL_UNET_KWARGS).to(torch.bfloat16)
+        mv = MultiViewBaseModel(pers, pano).to(torch.bfloat16)
+    random_init_(mv.cpu() if False else mv)
+    pipe = AnimationPipeline(None, None, None, pers, pano, mv, DDIMScheduler(**SCHEDULER_KWARGS))
+    pipe.device = torch.device(device)
+    rank = int(os.environ.get("RANK", "0"))
+    inp = synthetic_inputs(frames=size["frames"], pano_hw=size["pano_hw"], views=size["views"], device=device, seed=996995 + rank)
+    return pipe, inp
+
+
+def run_native(args, size, rank, world, device):
+    import random
+
+    from imagine360_b200 import _lib
+    from imagine360_b200 import ops
+
+    pipe, inp = build_native(device, size)
+    F_ = size["frames"]
+    lat = [inp["pano_latent"], inp["pers_latent"]]
+
+    def one_step(i):
+        lat[0], lat[1] = pipe.denoise(lat[0], lat[1], inp["pano_mask"], inp["pers_masks"], inp["pano_masked"], inp["pers_masked"],
+                                      inp["cond"], inp["cameras"], STEPS_PER_CLIP, 7.5, step_range=(i % STEPS_PER_CLIP, i % STEPS_PER_CLIP + 1))
+
+    random.seed(996995 + rank)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.int8, device=device)   # > L2 (126 MB); activations are GBs anyway
+    for i in range(args.warmup):
+        one_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    launches0 = _lib.LAUNCHES
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        one_step(args.warmup + i)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    launches = (_lib.LAUNCHES - launches0) // max(1, args.steps)
+    clocks = sampler.stop()
+    if world > 1:
+        torch.distributed.barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    t = torch.tensor([ms], device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # ---- e2e: same step through the public API with HOST buffers (pinned) -> H2D, step, D2H inside the timed region
+    host = {}
+    names = ["pano_latent", "pers_latent", "pano_mask", "pers_masks", "pano_masked", "pers_masked"]
+    cond = inp["cond"]
+    tens = {n: inp[n] for n in names}
+    tens.update(text_pano=cond.text_pano, text_pers=cond.text_pers, feats_pano=cond.feats_pano,
+                feats_pers=cond.feats_pers[:, :1].contiguous())
+    for k, v in tens.items():
+        host[k] = v.detach().cpu().pin_memory()
+    dev_buf = {k: torch.empty_like(v, device=device) for k, v in host.items()}
+    out_host = [torch.empty_like(host["pano_latent"]).pin_memory(), torch.empty_like(host["pers_latent"]).pin_memory()]
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = sum(v.numel() * v.element_size() for v in out_host)
+    from imagine360_b200.host.pipeline import Conditioning
+
+    def e2e_step(i):
+        for k in host:
+            dev_buf[k].copy_(host[k], non_blocking=True)
+        c = Conditioning(dev_buf["text_pano"], dev_buf["text_pers"], dev_buf["feats_pano"],
+                         dev_buf["feats_pers"].expand(-1, size["views"], -1, -1, -1), cond.rel_pos, cond.pitch, cond.fps)
+        a, b = pipe.denoise(dev_buf["pano_latent"], dev_buf["pers_latent"], dev_buf["pano_mask"], dev_buf["pers_masks"],
+                            dev_buf["pano_masked"], dev_buf["pers_masked"], c, inp["cameras"], STEPS_PER_CLIP, 7.5,
+                            step_range=(i % STEPS_PER_CLIP, i % STEPS_PER_CLIP + 1))
+        out_host[0].copy_(a, non_blocking=True)
+        out_host[1].copy_(b, non_blocking=True)
+
+    e2e_step(0)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(args.steps):
+        e2e_step(i + 1)
+    e.record()
+    torch.cuda.synchronize()
+    t2 = torch.tensor([s.elapsed_time(e) / args.steps], device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
+    ms_e2e = float(t2.item())
+
+    res = dict(ms=ms, ms_e2e=ms_e2e, launches=launches, clocks=clocks, h2d=h2d, d2h=d2h)
+    if rank == 0:
+        res["roofline"], res["breakdown"] = kernel_roofline(pipe, inp, size, one_step)
+    return res
+
+
+def kernel_roofline(pipe, inp, size, one_step):
+    """Per-kernel device time of ONE more step, measured live with CUDA events around every C-ABI launch on the
+    launching stream (torch's current stream).  The dominant kernel is the tcgen05 GEMM / implicit-GEMM conv engine
+    (gemm_conv_kernel<BN>); its algorithmic FLOPs are 2*M*N*K per launch as issued."""
+    from imagine360_b200 import ops
+    records = []
+    orig_gemm, orig_conv = ops.gemm, ops.conv3x3
+    L = ops.lib()
+    names = ["i360_gemm_bf16", "i360_conv3x3_bf16", "i360_attention_bf16", "i360_temporal_attention_bf16", "i360_groupnorm_stats",
+             "i360_groupnorm_apply", "i360_layernorm", "i360_upsample2x_nhwc", "i360_im2col3x3_s2_nhwc", "i360_axpby_bf16",
+             "i360_cfg_ddim_step_bf16", "i360_avgpool_frames4_bf16", "i360_grid_sample_f32", "i360_softmax_rows_bf16"]
+    timed = {}
+
+    class Timed:
+        def __init__(self, name, fn):
+            self.name, self.fn = name, fn
+
+        def __call__(self, *a):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = self.fn(*a)
+            e.record()
+            timed.setdefault(self.name, []).append((s, e))
+            return r
+
+    flops = {"gemm": 0.0, "conv": 0.0}
+
+    def gemm(a, w, *args, **kw):
+        flops["gemm"] += 2.0 * a.shape[0] * w.shape[0] * a.shape[1]
+        return orig_gemm(a, w, *args, **kw)
+
+    def conv(x, wp, *args, **kw):
+        b, h, wd, _ = x.shape
+        flops["conv"] += 2.0 * b * h * wd * wp.shape[0] * wp.shape[1]
+        return orig_conv(x, wp, *args, **kw)
+
+    class LibProxy:
+        def __getattr__(self, n):
+            f = getattr(L, n)
+            return Timed(n, f) if n in names else f
+
+    proxy = LibProxy()
+    orig_lib = ops.lib
+    ops.lib, ops.gemm, ops.conv3x3 = (lambda: proxy), gemm, conv
+    import imagine360_b200.host.forward as Fw
+    try:
+        one_step(7)
+        torch.cuda.synchronize()
+    finally:
+        ops.lib, ops.gemm, ops.conv3x3 = orig_lib, orig_gemm, orig_conv
+    per = {n: (len(v), sum(a.elapsed_time(b) for a, b in v)) for n, v in timed.items()}
+    total = sum(ms for _, ms in per.values())
+    gc_ms = per.get("i360_gemm_bf16", (0, 0))[1] + per.get("i360_conv3x3_bf16", (0, 0))[1]
+    gc_n = per.get("i360_gemm_bf16", (0, 0))[0] + per.get("i360_conv3x3_bf16", (0, 0))[0]
+    pk = peaks()
+    achieved = (flops["gemm"] + flops["conv"]) / (gc_ms * 1e-3) / 1e12 if gc_ms > 0 else 0.0
+    roof = {"kernel": "gemm_conv_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)", "bound": "tensor", "achieved": round(achieved, 1),
+            "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(achieved / pk["tflops"], 4), "traffic": None,
+            "peak_source": pk["source"] + " (bf16_tflops_sustained)", "launches_per_step": gc_n,
+            "avg_launch_ms": round(gc_ms / max(1, gc_n), 4), "alg_flops_per_step": flops["gemm"] + flops["conv"],
+            "share_of_step_kernel_time": round(gc_ms / total, 4) if total else None}
+    breakdown = {n: {"launches": c, "ms": round(ms, 3)} for n, (c, ms) in sorted(per.items(), key=lambda kv: -kv[1][1])}
+    return roof, breakdown
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (reference algorithm) on the host cores, bounded sample
+# ----------------------------------------------------------------------------------------------------------
+def cpu_sample_step(threads=None):
+    """One dual-branch denoise step of the reference algorithm at FULL channel widths / depth but reduced extent:
+    F=16, 128x256 panorama (latent 16x32), 2 views of 64x64 (latent 8x8... kept at 16x16 so every level exists)."""
+    from imagine360_b200.host.config import FULL_UNET_KWARGS
+    from imagine360_b200.host.mvgen import MultiViewBaseModel
+    from imagine360_b200.host.pipeline import random_init_
+    from imagine360_b200.host.unet3d import UNet3DConditionModel
+    from oracle import mvgen as OM
+    from torch.utils.flop_counter import FlopCounterMode
+
+    torch.set_num_threads(threads or os.cpu_count())
+    torch.manual_seed(0)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    with torch.device(dev):
+        mv = MultiViewBaseModel(UNet3DConditionModel(**FULL_UNET_KWARGS), UNet3DConditionModel(**FULL_UNET_KWARGS))
+    random_init_(mv)
+    sd = {k: v.detach().float().cpu() for k, v in mv.state_dict().items()}
+    del mv
+    f, m, b = 16, 2, 2
+    g = torch.Generator().manual_seed(1)
+
+    def rn(*s):
+        return torch.randn(*s, generator=g)
+
+    cams = dict(FoV=[90, 90], theta=[-150.0, 30.0], phi=[35.0, -20.0])
+    args = (rn(b, m, 9, f, 16, 16), rn(b, 9, f, 16, 32), torch.tensor([481]), rn(b * m, 77, 1024), rn(b, 77, 1024), cams,
+            torch.tensor([8, 8]), torch.tensor([[8, 8], [8, 8]]), rn(b, f, 4096, 256), rn(b, 1, f, 4096, 256).expand(-1, m, -1, -1, -1),
+            torch.tensor([1.0, 1, 63, 63, 128, 256])[None, None].repeat(b, f, 1), torch.zeros(b, f), [False] * 7,
+            rn(b, 64, 1024), rn(b * m, 64, 1024))
+    with torch.no_grad():
+        with FlopCounterMode(display=False) as fc:
+            OM.mv_forward(sd, *args)
+        flops = fc.get_total_flops()
+
+        def run():
+            t0 = time.perf_counter()
+            OM.mv_forward(sd, *args)
+            return time.perf_counter() - t0
+    return run, flops, "1 dual-branch step of the oracle (reference algorithm), fp32, full widths/depth, F=16, 128x256 pano " \
+                       "(latent 16x32) + 2 views (latent 16x16), CFG 2; scaled to the 16x512x1024 step by FLOPs"
+
+
+def cpu_metric(seconds, flops):
+    """frames/s at the C3 workload extrapolated by algorithmic FLOPs (262.61 TF per step)."""
+    return 16.0 / (STEPS_PER_CLIP * seconds * (C3_STEP_FLOPS / flops))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--size", default="c3", choices=list(SIZES))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    torch.set_grad_enabled(False)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    size = SIZES[args.size]
+    config = {"workload": f"dual-branch (20 pers views + pano) denoise step, {size['frames']}x{size['pano_hw'][0]}x{size['pano_hw'][1]}, "
+                          f"CFG 2, {STEPS_PER_CLIP}-step DDIM clip (BASELINE.json configs[2])" if args.size == "c3" else f"size={args.size}",
+              "clips_per_gpu": 1, "frames": size["frames"], "steps_per_clip": STEPS_PER_CLIP, "parallelism": f"dp{args.gpus} (independent clips)",
+              "l2_flush": "256 MiB buffer written between timed steps; working set >> 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        run, flops, sample = cpu_sample_step()
+        for _ in range(min(args.warmup, 1)):
+            run()
+        ts = [run() for _ in range(min(args.steps, 3))]
+        sec = sum(ts) / len(ts)
+        v = cpu_metric(sec, flops)
+        print(json.dumps({"impl": "reference", "metric": "denoised-frames/sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+                          "steps": len(ts), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": sample,
+                                           "sample_flops": flops, "sample_seconds": sec},
+                          "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    if world > 1:
+        torch.distributed.init_process_group("nccl")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    r = run_native(args, size, rank, world, device)
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    fps = world * size["frames"] / (STEPS_PER_CLIP * r["ms"] * 1e-3)
+    fps_e2e = world * size["frames"] / (STEPS_PER_CLIP * r["ms_e2e"] * 1e-3)
+    out = {"metric": "denoised-frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": config, "clocks": r["clocks"], "gpu_launches": r["launches"],
+           "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                   "ms_per_step": r["ms_e2e"]},
+           "roofline": r.get("roofline"), "step_tflops": (size["step_flops"] or 0) / (r["ms"] * 1e-3) / 1e12}
+    if not args.no_cpu_baseline and world == 1:
+        run, flops, sample = cpu_sample_step()
+        sec = run()
+        out["cpu_baseline"] = {"value": cpu_metric(sec, flops), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": sample, "sample_flops": flops, "sample_seconds": sec}
+    else:
+        out["cpu_baseline"] = None
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "bench_breakdown.json"), "w") as f:
+        json.dump({"breakdown": r.get("breakdown"), "roofline": r.get("roofline"), "ms_per_step": r["ms"]}, f, indent=1)
+    print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -38,12 +38,17 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+LAUNCHES = 0   # C-ABI kernel launches issued through this module (bench.py reports it as gpu_launches)
+
+
 def check(code: int, what: str) -> None:
     """Translate a C-ABI status into an exception.
 
     The reference wraps the pipeline call in a bare ``except: continue``
     (inference_dual_p2e.py:596-597), so also write to stderr before raising.
     """
+    global LAUNCHES
+    LAUNCHES += 1
     if code != 0:
         msg = f"imagine360_b200: {what} failed: {ERRORS.get(code, code)}"
         print(msg, file=sys.stderr, flush=True)

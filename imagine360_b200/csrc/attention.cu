@@ -114,7 +114,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (lane == 0) {
       mbar_expect_tx(q_full, C::kQBytes);
       tma_load_4d(sQ, &tmQ, q_full, p.q.col0 + head * HD, qc1, qc2, qc3);
-      const int q_base = (qt / p.q.n1) * p.q.box3 * p.q.d1 + (qt % p.q.n1) * p.q.box1;
+      const int q_base = qt * 128;   // the bias arrives tile-padded: [q_tiles*128, kv_tiles*128]
       for (int j = 0; j < p.kv_tiles; ++j) {
         const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
         int c1, c2, c3;
@@ -123,7 +123,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_expect_tx(&k_full[st], C::kKVBytes);
         tma_load_4d(sK + st * C::kKVBytes, &tmK, &k_full[st], p.kv.col0 + head * HD, c1, c2, c3);
         if (BIAS) {
-          const int kv_base = (j / p.kv.n1) * p.kv.box3 * p.kv.d1 + (j % p.kv.n1) * p.kv.box1;
+          const int kv_base = j * 128;
           mbar_wait(b_empty, (j & 1) ^ 1);
           mbar_expect_tx(b_full, C::kBiasBytes);
           tma_load_2d(sB, &tmB, b_full, kv_base, q_base);
@@ -343,8 +343,11 @@ static void fill_operand(AttnOperand* o, const I360TokenView& v) {
   o->col0 = v.col0;
 }
 
-// q/k/v/o: token views; heads x head_dim channels starting at col0 of each view; bias: optional dense
-// bf16 [bias_rows = Nq, bias_cols = Nk] additive logits bias shared by all batch items and heads.
+// q/k/v/o: token views; heads x head_dim channels starting at col0 of each view; bias: optional bf16
+// additive logits bias shared by all batch items and heads, in TILE layout: row qt*128 + r is the query held by
+// row r of query tile qt, column j*128 + c the key held by row c of key tile j (see fill_operand: a tile is 128
+// consecutive tokens of one view, or 128/d1 whole views when d1 divides 128).  For sequences whose views are
+// multiples of 128 tokens (every level of the 512x1024 / 256x512 configurations) this IS the dense [Nq, Nk] matrix.
 extern "C" int i360_attention_bf16(const I360TokenView* q, const I360TokenView* k, const I360TokenView* v,
                                    const I360TokenView* o, int heads, int head_dim, int batch, float scale,
                                    const void* bias, int bias_rows, int bias_cols, int accumulate, void* stream) {

@@ -32,9 +32,11 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__
   }
 }
 
-// out [B*Ho*Wo, 9*C] for a 3x3 / stride 2 / pad 1 conv; circular != 0: columns wrap (pano), rows zero-pad
+// out [B*Ho*Wo, 9*C] for a 3x3 / stride 2 conv with `pad_lo` zero rows/cols before and (2 - pad_lo - (H&1)) after
+// (pad_lo = 1: symmetric pad 1 of Downsample3D; pad_lo = 0: the VAE's asymmetric F.pad(0,1,0,1),
+// diffusers/models/resnet.py:184); circular != 0: columns wrap instead (pano halo), rows zero-pad
 __global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int B, int H, int W, int C,
-                                 int circular) {
+                                 int circular, int pad_lo) {
   const int nvec = C >> 3, Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(B) * Ho * Wo * 9 * nvec;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -45,8 +47,8 @@ __global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
     const int wo = static_cast<int>(r % Wo); r /= Wo;
     const int ho = static_cast<int>(r % Ho);
     const int b = static_cast<int>(r / Ho);
-    const int hi = 2 * ho + tap / 3 - 1;
-    int wi = 2 * wo + tap % 3 - 1;
+    const int hi = 2 * ho + tap / 3 - pad_lo;
+    int wi = 2 * wo + tap % 3 - pad_lo;
     bool ok = hi >= 0 && hi < H;
     if (circular) wi = (wi + W) % W; else ok = ok && wi >= 0 && wi < W;
     uint4 val = make_uint4(0, 0, 0, 0);
@@ -152,11 +154,12 @@ extern "C" int i360_upsample2x_nhwc(const void* x, void* out, int B, int H, int 
   return I360_OK;
 }
 
-extern "C" int i360_im2col3x3_s2_nhwc(const void* x, void* out, int B, int H, int W, int C, int circular, void* stream) {
-  if (!x || !out || (C % 8) || (H % 2) || (W % 2) || B <= 0) return I360_ERR_ARG;
+extern "C" int i360_im2col3x3_s2_nhwc(const void* x, void* out, int B, int H, int W, int C, int circular, int pad_lo,
+                                      void* stream) {
+  if (!x || !out || (C % 8) || (H % 2) || (W % 2) || B <= 0 || pad_lo < 0 || pad_lo > 1) return I360_ERR_ARG;
   const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * 9 * (C / 8);
   im2col_s2_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(x), static_cast<bf16*>(out), B, H, W, C, circular);
+      static_cast<const bf16*>(x), static_cast<bf16*>(out), B, H, W, C, circular, pad_lo);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }

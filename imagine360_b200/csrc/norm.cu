@@ -184,9 +184,59 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// row softmax (fp32 math on bf16 logits) -- the VAE's single-head AttentionBlock computes
+// softmax(scores.float()).type(bf16) on materialised scores (diffusers/models/attention.py:353-367)
+// ---------------------------------------------------------------------------------------------
+__global__ void softmax_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long ld, int N) {
+  __shared__ float red[32];
+  const bf16* xr = x + static_cast<long long>(blockIdx.x) * ld;
+  bf16* yr = y + static_cast<long long>(blockIdx.x) * ld;
+  const int nvec = N >> 3;
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float f[8]; unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx = fmaxf(mx, f[j]);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float f[8]; unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += __expf(f[j] - mx);
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) sum += red[w];
+  const float inv = 1.0f / sum;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float f[8]; unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __expf(f[j] - mx) * inv;
+    *reinterpret_cast<uint4*>(yr + v * 8) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                       pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+}
+
 }  // namespace i360
 
 using namespace i360;
+
+extern "C" int i360_softmax_rows_bf16(const void* x, void* y, long long ld, long long M, int N, void* stream) {
+  if (!x || !y || M <= 0 || N <= 0 || (N % 8) || (ld % 8)) return I360_ERR_ARG;
+  softmax_rows_kernel<<<static_cast<unsigned>(M), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(y), ld, N);
+  I360_CUDA_CHECK_LAUNCH();
+  return I360_OK;
+}
 
 static int gn_geometry(int C, int B, long long npix, int* block, int* chunk, int* chunks) {
   const int nvec = C / 8;

@@ -1,0 +1,233 @@
+"""Host-side mirror of ``animatediff.pipelines.pipeline_animation_inference_dual.AnimationPipeline``.
+
+Same constructor and ``__call__`` signature / ``video_batch`` contract as the reference (pipeline...dual.py:63-81,
+:553-596) so ``inference_dual_p2e.py`` can drive it unchanged.  The denoising loop (:734-809) is exposed on its own as
+:meth:`AnimationPipeline.denoise` -- that is the unit ``bench.py`` times: per step one dual-branch
+``MultiViewBaseModel.forward`` + one fused CFG/DDIM kernel per branch, no ``empty_cache`` / ``gc`` / ``.item()`` syncs.
+"""
+from __future__ import annotations
+
+import random
+from dataclasses import dataclass
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+from . import geometry as G
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class AnimationPipelineOutput:
+    videos: torch.Tensor
+
+
+@dataclass
+class Conditioning:
+    """Step-invariant inputs of the loop (what the reference computes before `for t in timesteps`)."""
+    text_pano: torch.Tensor      # [2, 77, D]      uncond (+) cond
+    text_pers: torch.Tensor      # [2*m, 77, D]
+    feats_pano: torch.Tensor     # [2, F, 4096, C] SAM features (cond == uncond copy, pipeline...dual.py:695)
+    feats_pers: torch.Tensor     # [2, m, F, 4096, C]
+    rel_pos: torch.Tensor        # [F, 6]
+    pitch: torch.Tensor          # [F]
+    fps: int = 8
+
+
+class AnimationPipeline:
+    def __init__(self, vae, text_encoder, tokenizer, pers_unet, pano_unet, mv_base_model, scheduler, image_encoder=None,
+                 image_encoder_name="CLIP"):
+        self.vae, self.text_encoder, self.tokenizer = vae, text_encoder, tokenizer
+        self.pers_unet, self.pano_unet, self.mv_base_model, self.scheduler = pers_unet, pano_unet, mv_base_model, scheduler
+        self.image_encoder, self.image_encoder_name = image_encoder, image_encoder_name
+        self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1) if vae is not None else 8
+        self.device = torch.device("cpu")
+
+    def to(self, device):
+        self.device = torch.device(device)
+        for m in (self.vae, self.text_encoder, self.mv_base_model, self.image_encoder):
+            if isinstance(m, torch.nn.Module):
+                m.to(device)
+        return self
+
+    @property
+    def _execution_device(self):
+        return self.device
+
+    def enable_vae_slicing(self):
+        if self.vae is not None:
+            self.vae.enable_slicing()
+
+    # ------------------------------------------------------------------------------------------------
+    def init_noise(self, bs, video_length, equi_h, equi_w, pers_h, pers_w, cameras, device, latents_dtype=BF16, pano_noise=None):
+        """pipeline...dual.py:361-387: one panorama noise draw; each view gets it resampled with nearest lookup.
+        All frames go through ONE gather launch (the grid only depends on the camera)."""
+        cams = {k: v.reshape(-1, *v.shape[2:]) if isinstance(v, torch.Tensor) and v.dim() >= 2 else v for k, v in cameras.items()}
+        m = len(G.camera_lists(cams)[0])
+        if pano_noise is None:
+            pano_noise = torch.randn(bs, video_length, 1, 4, equi_h, equi_w, device=device)
+        pano_out = pano_noise.squeeze(2).permute(0, 2, 1, 3, 4).contiguous()                       # b c f h w
+        src = pano_noise.squeeze(2).reshape(bs, 1, video_length * 4, equi_h, equi_w).expand(-1, m, -1, -1, -1)
+        views = G.e2p(src.reshape(bs * m, video_length * 4, equi_h, equi_w).contiguous(),
+                      {k: (list(v) * bs) for k, v in zip(("FoV", "theta", "phi"), G.camera_lists(cams))},
+                      (pers_h, pers_w), mode="nearest", grid_dtype=torch.float32)
+        pers = views.reshape(bs, m, video_length, 4, pers_h, pers_w).permute(0, 1, 3, 2, 4, 5).contiguous()   # b m c f h w
+        return pano_out.to(latents_dtype), pers.to(latents_dtype)
+
+    def prepare_masked_latents_pano(self, video_length, pixels_masked, mask):
+        """:427-448  (VAE encode in chunks of 8 frames, posterior sample, x 0.18215; mask nearest-resized)"""
+        x = pixels_masked.reshape(-1, *pixels_masked.shape[2:])
+        lat = torch.cat([self.vae.encode(x[i:i + 8].to(self.vae.dtype), 8).latent_dist.sample() for i in range(0, x.shape[0], 8)])
+        b = pixels_masked.shape[0]
+        lat = lat.reshape(b, video_length, *lat.shape[1:]).permute(0, 2, 1, 3, 4) * 0.18215
+        mask = mask.transpose(2, 1)
+        mask = F.interpolate(mask, size=(mask.shape[2], lat.shape[-2], lat.shape[-1]))
+        return lat, mask.to(self.device)
+
+    def prepare_masked_latents_pers(self, video_length, pixels_masked, masks):
+        """:451-473"""
+        b, f, m = pixels_masked.shape[:3]
+        x = pixels_masked.reshape(-1, *pixels_masked.shape[3:])
+        lat = torch.cat([self.vae.encode(x[i:i + 8].to(self.vae.dtype), 8).latent_dist.sample() for i in range(0, x.shape[0], 8)])
+        lat = lat.reshape(b, f, m, *lat.shape[1:]).permute(0, 2, 3, 1, 4, 5) * 0.18215              # b m c f h w
+        masks = masks.permute(0, 3, 1, 2, 4, 5).squeeze(0)
+        masks = F.interpolate(masks, size=(m, lat.shape[-2], lat.shape[-1])).unsqueeze(3)
+        masks = masks.permute(0, 2, 3, 1, 4, 5)                                                      # b m c f h w
+        return lat, masks.to(self.device)
+
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def denoise(self, pano_latent, pers_latent, pano_mask, pers_masks, pano_masked, pers_masked, cond: Conditioning, cameras,
+                num_inference_steps=50, guidance_scale=7.5, on_step=None, step_range=None, inject=None):
+        """The `for t in timesteps` loop (pipeline...dual.py:734-809) -> (pano_latent, pers_latent).
+        ``step_range=(i0, i1)`` runs only loop iterations i0..i1-1 of the ``num_inference_steps`` schedule.
+        ``inject(i) -> dict(antipodal_draws=[7 bools], ip_noise=(pano, pers))`` overrides the per-step random draws (tests)."""
+        dev = pano_latent.device
+        m = pers_latent.shape[1]
+        self.scheduler.set_timesteps(num_inference_steps, device=dev)
+        fps_pano = torch.tensor([cond.fps, cond.fps], device=dev)
+        fps_pers = fps_pano[:, None].repeat(1, m)
+        rel_pos = cond.rel_pos.to(dev)[None].repeat(2, 1, 1)
+        pitch = cond.pitch.to(dev)[None].repeat(2, 1)
+        static_pano = torch.cat([pano_mask.to(BF16), pano_masked.to(BF16)], dim=1)
+        static_pers = torch.cat([pers_masks.to(BF16), pers_masked.to(BF16)], dim=2)
+        pano_latent, pers_latent = pano_latent.to(BF16).contiguous(), pers_latent.to(BF16).contiguous()
+        i0, i1 = step_range if step_range is not None else (0, num_inference_steps)
+        for i, t in list(enumerate(self.scheduler.timesteps_host))[i0:i1]:
+            xin_pano = torch.cat([pano_latent, static_pano], dim=1)
+            xin_pers = torch.cat([pers_latent, static_pers], dim=2)
+            pred_pers, pred_pano = self.mv_base_model(
+                latents=torch.cat([xin_pers] * 2), pano_latent=torch.cat([xin_pano] * 2),
+                timestep=torch.tensor([t], device=dev), prompt_embd=cond.text_pers, pano_prompt_embd=cond.text_pano,
+                cameras=cameras, use_fps_condition=True, use_ip_plus_cross_attention=True, fps_tensor_pano=fps_pano,
+                fps_tensor_pers=fps_pers, reference_images_clip_feat_pano=cond.feats_pano,
+                reference_images_clip_feat_pers=cond.feats_pers, relative_position_tensor=rel_pos, pitchs_tensor=pitch,
+                **(inject(i) if inject is not None else {}))
+            sa, sb, sap, sbp = self.scheduler.coefficients(t)
+            pano_latent = ops.cfg_ddim_step(pano_latent, pred_pano[0:1].contiguous(), pred_pano[1:2].contiguous(),
+                                            guidance_scale, sa, sb, sap, sbp)
+            pers_latent = ops.cfg_ddim_step(pers_latent, pred_pers[0:1].contiguous(), pred_pers[1:2].contiguous(),
+                                            guidance_scale, sa, sb, sap, sbp)
+            if on_step is not None:
+                on_step(i, t)
+        return pano_latent, pers_latent
+
+    @torch.no_grad()
+    def decode_latents(self, latents, frames_per_call: int = 4):
+        """:301-313 -- returns fp32 [b, 3, f, H, W] in [0, 1] on the device (the caller moves it to the host)."""
+        b, c, f, h, w = latents.shape
+        z = (latents / 0.18215).permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w).to(self.vae.dtype)
+        out = torch.cat([self.vae.decode(z[i:i + frames_per_call]).sample for i in range(0, b * f, frames_per_call)])
+        out = out.reshape(b, f, *out.shape[1:]).permute(0, 2, 1, 3, 4)
+        return (out / 2 + 0.5).clamp(0, 1).float()
+
+    def decode_video(self, pano_latent):
+        """pad_pano(latent, 4) -> decode -> crop 32 px (:811-815)"""
+        video = self.decode_latents(G.pad_pano(pano_latent, 4))
+        return G.unpad_pano(video, 4 * self.vae_scale_factor)
+
+    # ------------------------------------------------------------------------------------------------
+    def _encode_prompt(self, prompt, device, negative_prompt):
+        """:227-299 through the caller-supplied CLIP tokenizer / text encoder (third-party, out of scope)."""
+        def enc(texts):
+            ids = self.tokenizer(texts, padding="max_length", max_length=self.tokenizer.model_max_length, truncation=True,
+                                 return_tensors="pt").input_ids
+            return self.text_encoder(ids.to(device))[0]
+        return torch.cat([enc(negative_prompt), enc(prompt)])
+
+    def _sam_features(self, anchor_pixels):
+        """:675-718 through the caller-supplied SAM predictor (third-party, out of scope)."""
+        if self.image_encoder is None or not callable(getattr(self.image_encoder, "embed_frames", None)):
+            raise NotImplementedError("pass an image_encoder exposing embed_frames(frames[f,3,h,w]) -> [f, 4096, 256]")
+        return self.image_encoder.embed_frames(anchor_pixels)
+
+    @torch.no_grad()
+    def __call__(self, prompt, num_inference_steps=50, guidance_scale_text=7.5, guidance_scale_adapter=7.5, negative_prompt=None,
+                 eta=0.0, generator=None, output_type="tensor", return_dict=True, latents_dtype=BF16, video_batch=None,
+                 use_outpaint=False, use_ip_plus_cross_attention=False, use_fps_condition=False, ip_plus_condition="image", **kwargs):
+        if not (use_outpaint and use_ip_plus_cross_attention and use_fps_condition and ip_plus_condition == "video"):
+            raise NotImplementedError("only the configuration of configs/prompt-dual.yaml is on the native path")
+        device = self._execution_device
+        vb = video_batch
+        pano_px, pano_mask = vb["pano_pixel_values"], vb["pano_mask"]
+        pers_px, pers_masks = vb["pers_pixel_values"], vb["pers_masks"]
+        cameras, f, m = vb["cameras"], vb["video_length"], pers_px.shape[2]
+        pano_px_m = (pano_px.clone() * (pano_mask < 0.5)).to(device)
+        pers_px_m = (pers_px.clone() * (pers_masks < 0.5)).to(device)
+        # RNG order of the reference: init_noise -> pano VAE samples -> pers VAE samples -> per-step IP noise
+        pano_latent, pers_latent = self.init_noise(1, f, vb["pano_H"] // 8, vb["pano_W"] // 8, vb["pers_size"] // 8,
+                                                   vb["pers_size"] // 8, cameras, device, latents_dtype)
+        pano_masked, pano_mask_l = self.prepare_masked_latents_pano(f, pano_px_m, pano_mask.to(device))
+        pers_masked, pers_masks_l = self.prepare_masked_latents_pers(f, pers_px_m, pers_masks.to(device))
+        text_pano = self._encode_prompt([prompt], device, [negative_prompt]).to(latents_dtype)
+        text_pers = self._encode_prompt([prompt] * m, device, [negative_prompt] * m).to(latents_dtype)
+        feats = self._sam_features(vb["anchor_pixels_values"].to(device)[0]).to(latents_dtype)[None]
+        feats_p = self._sam_features(vb["anchor_pixels_values_pers"].to(device)[0]).to(latents_dtype)[None]
+        cond = Conditioning(text_pano, text_pers, torch.cat([feats, feats]),
+                            torch.cat([feats_p, feats_p]).unsqueeze(1).expand(-1, m, -1, -1, -1),
+                            vb["relative_position"].to(device).reshape(f, 6), vb["pitchs"].to(device).reshape(f), vb["fps"])
+        pano_latent, _ = self.denoise(pano_latent, pers_latent, pano_mask_l, pers_masks_l, pano_masked, pers_masked, cond, cameras,
+                                      num_inference_steps, guidance_scale_text)
+        video = self.decode_video(pano_latent).cpu()
+        return AnimationPipelineOutput(videos=video) if return_dict else video
+
+
+# ------------------------------------------------------------------------------------------------------
+# synthetic inputs of SURVEY.md §8(d) (there are no datasets / checkpoints offline)
+# ------------------------------------------------------------------------------------------------------
+def synthetic_inputs(frames=16, pano_hw=(512, 1024), views=20, ctx_dim=1024, sam_dim=256, device="cuda", seed=996995,
+                     cameras=None):
+    g = torch.Generator(device=device).manual_seed(seed)
+    H, W = pano_hw
+    eh, ew, ph = H // 8, W // 8, H // 16
+
+    def rn(*shape, scale=1.0):
+        return (torch.randn(*shape, device=device, generator=g) * scale).to(BF16)
+
+    pano_latent, pers_latent = rn(1, 4, frames, eh, ew), rn(1, views, 4, frames, ph, ph)
+    pano_mask = torch.ones(1, 1, frames, eh, ew, device=device, dtype=BF16)
+    pano_mask[..., eh // 4: eh // 4 + eh // 2, ew // 2 - eh // 4: ew // 2 + eh // 4] = 0     # centred (H/2)x(H/2) known square
+    pers_masks = torch.ones(1, views, 1, frames, ph, ph, device=device, dtype=BF16)
+    cond = Conditioning(rn(2, 77, ctx_dim), rn(2 * views, 77, ctx_dim), rn(2, frames, 4096, sam_dim),
+                        rn(2, 1, frames, 4096, sam_dim).expand(-1, views, -1, -1, -1),
+                        torch.tensor([1.0, 1.0, H / 2 - 1, H / 2 - 1, H, W], device=device)[None].repeat(frames, 1),
+                        torch.zeros(frames, device=device), 8)
+    if cameras is None:
+        cameras = G.get_cameras(90, H // 2, device=device)
+    return dict(pano_latent=pano_latent, pers_latent=pers_latent, pano_mask=pano_mask, pers_masks=pers_masks,
+                pano_masked=rn(1, 4, frames, eh, ew, scale=0.18215), pers_masked=rn(1, views, 4, frames, ph, ph, scale=0.18215),
+                cond=cond, cameras=cameras)
+
+
+def random_init_(module, seed=0, std=0.02):
+    """Default init, then re-randomise the zero-initialised tensors (SURVEY.md trap 4) so every kernel sees data."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if p.numel() > 0 and p.is_floating_point() and float(p.detach().abs().max()) == 0.0:
+                p.copy_(torch.randn(p.shape, generator=g) * std)
+    return module

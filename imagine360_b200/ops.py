@@ -195,11 +195,39 @@ def multiview_view(t: torch.Tensor, n_clip: int, n_view: int, n_frame: int, n_to
                      ld * n_tok * n_frame, n_frame, 1, n_view, n_view)
 
 
+def _tile_rule(d1: int, ext3: int):
+    """(box1, box3, n1) exactly as attention.cu::fill_operand chooses them."""
+    if ext3 > 1 and d1 < 128 and 128 % d1 == 0:
+        return d1, 128 // d1, 1
+    return 128, 1, (d1 + 127) // 128
+
+
+def tile_attention_bias(bias: torch.Tensor, q: TokenView, k: TokenView) -> torch.Tensor:
+    """Dense [Nq, Nk] bias (sequence order (view, token)) -> the kernel's tile layout.  A no-op whenever every view
+    is a multiple of 128 tokens or divides 128 with the views filling whole tiles."""
+    def axis(t, dim, d1, ext3):
+        b1, b3, n1 = _tile_rule(d1, ext3)
+        if b3 > 1 or d1 % 128 == 0:
+            return t                                   # already contiguous in tile order
+        shp = list(t.shape)
+        t = t.unflatten(dim, (ext3, d1))
+        pad = [0, 0] * (t.dim() - dim - 2) + [0, n1 * 128 - d1]
+        t = F.pad(t, pad)
+        return t.flatten(dim, dim + 1)
+    import torch.nn.functional as F
+    out = axis(bias, 0, q.d1, max(q.ext3, 1))
+    out = axis(out, 1, k.d1, max(k.ext3, 1))
+    if out.shape[1] % 8:
+        out = F.pad(out, (0, 8 - out.shape[1] % 8))
+    return out.contiguous()
+
+
 def attention(q: TokenView, k: TokenView, v: TokenView, o: TokenView, heads: int, head_dim: int, batch: int,
               scale: float | None = None, bias: torch.Tensor | None = None, accumulate: bool = False) -> None:
     if bias is not None:
         _chk_bf16(bias)
-        assert bias.dim() == 2 and bias.is_contiguous()
+        assert bias.dim() == 2
+        bias = tile_attention_bias(bias, q, k)       # identity for every production shape
     rc = lib().i360_attention_bf16(ctypes.byref(q), ctypes.byref(k), ctypes.byref(v), ctypes.byref(o), c_int(heads),
                                    c_int(head_dim), c_int(batch), c_float(scale if scale is not None else head_dim ** -0.5),
                                    _p(bias), c_int(bias.shape[0] if bias is not None else 0),
@@ -229,12 +257,21 @@ def upsample2x(x: torch.Tensor, pad_in: int = 0) -> torch.Tensor:
     return out
 
 
-def im2col_s2(x: torch.Tensor, circular: bool) -> torch.Tensor:
+def softmax_rows(x: torch.Tensor) -> torch.Tensor:
+    _chk_bf16(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    out = torch.empty_like(x)
+    check(lib().i360_softmax_rows_bf16(_p(x), _p(out), c_longlong(x.stride(0)), c_longlong(x.shape[0]), c_int(x.shape[1]),
+                                       _stream()), "i360_softmax_rows_bf16")
+    return out
+
+
+def im2col_s2(x: torch.Tensor, circular: bool, pad_lo: int = 1) -> torch.Tensor:
     _chk_bf16(x)
     B, H, W, C = x.shape
     out = torch.empty((B * (H // 2) * (W // 2), 9 * C), dtype=BF16, device=x.device)
     check(lib().i360_im2col3x3_s2_nhwc(_p(x), _p(out), c_int(B), c_int(H), c_int(W), c_int(C), c_int(1 if circular else 0),
-                                       _stream()), "i360_im2col3x3_s2_nhwc")
+                                       c_int(pad_lo), _stream()), "i360_im2col3x3_s2_nhwc")
     return out
 
 

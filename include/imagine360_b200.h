@@ -98,13 +98,19 @@ int i360_temporal_attention_bf16(const void* q, long long ldq, const void* k, lo
                                  long long ldv, void* o, long long ldo, int B, int F, int D, int heads, int head_dim,
                                  float scale, void* stream);
 
+/* Row softmax with fp32 math over materialised bf16 logits [M, N] (the VAE's single-head AttentionBlock,
+ * diffusers/models/attention.py:353-367: head_dim 512 does not fit the fused kernel's TMEM budget). */
+int i360_softmax_rows_bf16(const void* x, void* y, long long ld, long long M, int N, void* stream);
+
 /* nearest x2 upsample, out [B, 2H, 2(W+2*pad_in), C] (Upsample3D, animatediff/models/resnet.py:86-110, with the
  * pano halo of MVGenModel.py:449-452 folded in). */
 int i360_upsample2x_nhwc(const void* x, void* out, int B, int H, int W, int C, int pad_in, void* stream);
 
 /* im2col for the stride-2 downsample convs (Downsample3D, resnet.py:117-140; circular = pano halo of
- * MVGenModel.py:305-314).  out [B*(H/2)*(W/2), 9*C]. */
-int i360_im2col3x3_s2_nhwc(const void* x, void* out, int B, int H, int W, int C, int circular, void* stream);
+ * MVGenModel.py:305-314; pad_lo = 0 = the VAE encoder's asymmetric (0,1,0,1) pad, diffusers/models/resnet.py:181-190).
+ * out [B*(H/2)*(W/2), 9*C]. */
+int i360_im2col3x3_s2_nhwc(const void* x, void* out, int B, int H, int W, int C, int circular, int pad_lo,
+                           void* stream);
 
 /* out = a*x + bf16(b*y)  (add_noise_to_condition, src/models/MVGenModel.py:11-14). */
 int i360_axpby_bf16(const void* x, const void* y, void* out, float a, float b, long long n, void* stream);
