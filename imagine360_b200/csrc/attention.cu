@@ -56,6 +56,12 @@ struct AttnCfg {
   static constexpr int kTmemCols = 256;   // S: 128, O: HD
 };
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void tile_coords(const AttnOperand& op, int bi, int tile, int& c1, int& c2, int& c3) {
   c1 = (tile % op.n1) * op.box1;
   c2 = (bi % op.A) / op.Bdiv;
@@ -182,6 +188,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
     for (int j = 0; j < p.kv_tiles; ++j) {
       const int kv_i1 = (j % p.kv.n1) * p.kv.box1, kv_i3 = (j / p.kv.n1) * p.kv.box3;
+      // columns [0, limit) of this tile hold real keys (tile = 128 tokens of one view, or box3 whole views)
+      int limit;
+      if (p.kv.box3 == 1) limit = (kv_i3 < p.kv.ext3) ? min(128, p.kv.d1 - kv_i1) : 0;
+      else limit = min(128, (p.kv.ext3 - kv_i3) * p.kv.box1);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       if (BIAS) mbar_wait(b_full, j & 1);
@@ -205,16 +215,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int col = c + g * 8 + e;
-            const int tok = kv_i1 + col % p.kv.box1, view = kv_i3 + col / p.kv.box1;
             float s = __uint_as_float(v[g * 8 + e]) * p.scale_log2;
             if (BIAS) s += bvals[e] * LOG2E;
-            if (tok >= p.kv.d1 || view >= p.kv.ext3) s = -INFINITY;
+            if (col >= limit) s = -INFINITY;
             m_tile = fmaxf(m_tile, s);
           }
         }
       }
       const float m_new = fmaxf(m_run, m_tile);
-      const float alpha = exp2f(m_run - m_new);   // first tile: exp2(-inf) = 0
+      const float alpha = fast_exp2(m_run - m_new);   // first tile: exp2(-inf) = 0
       // pass 2: p = exp2(s - m), row sum, P -> smem (K-major, 128B swizzle, two 64-column halves)
       float l_tile = 0.f;
 #pragma unroll 1
@@ -236,11 +245,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int col = cc + e;
-            const int tok = kv_i1 + col % p.kv.box1, view = kv_i3 + col / p.kv.box1;
             float s = __uint_as_float(v[g * 8 + e]) * p.scale_log2;
             if (BIAS) s += bvals[e] * LOG2E;
-            float pe = exp2f(s - m_new);
-            if (tok >= p.kv.d1 || view >= p.kv.ext3) pe = 0.f;
+            float pe = fast_exp2(s - m_new);
+            if (col >= limit) pe = 0.f;
             pv[e] = pe; l_tile += pe;
           }
           *reinterpret_cast<uint4*>(sP + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ (row & 7)) << 4)) =

@@ -56,8 +56,12 @@ template <int BN> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // epilogue staging: output columns leave in chunks of CH (one swizzle span wide) through 2 smem buffers
+  static constexpr int CH = (BN % 64 == 0) ? 64 : 32;
+  static constexpr int kStgBytes = 128 * CH * 2;
+  static constexpr int kBudget = 226 * 1024 - 2 * kStgBytes - 1024 - 256;
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStgBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
 };
@@ -66,12 +70,13 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW,
-                 const GemmConvParams p) {
+                 const __grid_constant__ CUtensorMap tmD, const GemmConvParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* stg = smem + C::kStages * C::kStageBytes;            // 2 staging buffers (1024-aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 2 * C::kStgBytes);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + C::kStages;         // [kStages]
   uint64_t* tfull = bars + 2 * C::kStages;     // [2]
@@ -82,7 +87,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmD);
     if (p.C2 > 0) tma_prefetch_desc(&tmA2);
     if (p.C3 > 0) tma_prefetch_desc(&tmA3);
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -162,19 +167,26 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // =============================== epilogue (warps 2..5) ===============================
+    // TMEM -> registers -> (bias / temb / activation / residual) -> bf16 -> swizzled smem -> TMA tensor store.
+    // The TMA store clips rows/columns outside the output tensor, which handles M/N tails and, through the
+    // shifted w coordinate, the cropped pano halo.
+    constexpr int CH = C::CH;
+    constexpr int QPR = CH / 8;                      // 16-byte chunks per staged row
     const int ew = warp & 3;                 // TMEM lane quarter this warp may read
     const int row = ew * 32 + lane;          // row inside the 128-row tile
+    const bool store_thread = (threadIdx.x == 64);
+    const uint32_t swz = (CH == 64) ? (row & 7) : ((row >> 1) & 3);
     int as = 0; uint32_t aphase = 0;
-    constexpr int NOUT = BN;                 // accumulator columns
+    uint32_t chunk_ctr = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
-      // ---- row mapping ----
+      // ---- row mapping (needed for the residual / per-image vector reads) ----
       bool valid; long long orow; int vec_idx;
+      int w0 = 0, h0 = 0, b0 = 0;
       if (p.conv) {
+        w0 = (m_blk % p.n_wt) * p.TW; h0 = ((m_blk / p.n_wt) % p.n_ht) * p.TH; b0 = (m_blk / (p.n_wt * p.n_ht)) * p.TB;
         const int tw = row % p.TW, th = (row / p.TW) % p.TH, tb = row / (p.TW * p.TH);
-        const int w = (m_blk % p.n_wt) * p.TW + tw;
-        const int h = ((m_blk / p.n_wt) % p.n_ht) * p.TH + th;
-        const int b = (m_blk / (p.n_wt * p.n_ht)) * p.TB + tb;
+        const int w = w0 + tw, h = h0 + th, b = b0 + tb;
         valid = (b < p.B) && (h < p.H) && (w >= p.crop) && (w < p.W - p.crop);
         orow = (static_cast<long long>(b) * p.Hout + h) * p.Wout + (w - p.crop);
         vec_idx = b;
@@ -182,105 +194,108 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int r = m_blk * BM + row;
         valid = r < p.M; orow = r; vec_idx = r;
       }
+      if (!valid) { orow = 0; vec_idx = 0; }
       const float* rv = (p.rowvec != nullptr)
                             ? p.rowvec + static_cast<long long>(vec_idx / p.rowvec_div) * p.rowvec_ld
                             : nullptr;
-      bf16* drow = p.D + orow * p.ldd;
-      const bf16* rrow = (p.resid != nullptr) ? p.resid + orow * p.ldr : nullptr;
+      const bf16* rrow = (p.resid != nullptr && valid) ? p.resid + orow * p.ldr : nullptr;
 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+      const int n_chunks = (p.act == 1) ? (BN / 2) / CH : BN / CH;
+      const int oc0 = (p.act == 1) ? n_blk * (BN / 2) : n_blk * BN;     // first OUTPUT column of this tile
 
-      if (p.act == 1) {
-        // GEGLU: accumulator columns [0,BN/2) are values, [BN/2,BN) the matching gates
-        constexpr int HALF = NOUT / 2;
-        const int oc0 = n_blk * HALF;
 #pragma unroll 1
-        for (int c = 0; c < HALF; c += 16) {
-          uint32_t va[16], vg[16];
-          tmem_ld_x16(t_acc + c, va);
-          tmem_ld_x16(t_acc + HALF + c, vg);
-          tmem_ld_wait();
-          const int col = oc0 + c;
-          if (valid && col < p.n_out) {
-            uint32_t o[8];
+      for (int ci = 0; ci < n_chunks; ++ci) {
+        uint8_t* buf = stg + (chunk_ctr & 1) * C::kStgBytes;
+        uint8_t* my = buf + row * (CH * 2);
+        const int ocol = oc0 + ci * CH;                 // output column of staged column 0
+        // the store that used this buffer two chunks ago must have finished reading it
+        if (store_thread) bulk_wait_read<1>();
+        named_bar_sync(1, 128);
+        if (ocol < p.n_out) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              float a0 = __uint_as_float(va[j]), a1 = __uint_as_float(va[j + 1]);
-              float g0 = __uint_as_float(vg[j]), g1 = __uint_as_float(vg[j + 1]);
-              if (p.bias) {
-                a0 += __bfloat162float(p.bias[n_blk * BN + c + j]);
-                a1 += __bfloat162float(p.bias[n_blk * BN + c + j + 1]);
-                g0 += __bfloat162float(p.bias[n_blk * BN + HALF + c + j]);
-                g1 += __bfloat162float(p.bias[n_blk * BN + HALF + c + j + 1]);
+          for (int hlf = 0; hlf < CH / 32; ++hlf) {
+            uint32_t v[32];
+            float f[32];
+            if (p.act == 1) {
+              uint32_t vg[32];
+              tmem_ld_x32(t_acc + ci * CH + hlf * 32, v);
+              tmem_ld_x32(t_acc + BN / 2 + ci * CH + hlf * 32, vg);
+              tmem_ld_wait();
+              const int wc = n_blk * BN + ci * CH + hlf * 32;     // packed weight/bias row of value column 0
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float a = __uint_as_float(v[j]), g = __uint_as_float(vg[j]);
+                if (p.bias) { a += __bfloat162float(p.bias[wc + j]); g += __bfloat162float(p.bias[wc + BN / 2 + j]); }
+                f[j] = a * gelu_erf(g);
               }
-              o[j / 2] = pack_bf16x2(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
+            } else {
+              tmem_ld_x32(t_acc + ci * CH + hlf * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int col = ocol + hlf * 32 + g * 8;
+                if (col < p.N) {
+                  if (p.bias) {
+                    const uint4 bb = *reinterpret_cast<const uint4*>(p.bias + col);
+                    float2 t0 = unpack_bf16x2(bb.x), t1 = unpack_bf16x2(bb.y), t2 = unpack_bf16x2(bb.z), t3 = unpack_bf16x2(bb.w);
+                    f[g * 8 + 0] += t0.x; f[g * 8 + 1] += t0.y; f[g * 8 + 2] += t1.x; f[g * 8 + 3] += t1.y;
+                    f[g * 8 + 4] += t2.x; f[g * 8 + 5] += t2.y; f[g * 8 + 6] += t3.x; f[g * 8 + 7] += t3.y;
+                  }
+                  if (rv) {
+                    const float4 r0 = *reinterpret_cast<const float4*>(rv + col);
+                    const float4 r1 = *reinterpret_cast<const float4*>(rv + col + 4);
+                    f[g * 8 + 0] += r0.x; f[g * 8 + 1] += r0.y; f[g * 8 + 2] += r0.z; f[g * 8 + 3] += r0.w;
+                    f[g * 8 + 4] += r1.x; f[g * 8 + 5] += r1.y; f[g * 8 + 6] += r1.z; f[g * 8 + 7] += r1.w;
+                  }
+                  if (p.act == 2) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[g * 8 + j] = gelu_erf(f[g * 8 + j]);
+                  } else if (p.act == 3) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[g * 8 + j] = silu(f[g * 8 + j]);
+                  }
+                  if (rrow) {
+                    const uint4 rr = *reinterpret_cast<const uint4*>(rrow + col);
+                    float2 t0 = unpack_bf16x2(rr.x), t1 = unpack_bf16x2(rr.y), t2 = unpack_bf16x2(rr.z), t3 = unpack_bf16x2(rr.w);
+                    f[g * 8 + 0] += t0.x; f[g * 8 + 1] += t0.y; f[g * 8 + 2] += t1.x; f[g * 8 + 3] += t1.y;
+                    f[g * 8 + 4] += t2.x; f[g * 8 + 5] += t2.y; f[g * 8 + 6] += t3.x; f[g * 8 + 7] += t3.y;
+                  }
+                }
+              }
             }
-            uint4* dst = reinterpret_cast<uint4*>(drow + col);
-            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-          }
-        }
-      } else {
-        const int oc0 = n_blk * BN;
-#pragma unroll 1
-        for (int c = 0; c < NOUT; c += 32) {
-          uint32_t v[32];
-          tmem_ld_x32(t_acc + c, v);
-          tmem_ld_wait();
-          if (valid) {
+            if (p.out_scale != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+            }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const int col = oc0 + c + g * 8;
-              if (col < p.N) {   // N is a multiple of 8 (checked on the host)
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-                if (p.bias) {
-                  const uint4 bb = *reinterpret_cast<const uint4*>(p.bias + col);
-                  float2 t0 = unpack_bf16x2(bb.x), t1 = unpack_bf16x2(bb.y);
-                  float2 t2 = unpack_bf16x2(bb.z), t3 = unpack_bf16x2(bb.w);
-                  f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
-                  f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
-                }
-                if (rv) {
-                  const float4 r0 = *reinterpret_cast<const float4*>(rv + col);
-                  const float4 r1 = *reinterpret_cast<const float4*>(rv + col + 4);
-                  f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-                  f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-                }
-                if (p.act == 2) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
-                } else if (p.act == 3) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = silu(f[j]);
-                }
-                if (rrow) {
-                  const uint4 rr = *reinterpret_cast<const uint4*>(rrow + col);
-                  float2 t0 = unpack_bf16x2(rr.x), t1 = unpack_bf16x2(rr.y);
-                  float2 t2 = unpack_bf16x2(rr.z), t3 = unpack_bf16x2(rr.w);
-                  f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
-                  f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
-                }
-                if (p.out_scale != 1.0f) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] *= p.out_scale;
-                }
-                *reinterpret_cast<uint4*>(drow + col) =
-                    make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                               pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-              }
+              const uint32_t q = static_cast<uint32_t>(hlf * 4 + g);
+              *reinterpret_cast<uint4*>(my + (((q ^ swz) & (QPR - 1)) << 4)) =
+                  make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
+                             pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
             }
           }
         }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (store_thread && ocol < p.n_out) {
+          if (p.conv) tma_store_4d(&tmD, buf, ocol, w0 - p.crop, h0, b0);
+          else        tma_store_2d(&tmD, buf, ocol, m_blk * BM);
+          bulk_commit();
+        }
+        ++chunk_ctr;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (store_thread) bulk_wait<0>();
   }
 
   tc_fence_before();
@@ -293,7 +308,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 template <int BN>
 static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3,
-                  const CUtensorMap& w, const GemmConvParams& p, cudaStream_t st) {
+                  const CUtensorMap& w, const CUtensorMap& d, const GemmConvParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -305,14 +320,14 @@ static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms()) grid = num_sms();
   if (grid <= 0) return I360_OK;
-  gemm_conv_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(a, a2, a3, w, p);
+  gemm_conv_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(a, a2, a3, w, d, p);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
 
 static int pick_bn(int N, int act) {
-  // GEGLU tiles need value/gate halves -> 256 (128 out cols) unless the problem is tiny
-  if (act == 1) return (N % 256 == 0) ? 256 : ((N % 160 == 0) ? 160 : ((N % 128 == 0) ? 128 : 64));
+  // GEGLU tiles hold [values | gates] halves that must be whole 64-column store chunks
+  if (act == 1) return (N % 256 == 0) ? 256 : 128;
   if (N <= 64) return 64;
   if (N <= 128) return 128;
   // minimise padded columns; prefer the wider tile on ties (better smem traffic per FLOP)
@@ -326,12 +341,12 @@ static int pick_bn(int N, int act) {
 }
 
 static int dispatch(int bn, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3,
-                    const CUtensorMap& w, const GemmConvParams& p, cudaStream_t st) {
+                    const CUtensorMap& w, const CUtensorMap& d, const GemmConvParams& p, cudaStream_t st) {
   switch (bn) {
-    case 64: return launch<64>(a, a2, a3, w, p, st);
-    case 128: return launch<128>(a, a2, a3, w, p, st);
-    case 160: return launch<160>(a, a2, a3, w, p, st);
-    case 256: return launch<256>(a, a2, a3, w, p, st);
+    case 64: return launch<64>(a, a2, a3, w, d, p, st);
+    case 128: return launch<128>(a, a2, a3, w, d, p, st);
+    case 160: return launch<160>(a, a2, a3, w, d, p, st);
+    case 256: return launch<256>(a, a2, a3, w, d, p, st);
   }
   return I360_ERR_ARG;
 }
@@ -351,9 +366,8 @@ extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long 
   if (!A || !W || !D || M <= 0 || N <= 0 || K <= 0) return I360_ERR_ARG;
   if ((K % 8) || (lda % 8) || (ldw % 8) || (ldd % 8) || (N % 8)) return I360_ERR_ARG;
   if (resid && (ldr % 8)) return I360_ERR_ARG;
-  if (act == 1 && (N % 2)) return I360_ERR_ARG;
+  if (act == 1 && (N % 128)) return I360_ERR_ARG;
   const int bn = pick_bn(N, act);
-  if (act == 1 && (N % bn)) return I360_ERR_ARG;
   GemmConvParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K; p.conv = 0;
@@ -370,7 +384,12 @@ extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long 
   uint32_t bW[2] = {BK, (uint32_t)bn};
   int r = get_tmap_bf16(&ta, A, 2, dA, sA, bA, 3); if (r) return r;
   r = get_tmap_bf16(&tw, W, 2, dW, sW, bW, 3); if (r) return r;
-  return dispatch(bn, ta, ta, ta, tw, p, static_cast<cudaStream_t>(stream));
+  const uint32_t ch = (bn % 64 == 0) ? 64 : 32;
+  CUtensorMap td;
+  uint64_t dD[2] = {(uint64_t)p.n_out, (uint64_t)M}; uint64_t sD[1] = {(uint64_t)ldd * 2};
+  uint32_t bD[2] = {ch, BM};
+  r = get_tmap_bf16(&td, D, 2, dD, sD, bD, ch == 64 ? 3 : 2); if (r) return r;
+  return dispatch(bn, ta, ta, ta, tw, td, p, static_cast<cudaStream_t>(stream));
 }
 
 // x: NHWC [B,H,W,Cin] (H,W include any materialised halo); Wt: [Cout, 9*Cin + C2 + C3] with the
@@ -428,5 +447,14 @@ extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, co
   uint64_t dW[2] = {(uint64_t)Ktot, (uint64_t)Cout}; uint64_t sW[1] = {(uint64_t)Ktot * 2};
   uint32_t bW[2] = {BK, (uint32_t)bn};
   r = get_tmap_bf16(&tw, Wt, 2, dW, sW, bW, 3); if (r) return r;
-  return dispatch(bn, ta, ta2, ta3, tw, p, static_cast<cudaStream_t>(stream));
+  const uint32_t ch = (bn % 64 == 0) ? 64 : 32;
+  CUtensorMap td;
+  {
+    const int Wo = W - 2 * crop;
+    uint64_t d[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)H, (uint64_t)B};
+    uint64_t s[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, (uint64_t)H * Wo * Cout * 2};
+    uint32_t b[4] = {ch, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
+    r = get_tmap_bf16(&td, D, 4, d, s, b, ch == 64 ? 3 : 2); if (r) return r;
+  }
+  return dispatch(bn, ta, ta2, ta3, tw, td, p, static_cast<cudaStream_t>(stream));
 }

@@ -48,5 +48,38 @@ if "conv" in sys.argv or len(sys.argv) == 1:
         ms = timeit(lambda: torch.nn.functional.conv2d(xn, wn, padding=1))
         rec(f"  cudnn conv {B}x{H}x{W} {Ci}->{Co}", ms, fl, 0)
         del x, w, wp, xn, wn
+if "attn" in sys.argv or len(sys.argv) == 1:
+    for (imgs, N, heads, hd) in [(32, 8192, 5, 64), (640, 1024, 5, 64), (32, 2048, 10, 64), (640, 256, 10, 64), (32, 512, 20, 64), (640, 64, 20, 64)]:
+        C = heads * hd
+        qkv = torch.randn(imgs * N, 3 * C, device="cuda").bfloat16()
+        out = torch.empty(imgs * N, C, device="cuda", dtype=torch.bfloat16)
+        fn = lambda: ops.attention(ops.seq_view(qkv, imgs, N, 0), ops.seq_view(qkv, imgs, N, C), ops.seq_view(qkv, imgs, N, 2 * C),
+                                   ops.seq_view(out, imgs, N), heads, hd, imgs)
+        ms = timeit(fn)
+        fl = 4.0 * imgs * heads * N * N * hd
+        rec(f"attn self imgs{imgs} N{N} h{heads} d{hd}", ms, fl, 2.0 * 4 * imgs * N * C)
+        q4 = qkv.view(imgs, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+        ms = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q4[0], q4[1], q4[2]))
+        rec(f"  torch sdpa imgs{imgs} N{N}", ms, fl, 0)
+        del qkv, out, q4
+    # WarpAttn level enc0: equi 2048 tokens <- 20 views x 256, heads 10 (C=320), hd 32, bias
+    b, Fr, m, hw, EN, heads, hd = 2, 16, 20, 256, 2048, 10, 32
+    C = heads * hd
+    pers_kv = torch.randn(b * m * Fr * hw, 2 * C, device="cuda").bfloat16()
+    equi = torch.randn(b * Fr * EN, C, device="cuda").bfloat16()
+    bias = torch.randn(EN, m * hw, device="cuda").bfloat16()
+    out = torch.empty_like(equi)
+    fn = lambda: ops.attention(ops.seq_view(equi, b * Fr, EN), ops.multiview_view(pers_kv, b, m, Fr, hw, 0),
+                               ops.multiview_view(pers_kv, b, m, Fr, hw, C), ops.seq_view(out, b * Fr, EN), heads, hd, b * Fr, bias=bias)
+    rec("attn warp equi<-pers enc0", timeit(fn), 4.0 * b * Fr * heads * EN * m * hw * hd, 0)
+if "norm" in sys.argv or len(sys.argv) == 1:
+    for (B, H, W, C) in [(640, 32, 32, 320), (32, 64, 128, 320), (640, 16, 16, 640), (640, 8, 8, 1280)]:
+        x = torch.randn(B, H, W, C, device="cuda").bfloat16()
+        g = torch.ones(C, device="cuda").bfloat16(); bta = torch.zeros(C, device="cuda").bfloat16()
+        ms = timeit(lambda: ops.groupnorm(x, g, bta, 32, 1e-5, True))
+        rec(f"groupnorm+silu {B}x{H}x{W}x{C}", ms, 0, 2.0 * 3 * x.numel())
+        ms = timeit(lambda: ops.layernorm(x.view(-1, C), g, bta))
+        rec(f"layernorm {B*H*W}x{C}", ms, 0, 2.0 * 2 * x.numel())
+        del x
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/microbench.json", "w"), indent=1)
