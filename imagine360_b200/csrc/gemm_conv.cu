@@ -11,8 +11,9 @@
 //               Up to two extra 1x1 sources are accumulated into the same tile (ResnetBlock's
 //               conv_shortcut over the un-normalised input / the skip-concat halves).
 //
-// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer (one elected
-// lane), warps 2..5 = epilogue (TMEM -> registers -> bias/temb/residual/GEGLU -> global).
+// Warp roles (320 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer (one elected
+// lane), warps 2..9 = two epilogue groups (TMEM -> registers -> bias/temb/residual/GEGLU -> bf16 ->
+// swizzled smem -> TMA tensor store), each group taking every other 64-column chunk of the tile.
 // Two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
 //
 // Replaces the reference's library calls: nn.Conv2d inside InflatedConv3d
@@ -50,7 +51,7 @@ struct GemmConvParams {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue (two groups of 4)
 
 template <int BN> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
@@ -91,7 +92,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.C2 > 0) tma_prefetch_desc(&tmA2);
     if (p.C3 > 0) tma_prefetch_desc(&tmA3);
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, C::kTmemCols); tmem_relinquish(); }
@@ -166,21 +167,25 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // =============================== epilogue (warps 2..5) ===============================
+    // =============================== epilogue (warps 2..9) ===============================
     // TMEM -> registers -> (bias / temb / activation / residual) -> bf16 -> swizzled smem -> TMA tensor store.
-    // The TMA store clips rows/columns outside the output tensor, which handles M/N tails and, through the
-    // shifted w coordinate, the cropped pano halo.
+    // The TMA store clips rows/columns outside the output tensor (M/N tails).  Tiles whose output is a cropped
+    // pano halo (crop > 0) would need a negative start coordinate, which TMA stores reject, so those rows are
+    // written with predicated 16-byte global stores instead.
     constexpr int CH = C::CH;
     constexpr int QPR = CH / 8;                      // 16-byte chunks per staged row
     const int ew = warp & 3;                 // TMEM lane quarter this warp may read
+    const int grp = (warp - 2) >> 2;         // epilogue group 0/1: chunks grp, grp+2, ...
     const int row = ew * 32 + lane;          // row inside the 128-row tile
-    const bool store_thread = (threadIdx.x == 64);
+    const bool store_thread = (lane == 0) && (warp == 2 || warp == 6);
+    const bool direct = p.conv && p.crop > 0;
     const uint32_t swz = (CH == 64) ? (row & 7) : ((row >> 1) & 3);
+    uint8_t* buf = stg + grp * C::kStgBytes;
+    uint8_t* my = buf + row * (CH * 2);
     int as = 0; uint32_t aphase = 0;
-    uint32_t chunk_ctr = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
-      // ---- row mapping (needed for the residual / per-image vector reads) ----
+      // ---- row mapping (residual / per-image vector reads, direct stores) ----
       bool valid; long long orow; int vec_idx;
       int w0 = 0, h0 = 0, b0 = 0;
       if (p.conv) {
@@ -199,6 +204,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             ? p.rowvec + static_cast<long long>(vec_idx / p.rowvec_div) * p.rowvec_ld
                             : nullptr;
       const bf16* rrow = (p.resid != nullptr && valid) ? p.resid + orow * p.ldr : nullptr;
+      bf16* drow = p.D + orow * p.ldd;
 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
@@ -207,38 +213,50 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int oc0 = (p.act == 1) ? n_blk * (BN / 2) : n_blk * BN;     // first OUTPUT column of this tile
 
 #pragma unroll 1
-      for (int ci = 0; ci < n_chunks; ++ci) {
-        uint8_t* buf = stg + (chunk_ctr & 1) * C::kStgBytes;
-        uint8_t* my = buf + row * (CH * 2);
+      for (int ci = grp; ci < n_chunks; ci += 2) {
         const int ocol = oc0 + ci * CH;                 // output column of staged column 0
-        // the store that used this buffer two chunks ago must have finished reading it
-        if (store_thread) bulk_wait_read<1>();
-        named_bar_sync(1, 128);
-        if (ocol < p.n_out) {
+        const bool live = ocol < p.n_out;
+        if (!direct) {
+          if (store_thread) bulk_wait_read<0>();        // this group's previous store has finished reading the buffer
+          named_bar_sync(1 + grp, 128);
+        }
+        if (live) {
 #pragma unroll
-          for (int hlf = 0; hlf < CH / 32; ++hlf) {
-            uint32_t v[32];
-            float f[32];
+          for (int u = 0; u < CH / 16; ++u) {
+            uint32_t v[16];
+            float f[16];
             if (p.act == 1) {
-              uint32_t vg[32];
-              tmem_ld_x32(t_acc + ci * CH + hlf * 32, v);
-              tmem_ld_x32(t_acc + BN / 2 + ci * CH + hlf * 32, vg);
+              uint32_t vg[16];
+              tmem_ld_x16(t_acc + ci * CH + u * 16, v);
+              tmem_ld_x16(t_acc + BN / 2 + ci * CH + u * 16, vg);
               tmem_ld_wait();
-              const int wc = n_blk * BN + ci * CH + hlf * 32;     // packed weight/bias row of value column 0
+              const int wc = n_blk * BN + ci * CH + u * 16;     // packed weight/bias row of value column 0
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float a = __uint_as_float(v[j]), g = __uint_as_float(vg[j]);
-                if (p.bias) { a += __bfloat162float(p.bias[wc + j]); g += __bfloat162float(p.bias[wc + BN / 2 + j]); }
-                f[j] = a * gelu_erf(g);
+              for (int h8 = 0; h8 < 2; ++h8) {
+                float ba[8], bg[8];
+                if (p.bias) {
+                  const uint4 x = *reinterpret_cast<const uint4*>(p.bias + wc + h8 * 8);
+                  const uint4 y = *reinterpret_cast<const uint4*>(p.bias + wc + BN / 2 + h8 * 8);
+                  float2 t0 = unpack_bf16x2(x.x), t1 = unpack_bf16x2(x.y), t2 = unpack_bf16x2(x.z), t3 = unpack_bf16x2(x.w);
+                  ba[0] = t0.x; ba[1] = t0.y; ba[2] = t1.x; ba[3] = t1.y; ba[4] = t2.x; ba[5] = t2.y; ba[6] = t3.x; ba[7] = t3.y;
+                  t0 = unpack_bf16x2(y.x); t1 = unpack_bf16x2(y.y); t2 = unpack_bf16x2(y.z); t3 = unpack_bf16x2(y.w);
+                  bg[0] = t0.x; bg[1] = t0.y; bg[2] = t1.x; bg[3] = t1.y; bg[4] = t2.x; bg[5] = t2.y; bg[6] = t3.x; bg[7] = t3.y;
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) { ba[j] = 0.f; bg[j] = 0.f; }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  f[h8 * 8 + j] = (__uint_as_float(v[h8 * 8 + j]) + ba[j]) * gelu_erf(__uint_as_float(vg[h8 * 8 + j]) + bg[j]);
               }
             } else {
-              tmem_ld_x32(t_acc + ci * CH + hlf * 32, v);
+              tmem_ld_x16(t_acc + ci * CH + u * 16, v);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int col = ocol + hlf * 32 + g * 8;
+              for (int g = 0; g < 2; ++g) {
+                const int col = ocol + u * 16 + g * 8;
                 if (col < p.N) {
                   if (p.bias) {
                     const uint4 bb = *reinterpret_cast<const uint4*>(p.bias + col);
@@ -270,25 +288,31 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (p.out_scale != 1.0f) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+              for (int j = 0; j < 16; ++j) f[j] *= p.out_scale;
             }
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t q = static_cast<uint32_t>(hlf * 4 + g);
-              *reinterpret_cast<uint4*>(my + (((q ^ swz) & (QPR - 1)) << 4)) =
-                  make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
-                             pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
+            for (int g = 0; g < 2; ++g) {
+              const uint4 packed = make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
+                                              pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
+              if (direct) {
+                const int col = ocol + u * 16 + g * 8;
+                if (valid && col < p.n_out) *reinterpret_cast<uint4*>(drow + col) = packed;
+              } else {
+                const uint32_t q = static_cast<uint32_t>(u * 2 + g);
+                *reinterpret_cast<uint4*>(my + (((q ^ swz) & (QPR - 1)) << 4)) = packed;
+              }
             }
           }
         }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (store_thread && ocol < p.n_out) {
-          if (p.conv) tma_store_4d(&tmD, buf, ocol, w0 - p.crop, h0, b0);
-          else        tma_store_2d(&tmD, buf, ocol, m_blk * BM);
-          bulk_commit();
+        if (!direct) {
+          fence_proxy_async_smem();
+          named_bar_sync(1 + grp, 128);
+          if (store_thread && live) {
+            if (p.conv) tma_store_4d(&tmD, buf, ocol, w0, h0, b0);
+            else        tma_store_2d(&tmD, buf, ocol, m_blk * BM);
+            bulk_commit();
+          }
         }
-        ++chunk_ctr;
       }
       tc_fence_before();
       __syncwarp();
