@@ -57,17 +57,23 @@ template <int BN> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // epilogue staging: output columns leave in chunks of CH (one swizzle span wide) through 2 smem buffers
-  static constexpr int CH = (BN % 64 == 0) ? 64 : 32;
+  // epilogue staging: output columns leave in 32-column chunks (64-byte rows, 64B swizzle) through 2 smem
+  // buffers per epilogue group
+  static constexpr int CH = 32;
   static constexpr int kStgBytes = 128 * CH * 2;
-  static constexpr int kBudget = 226 * 1024 - 2 * kStgBytes - 1024 - 256;
+  static constexpr int kNumStg = 4;
+  static constexpr int kBudget = 226 * 1024 - kNumStg * kStgBytes - 1024 - 256;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStgBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNumStg * kStgBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
 };
 
-template <int BN>
+// Epilogue flavours (compile-time: the epilogue is the critical path of the small-K layers, and one generic,
+// runtime-branchy version thrashes the instruction cache)
+enum : int { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_RESID = 2, EPI_ROWVEC = 3, EPI_ACT = 4, EPI_GENERAL = 5 };
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW,
@@ -77,7 +83,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* stg = smem + C::kStages * C::kStageBytes;            // 2 staging buffers (1024-aligned)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 2 * C::kStgBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + C::kNumStg * C::kStgBytes);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + C::kStages;         // [kStages]
   uint64_t* tfull = bars + 2 * C::kStages;     // [2]
@@ -169,107 +175,111 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // =============================== epilogue (warps 2..9) ===============================
     // TMEM -> registers -> (bias / temb / activation / residual) -> bf16 -> swizzled smem -> TMA tensor store.
-    // The TMA store clips rows/columns outside the output tensor (M/N tails).  Tiles whose output is a cropped
-    // pano halo (crop > 0) would need a negative start coordinate, which TMA stores reject, so those rows are
-    // written with predicated 16-byte global stores instead.
+    // Two groups of 4 warps take alternate 32-column chunks; each group double-buffers its staging tile and
+    // needs ONE named barrier per chunk: the group's store thread waits (before that barrier) until the store
+    // issued one chunk earlier has finished reading, so after the barrier everybody may overwrite that buffer.
+    // The TMA store clips rows/columns outside the output tensor (M/N tails).  Cropped pano tiles (crop > 0)
+    // would need a negative start coordinate, which TMA stores reject: those use predicated global stores.
     constexpr int CH = C::CH;
-    constexpr int QPR = CH / 8;                      // 16-byte chunks per staged row
+    constexpr bool kGeglu = (EPI == EPI_GEGLU);
+    constexpr bool kResid = (EPI == EPI_RESID) || (EPI == EPI_GENERAL);
+    constexpr bool kRowvec = (EPI == EPI_ROWVEC) || (EPI == EPI_GENERAL);
+    constexpr bool kAct = (EPI == EPI_ACT) || (EPI == EPI_GENERAL);
     const int ew = warp & 3;                 // TMEM lane quarter this warp may read
     const int grp = (warp - 2) >> 2;         // epilogue group 0/1: chunks grp, grp+2, ...
     const int row = ew * 32 + lane;          // row inside the 128-row tile
     const bool store_thread = (lane == 0) && (warp == 2 || warp == 6);
     const bool direct = p.conv && p.crop > 0;
-    const uint32_t swz = (CH == 64) ? (row & 7) : ((row >> 1) & 3);
-    uint8_t* buf = stg + grp * C::kStgBytes;
-    uint8_t* my = buf + row * (CH * 2);
+    const uint32_t swz = (row >> 1) & 3;     // 64B swizzle: 16-byte chunk index ^= address bits [7,9)
+    uint8_t* gbuf = stg + grp * 2 * C::kStgBytes;
+    uint32_t kchunk = 0;                     // chunks issued by this group so far (buffer parity)
     int as = 0; uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
       // ---- row mapping (residual / per-image vector reads, direct stores) ----
-      bool valid; long long orow; int vec_idx;
+      bool valid = true; long long orow = 0; int vec_idx = 0;
       int w0 = 0, h0 = 0, b0 = 0;
       if (p.conv) {
         w0 = (m_blk % p.n_wt) * p.TW; h0 = ((m_blk / p.n_wt) % p.n_ht) * p.TH; b0 = (m_blk / (p.n_wt * p.n_ht)) * p.TB;
-        const int tw = row % p.TW, th = (row / p.TW) % p.TH, tb = row / (p.TW * p.TH);
-        const int w = w0 + tw, h = h0 + th, b = b0 + tb;
-        valid = (b < p.B) && (h < p.H) && (w >= p.crop) && (w < p.W - p.crop);
-        orow = (static_cast<long long>(b) * p.Hout + h) * p.Wout + (w - p.crop);
-        vec_idx = b;
+        if (kResid || kRowvec || direct) {
+          const int tw = row % p.TW, th = (row / p.TW) % p.TH, tb = row / (p.TW * p.TH);
+          const int w = w0 + tw, h = h0 + th, b = b0 + tb;
+          valid = (b < p.B) && (h < p.H) && (w >= p.crop) && (w < p.W - p.crop);
+          orow = (static_cast<long long>(b) * p.Hout + h) * p.Wout + (w - p.crop);
+          vec_idx = b;
+        }
       } else {
         const int r = m_blk * BM + row;
         valid = r < p.M; orow = r; vec_idx = r;
       }
       if (!valid) { orow = 0; vec_idx = 0; }
-      const float* rv = (p.rowvec != nullptr)
-                            ? p.rowvec + static_cast<long long>(vec_idx / p.rowvec_div) * p.rowvec_ld
-                            : nullptr;
-      const bf16* rrow = (p.resid != nullptr && valid) ? p.resid + orow * p.ldr : nullptr;
+      const float* rv = (kRowvec && p.rowvec != nullptr)
+                            ? p.rowvec + static_cast<long long>(vec_idx / p.rowvec_div) * p.rowvec_ld : nullptr;
+      const bf16* rrow = (kResid && p.resid != nullptr && valid) ? p.resid + orow * p.ldr : nullptr;
       bf16* drow = p.D + orow * p.ldd;
 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
-      const int n_chunks = (p.act == 1) ? (BN / 2) / CH : BN / CH;
-      const int oc0 = (p.act == 1) ? n_blk * (BN / 2) : n_blk * BN;     // first OUTPUT column of this tile
+      constexpr int n_chunks = kGeglu ? (BN / 2) / CH : BN / CH;
+      const int oc0 = kGeglu ? n_blk * (BN / 2) : n_blk * BN;     // first OUTPUT column of this tile
 
 #pragma unroll 1
       for (int ci = grp; ci < n_chunks; ci += 2) {
         const int ocol = oc0 + ci * CH;                 // output column of staged column 0
         const bool live = ocol < p.n_out;
-        if (!direct) {
-          if (store_thread) bulk_wait_read<0>();        // this group's previous store has finished reading the buffer
-          named_bar_sync(1 + grp, 128);
-        }
+        uint8_t* buf = gbuf + (kchunk & 1) * C::kStgBytes;
+        uint8_t* my = buf + row * (CH * 2);
+        float f[32];
         if (live) {
+          uint32_t v[32];
+          tmem_ld_x16(t_acc + ci * CH, v);
+          tmem_ld_x16(t_acc + ci * CH + 16, v + 16);
+          if (kGeglu) {
+            uint32_t vg[32];
+            tmem_ld_x16(t_acc + BN / 2 + ci * CH, vg);
+            tmem_ld_x16(t_acc + BN / 2 + ci * CH + 16, vg + 16);
+            tmem_ld_wait();
+            const int wc = n_blk * BN + ci * CH;          // packed weight/bias row of value column 0
 #pragma unroll
-          for (int u = 0; u < CH / 16; ++u) {
-            uint32_t v[16];
-            float f[16];
-            if (p.act == 1) {
-              uint32_t vg[16];
-              tmem_ld_x16(t_acc + ci * CH + u * 16, v);
-              tmem_ld_x16(t_acc + BN / 2 + ci * CH + u * 16, vg);
-              tmem_ld_wait();
-              const int wc = n_blk * BN + ci * CH + u * 16;     // packed weight/bias row of value column 0
+            for (int g = 0; g < 4; ++g) {
+              float ba[8], bg[8];
+              if (p.bias) {
+                const uint4 x = *reinterpret_cast<const uint4*>(p.bias + wc + g * 8);
+                const uint4 y = *reinterpret_cast<const uint4*>(p.bias + wc + BN / 2 + g * 8);
+                float2 t0 = unpack_bf16x2(x.x), t1 = unpack_bf16x2(x.y), t2 = unpack_bf16x2(x.z), t3 = unpack_bf16x2(x.w);
+                ba[0] = t0.x; ba[1] = t0.y; ba[2] = t1.x; ba[3] = t1.y; ba[4] = t2.x; ba[5] = t2.y; ba[6] = t3.x; ba[7] = t3.y;
+                t0 = unpack_bf16x2(y.x); t1 = unpack_bf16x2(y.y); t2 = unpack_bf16x2(y.z); t3 = unpack_bf16x2(y.w);
+                bg[0] = t0.x; bg[1] = t0.y; bg[2] = t1.x; bg[3] = t1.y; bg[4] = t2.x; bg[5] = t2.y; bg[6] = t3.x; bg[7] = t3.y;
+              } else {
 #pragma unroll
-              for (int h8 = 0; h8 < 2; ++h8) {
-                float ba[8], bg[8];
-                if (p.bias) {
-                  const uint4 x = *reinterpret_cast<const uint4*>(p.bias + wc + h8 * 8);
-                  const uint4 y = *reinterpret_cast<const uint4*>(p.bias + wc + BN / 2 + h8 * 8);
-                  float2 t0 = unpack_bf16x2(x.x), t1 = unpack_bf16x2(x.y), t2 = unpack_bf16x2(x.z), t3 = unpack_bf16x2(x.w);
-                  ba[0] = t0.x; ba[1] = t0.y; ba[2] = t1.x; ba[3] = t1.y; ba[4] = t2.x; ba[5] = t2.y; ba[6] = t3.x; ba[7] = t3.y;
-                  t0 = unpack_bf16x2(y.x); t1 = unpack_bf16x2(y.y); t2 = unpack_bf16x2(y.z); t3 = unpack_bf16x2(y.w);
-                  bg[0] = t0.x; bg[1] = t0.y; bg[2] = t1.x; bg[3] = t1.y; bg[4] = t2.x; bg[5] = t2.y; bg[6] = t3.x; bg[7] = t3.y;
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) { ba[j] = 0.f; bg[j] = 0.f; }
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  f[h8 * 8 + j] = (__uint_as_float(v[h8 * 8 + j]) + ba[j]) * gelu_erf(__uint_as_float(vg[h8 * 8 + j]) + bg[j]);
+                for (int j = 0; j < 8; ++j) { ba[j] = 0.f; bg[j] = 0.f; }
               }
-            } else {
-              tmem_ld_x16(t_acc + ci * CH + u * 16, v);
-              tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+              for (int j = 0; j < 8; ++j)
+                f[g * 8 + j] = (__uint_as_float(v[g * 8 + j]) + ba[j]) * gelu_erf(__uint_as_float(vg[g * 8 + j]) + bg[j]);
+            }
+          } else {
+            tmem_ld_wait();
 #pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                const int col = ocol + u * 16 + g * 8;
-                if (col < p.N) {
-                  if (p.bias) {
-                    const uint4 bb = *reinterpret_cast<const uint4*>(p.bias + col);
-                    float2 t0 = unpack_bf16x2(bb.x), t1 = unpack_bf16x2(bb.y), t2 = unpack_bf16x2(bb.z), t3 = unpack_bf16x2(bb.w);
-                    f[g * 8 + 0] += t0.x; f[g * 8 + 1] += t0.y; f[g * 8 + 2] += t1.x; f[g * 8 + 3] += t1.y;
-                    f[g * 8 + 4] += t2.x; f[g * 8 + 5] += t2.y; f[g * 8 + 6] += t3.x; f[g * 8 + 7] += t3.y;
-                  }
-                  if (rv) {
-                    const float4 r0 = *reinterpret_cast<const float4*>(rv + col);
-                    const float4 r1 = *reinterpret_cast<const float4*>(rv + col + 4);
-                    f[g * 8 + 0] += r0.x; f[g * 8 + 1] += r0.y; f[g * 8 + 2] += r0.z; f[g * 8 + 3] += r0.w;
-                    f[g * 8 + 4] += r1.x; f[g * 8 + 5] += r1.y; f[g * 8 + 6] += r1.z; f[g * 8 + 7] += r1.w;
-                  }
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = ocol + g * 8;
+              if (col < p.N) {
+                if (p.bias) {
+                  const uint4 bb = *reinterpret_cast<const uint4*>(p.bias + col);
+                  float2 t0 = unpack_bf16x2(bb.x), t1 = unpack_bf16x2(bb.y), t2 = unpack_bf16x2(bb.z), t3 = unpack_bf16x2(bb.w);
+                  f[g * 8 + 0] += t0.x; f[g * 8 + 1] += t0.y; f[g * 8 + 2] += t1.x; f[g * 8 + 3] += t1.y;
+                  f[g * 8 + 4] += t2.x; f[g * 8 + 5] += t2.y; f[g * 8 + 6] += t3.x; f[g * 8 + 7] += t3.y;
+                }
+                if (kRowvec && rv) {
+                  const float4 r0 = *reinterpret_cast<const float4*>(rv + col);
+                  const float4 r1 = *reinterpret_cast<const float4*>(rv + col + 4);
+                  f[g * 8 + 0] += r0.x; f[g * 8 + 1] += r0.y; f[g * 8 + 2] += r0.z; f[g * 8 + 3] += r0.w;
+                  f[g * 8 + 4] += r1.x; f[g * 8 + 5] += r1.y; f[g * 8 + 6] += r1.z; f[g * 8 + 7] += r1.w;
+                }
+                if (kAct) {
                   if (p.act == 2) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[g * 8 + j] = gelu_erf(f[g * 8 + j]);
@@ -277,41 +287,42 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[g * 8 + j] = silu(f[g * 8 + j]);
                   }
-                  if (rrow) {
-                    const uint4 rr = *reinterpret_cast<const uint4*>(rrow + col);
-                    float2 t0 = unpack_bf16x2(rr.x), t1 = unpack_bf16x2(rr.y), t2 = unpack_bf16x2(rr.z), t3 = unpack_bf16x2(rr.w);
-                    f[g * 8 + 0] += t0.x; f[g * 8 + 1] += t0.y; f[g * 8 + 2] += t1.x; f[g * 8 + 3] += t1.y;
-                    f[g * 8 + 4] += t2.x; f[g * 8 + 5] += t2.y; f[g * 8 + 6] += t3.x; f[g * 8 + 7] += t3.y;
-                  }
+                }
+                if (kResid && rrow) {
+                  const uint4 rr = *reinterpret_cast<const uint4*>(rrow + col);
+                  float2 t0 = unpack_bf16x2(rr.x), t1 = unpack_bf16x2(rr.y), t2 = unpack_bf16x2(rr.z), t3 = unpack_bf16x2(rr.w);
+                  f[g * 8 + 0] += t0.x; f[g * 8 + 1] += t0.y; f[g * 8 + 2] += t1.x; f[g * 8 + 3] += t1.y;
+                  f[g * 8 + 4] += t2.x; f[g * 8 + 5] += t2.y; f[g * 8 + 6] += t3.x; f[g * 8 + 7] += t3.y;
                 }
               }
             }
-            if (p.out_scale != 1.0f) {
+          }
+          if (p.out_scale != 1.0f) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] *= p.out_scale;
-            }
+            for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+          }
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const uint4 packed = make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
-                                              pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
-              if (direct) {
-                const int col = ocol + u * 16 + g * 8;
-                if (valid && col < p.n_out) *reinterpret_cast<uint4*>(drow + col) = packed;
-              } else {
-                const uint32_t q = static_cast<uint32_t>(u * 2 + g);
-                *reinterpret_cast<uint4*>(my + (((q ^ swz) & (QPR - 1)) << 4)) = packed;
-              }
+          for (int g = 0; g < 4; ++g) {
+            const uint4 packed = make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
+                                            pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
+            if (direct) {
+              const int col = ocol + g * 8;
+              if (valid && col < p.n_out) *reinterpret_cast<uint4*>(drow + col) = packed;
+            } else {
+              *reinterpret_cast<uint4*>(my + ((static_cast<uint32_t>(g) ^ swz) << 4)) = packed;
             }
           }
         }
         if (!direct) {
           fence_proxy_async_smem();
+          if (store_thread) bulk_wait_read<0>();     // the store of the previous chunk (other buffer) is done reading
           named_bar_sync(1 + grp, 128);
           if (store_thread && live) {
             if (p.conv) tma_store_4d(&tmD, buf, ocol, w0, h0, b0);
             else        tma_store_2d(&tmD, buf, ocol, m_blk * BM);
             bulk_commit();
           }
+          ++kchunk;
         }
       }
       tc_fence_before();
@@ -330,13 +341,13 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int EPI>
 static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3,
                   const CUtensorMap& w, const CUtensorMap& d, const GemmConvParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_conv_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              C::kSmemBytes) != cudaSuccess)
       return I360_ERR_CUDA;
     attr_set = true;
@@ -344,7 +355,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms()) grid = num_sms();
   if (grid <= 0) return I360_OK;
-  gemm_conv_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(a, a2, a3, w, d, p);
+  gemm_conv_kernel<BN, EPI><<<grid, kThreads, C::kSmemBytes, st>>>(a, a2, a3, w, d, p);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -364,13 +375,36 @@ static int pick_bn(int N, int act) {
   return best;
 }
 
+static int pick_epi(const GemmConvParams& p) {
+  if (p.act == 1) return EPI_GEGLU;
+  const bool r = p.resid != nullptr, v = p.rowvec != nullptr, a = p.act != 0;
+  if (!r && !v && !a) return EPI_PLAIN;
+  if (r && !v && !a) return EPI_RESID;
+  if (!r && v && !a) return EPI_ROWVEC;
+  if (!r && !v && a) return EPI_ACT;
+  return EPI_GENERAL;
+}
+
+template <int BN>
+static int dispatch_epi(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3, const CUtensorMap& w,
+                        const CUtensorMap& d, const GemmConvParams& p, cudaStream_t st) {
+  switch (pick_epi(p)) {
+    case EPI_PLAIN: return launch<BN, EPI_PLAIN>(a, a2, a3, w, d, p, st);
+    case EPI_GEGLU: return launch<BN, EPI_GEGLU>(a, a2, a3, w, d, p, st);
+    case EPI_RESID: return launch<BN, EPI_RESID>(a, a2, a3, w, d, p, st);
+    case EPI_ROWVEC: return launch<BN, EPI_ROWVEC>(a, a2, a3, w, d, p, st);
+    case EPI_ACT: return launch<BN, EPI_ACT>(a, a2, a3, w, d, p, st);
+    default: return launch<BN, EPI_GENERAL>(a, a2, a3, w, d, p, st);
+  }
+}
+
 static int dispatch(int bn, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3,
                     const CUtensorMap& w, const CUtensorMap& d, const GemmConvParams& p, cudaStream_t st) {
   switch (bn) {
-    case 64: return launch<64>(a, a2, a3, w, d, p, st);
-    case 128: return launch<128>(a, a2, a3, w, d, p, st);
-    case 160: return launch<160>(a, a2, a3, w, d, p, st);
-    case 256: return launch<256>(a, a2, a3, w, d, p, st);
+    case 64: return dispatch_epi<64>(a, a2, a3, w, d, p, st);
+    case 128: return dispatch_epi<128>(a, a2, a3, w, d, p, st);
+    case 160: return dispatch_epi<160>(a, a2, a3, w, d, p, st);
+    case 256: return dispatch_epi<256>(a, a2, a3, w, d, p, st);
   }
   return I360_ERR_ARG;
 }
@@ -391,6 +425,7 @@ extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long 
   if ((K % 8) || (lda % 8) || (ldw % 8) || (ldd % 8) || (N % 8)) return I360_ERR_ARG;
   if (resid && (ldr % 8)) return I360_ERR_ARG;
   if (act == 1 && (N % 128)) return I360_ERR_ARG;
+  if (act == 1 && (resid || rowvec)) return I360_ERR_UNSUPPORTED;
   const int bn = pick_bn(N, act);
   GemmConvParams p;
   memset(&p, 0, sizeof(p));
@@ -408,11 +443,10 @@ extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long 
   uint32_t bW[2] = {BK, (uint32_t)bn};
   int r = get_tmap_bf16(&ta, A, 2, dA, sA, bA, 3); if (r) return r;
   r = get_tmap_bf16(&tw, W, 2, dW, sW, bW, 3); if (r) return r;
-  const uint32_t ch = (bn % 64 == 0) ? 64 : 32;
   CUtensorMap td;
   uint64_t dD[2] = {(uint64_t)p.n_out, (uint64_t)M}; uint64_t sD[1] = {(uint64_t)ldd * 2};
-  uint32_t bD[2] = {ch, BM};
-  r = get_tmap_bf16(&td, D, 2, dD, sD, bD, ch == 64 ? 3 : 2); if (r) return r;
+  uint32_t bD[2] = {32, BM};
+  r = get_tmap_bf16(&td, D, 2, dD, sD, bD, 2); if (r) return r;
   return dispatch(bn, ta, ta, ta, tw, td, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -471,14 +505,13 @@ extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, co
   uint64_t dW[2] = {(uint64_t)Ktot, (uint64_t)Cout}; uint64_t sW[1] = {(uint64_t)Ktot * 2};
   uint32_t bW[2] = {BK, (uint32_t)bn};
   r = get_tmap_bf16(&tw, Wt, 2, dW, sW, bW, 3); if (r) return r;
-  const uint32_t ch = (bn % 64 == 0) ? 64 : 32;
   CUtensorMap td;
   {
     const int Wo = W - 2 * crop;
     uint64_t d[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)H, (uint64_t)B};
     uint64_t s[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, (uint64_t)H * Wo * Cout * 2};
-    uint32_t b[4] = {ch, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
-    r = get_tmap_bf16(&td, D, 4, d, s, b, ch == 64 ? 3 : 2); if (r) return r;
+    uint32_t b[4] = {32, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
+    r = get_tmap_bf16(&td, D, 4, d, s, b, 2); if (r) return r;
   }
   return dispatch(bn, ta, ta2, ta3, tw, td, p, static_cast<cudaStream_t>(stream));
 }

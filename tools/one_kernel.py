@@ -1,0 +1,26 @@
+"""Launch one kernel shape a few times (for ncu captures).  usage: one_kernel.py gemm M N K [act] | attn imgs N heads hd | conv B H W Ci Co"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from imagine360_b200 import ops
+kind = sys.argv[1]
+a = [int(x) for x in sys.argv[2:]]
+torch.manual_seed(0)
+if kind == "gemm":
+    M, N, K = a[:3]; act = a[3] if len(a) > 3 else 0
+    x = torch.randn(M, K, device="cuda").bfloat16(); w = torch.randn(N, K, device="cuda").bfloat16()
+    out = torch.empty(M, N // 2 if act == 1 else N, device="cuda", dtype=torch.bfloat16)
+    fn = lambda: ops.gemm(x, w, act=act, out=out)
+elif kind == "attn":
+    imgs, N, heads, hd = a
+    C = heads * hd
+    qkv = torch.randn(imgs * N, 3 * C, device="cuda").bfloat16(); out = torch.empty(imgs * N, C, device="cuda", dtype=torch.bfloat16)
+    fn = lambda: ops.attention(ops.seq_view(qkv, imgs, N, 0), ops.seq_view(qkv, imgs, N, C), ops.seq_view(qkv, imgs, N, 2 * C),
+                               ops.seq_view(out, imgs, N), heads, hd, imgs)
+elif kind == "conv":
+    B, H, W, Ci, Co = a
+    x = torch.randn(B, H, W, Ci, device="cuda").bfloat16(); wp = ops.pack_conv3x3(torch.randn(Co, Ci, 3, 3, device="cuda").bfloat16())
+    fn = lambda: ops.conv3x3(x, wp)
+for _ in range(4):
+    fn()
+torch.cuda.synchronize()
