@@ -188,6 +188,32 @@ def run_native(args, size, rank, world, device):
     return res
 
 
+def vae_decode_roofline(device, frames=16, latent_hw=(64, 136)):
+    """VAE decode of the circular-padded latent (pipeline...dual.py:811-815): configs[3]'s extra stage.  Reported next to
+    the loop metric with BOTH rooflines: 5.43 TFLOP and 7.2 GB algorithmic traffic per 512x1088 frame."""
+    from imagine360_b200.host.config import FULL_VAE_KWARGS
+    from imagine360_b200.host.pipeline import random_init_
+    from imagine360_b200.host.vae import AutoencoderKL
+    with torch.device(device):
+        vae = AutoencoderKL(**FULL_VAE_KWARGS).to(torch.bfloat16)
+    z = torch.randn(frames, 4, *latent_hw, device=device).to(torch.bfloat16)
+    for _ in range(2):
+        vae.decode(z[:4])
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(0, frames, 4):
+        vae.decode(z[i:i + 4])
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / frames
+    pk = peaks()
+    scale = (latent_hw[0] * latent_hw[1]) / (64 * 136)
+    fl, by = 5.43e12 * scale, 7.2e9 * scale
+    return {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "tflops": fl / ms / 1e9, "tensor_frac": fl / ms / 1e9 / pk["tflops"],
+            "alg_gbs": by / ms / 1e6, "hbm_frac": by / ms / 1e6 / pk["hbm_gbs"], "alg_flops_per_frame": fl, "alg_bytes_per_frame": by}
+
+
 def kernel_roofline(pipe, inp, size, one_step):
     """Per-kernel device time of ONE more step, measured live with CUDA events around every C-ABI launch on the
     launching stream (torch's current stream).  The dominant kernel is the tcgen05 GEMM / implicit-GEMM conv engine
@@ -348,6 +374,9 @@ def main():
         if world > 1:
             torch.distributed.destroy_process_group()
         return
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "bench_breakdown.json"), "w") as f:
+        json.dump({"breakdown": r.get("breakdown"), "roofline": r.get("roofline"), "ms_per_step": r["ms"]}, f, indent=1)
     fps = world * size["frames"] / (STEPS_PER_CLIP * r["ms"] * 1e-3)
     fps_e2e = world * size["frames"] / (STEPS_PER_CLIP * r["ms_e2e"] * 1e-3)
     out = {"metric": "denoised-frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -356,6 +385,13 @@ def main():
            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                    "ms_per_step": r["ms_e2e"]},
            "roofline": r.get("roofline"), "step_tflops": (size["step_flops"] or 0) / (r["ms"] * 1e-3) / 1e12}
+    if world == 1 and args.size == "c3":
+        del r
+        torch.cuda.empty_cache()
+        try:
+            out["vae_decode"] = vae_decode_roofline(device)
+        except Exception as ex:  # keep the headline line even if the side measurement fails
+            out["vae_decode"] = {"error": repr(ex)}
     if not args.no_cpu_baseline and world == 1:
         run, flops, sample = cpu_sample_step()
         sec = run()
@@ -363,9 +399,6 @@ def main():
                                "sample": sample, "sample_flops": flops, "sample_seconds": sec}
     else:
         out["cpu_baseline"] = None
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "bench_breakdown.json"), "w") as f:
-        json.dump({"breakdown": r.get("breakdown"), "roofline": r.get("roofline"), "ms_per_step": r["ms"]}, f, indent=1)
     print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -56,10 +56,85 @@ struct AttnCfg {
   static constexpr int kTmemCols = 256;   // S: 128, O: HD
 };
 
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// One KV tile of the online softmax for one query row (= one thread): two passes over the 128 fp32 logits in
+// TMEM.  Pass 1 reduces the row maximum; pass 2 evaluates p = exp2(s*scale - m) with one packed FFMA2 per two
+// logits, accumulates the row sum with FADD2 and writes bf16 P into the 128B-swizzled smem tile that is the A
+// operand of the P.V MMA.  MASKED (partial tiles) and BIAS (WarpAttn) are compile-time so the common case -- a
+// full, unbiased tile of the spatial self-attention -- carries no selects and no per-element scale multiply.
+template <bool BIAS, bool MASKED>
+__device__ __forceinline__ void softmax_tile(uint32_t tS_row, const uint8_t* sB, uint8_t* sP, int row, int limit,
+                                             float scale_log2, float& m_run, float& l_run, float& alpha) {
+  const float LOG2E = 1.4426950408889634f;
+  const uint32_t rsw = static_cast<uint32_t>(row & 7);
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 128; c += 32) {
+    uint32_t v[32];
+    tmem_ld_x32(tS_row + c, v);
+    tmem_ld_wait();
+    if (!BIAS && !MASKED) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) mx = fmax3(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float bv[8];
+        if (BIAS) {
+          const int cc = c + g * 8;
+          unpack8(*reinterpret_cast<const uint4*>(sB + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ rsw) << 4)), bv);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float sv = __uint_as_float(v[g * 8 + e]) * scale_log2;
+          if (BIAS) sv = fmaf(bv[e], LOG2E, sv);
+          if (MASKED && (c + g * 8 + e >= limit)) sv = -INFINITY;
+          mx = fmaxf(mx, sv);
+        }
+      }
+    }
+  }
+  if (!BIAS && !MASKED) mx *= scale_log2;          // scale > 0: max commutes with the scaling
+  const float m_new = fmaxf(m_run, mx);
+  alpha = fast_exp2(m_run - m_new);               // first tile: exp2(-inf) = 0
+  const float2 sc2 = make_float2(scale_log2, scale_log2);
+  const float2 nm2 = make_float2(-m_new, -m_new);
+  const float2 l2e2 = make_float2(LOG2E, LOG2E);
+  float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int c = 0; c < 128; c += 32) {
+    uint32_t v[32];
+    tmem_ld_x32(tS_row + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int cc = c + g * 8;
+      float bv[8];
+      if (BIAS) unpack8(*reinterpret_cast<const uint4*>(sB + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ rsw) << 4)), bv);
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        float2 off = nm2;
+        if (BIAS) off = ffma2(make_float2(bv[e], bv[e + 1]), l2e2, nm2);
+        const float2 t = ffma2(make_float2(__uint_as_float(v[g * 8 + e]), __uint_as_float(v[g * 8 + e + 1])), sc2, off);
+        float2 pe = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+        if (MASKED) {
+          if (cc + e >= limit) pe.x = 0.f;
+          if (cc + e + 1 >= limit) pe.y = 0.f;
+        }
+        sum2 = fadd2(sum2, pe);
+        pk[e >> 1] = pack_bf16x2(pe.x, pe.y);
+      }
+      *reinterpret_cast<uint4*>(sP + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ rsw) << 4)) =
+          make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+  l_run = l_run * alpha + (sum2.x + sum2.y);
+  m_run = m_new;
 }
 
 __device__ __forceinline__ void tile_coords(const AttnOperand& op, int bi, int tile, int& c1, int& c2, int& c3) {
@@ -184,8 +259,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float acc[HD];
 #pragma unroll
     for (int i = 0; i < HD; ++i) acc[i] = 0.f;
-    const float LOG2E = 1.4426950408889634f;
-
     for (int j = 0; j < p.kv_tiles; ++j) {
       const int kv_i1 = (j % p.kv.n1) * p.kv.box1, kv_i3 = (j / p.kv.n1) * p.kv.box3;
       // columns [0, limit) of this tile hold real keys (tile = 128 tokens of one view, or box3 whole views)
@@ -195,68 +268,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       if (BIAS) mbar_wait(b_full, j & 1);
-      // pass 1: row max
-      float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(tS + lane_sel + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float bvals[8];
-          if (BIAS) {
-            const int cc = c + g * 8;
-            const uint4 bb = *reinterpret_cast<const uint4*>(sB + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ (row & 7)) << 4));
-            float2 t0 = unpack_bf16x2(bb.x), t1 = unpack_bf16x2(bb.y), t2 = unpack_bf16x2(bb.z), t3 = unpack_bf16x2(bb.w);
-            bvals[0] = t0.x; bvals[1] = t0.y; bvals[2] = t1.x; bvals[3] = t1.y;
-            bvals[4] = t2.x; bvals[5] = t2.y; bvals[6] = t3.x; bvals[7] = t3.y;
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int col = c + g * 8 + e;
-            float s = __uint_as_float(v[g * 8 + e]) * p.scale_log2;
-            if (BIAS) s += bvals[e] * LOG2E;
-            if (col >= limit) s = -INFINITY;
-            m_tile = fmaxf(m_tile, s);
-          }
-        }
-      }
-      const float m_new = fmaxf(m_run, m_tile);
-      const float alpha = fast_exp2(m_run - m_new);   // first tile: exp2(-inf) = 0
-      // pass 2: p = exp2(s - m), row sum, P -> smem (K-major, 128B swizzle, two 64-column halves)
-      float l_tile = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(tS + lane_sel + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int cc = c + g * 8;
-          float bvals[8];
-          if (BIAS) {
-            const uint4 bb = *reinterpret_cast<const uint4*>(sB + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ (row & 7)) << 4));
-            float2 t0 = unpack_bf16x2(bb.x), t1 = unpack_bf16x2(bb.y), t2 = unpack_bf16x2(bb.z), t3 = unpack_bf16x2(bb.w);
-            bvals[0] = t0.x; bvals[1] = t0.y; bvals[2] = t1.x; bvals[3] = t1.y;
-            bvals[4] = t2.x; bvals[5] = t2.y; bvals[6] = t3.x; bvals[7] = t3.y;
-          }
-          float pv[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int col = cc + e;
-            float s = __uint_as_float(v[g * 8 + e]) * p.scale_log2;
-            if (BIAS) s += bvals[e] * LOG2E;
-            float pe = fast_exp2(s - m_new);
-            if (col >= limit) pe = 0.f;
-            pv[e] = pe; l_tile += pe;
-          }
-          *reinterpret_cast<uint4*>(sP + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ (row & 7)) << 4)) =
-              make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
-        }
-      }
-      l_run = l_run * alpha + l_tile;
-      m_run = m_new;
+      float alpha;
+      if (limit >= 128) softmax_tile<BIAS, false>(tS + lane_sel, sB, sP, row, limit, p.scale_log2, m_run, l_run, alpha);
+      else              softmax_tile<BIAS, true>(tS + lane_sel, sB, sP, row, limit, p.scale_log2, m_run, l_run, alpha);
       fence_proxy_async_smem();       // P visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_full);
@@ -269,8 +283,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t v[32];
         tmem_ld_x32(tO + lane_sel + c, v);
         tmem_ld_wait();
+        const float2 al2 = make_float2(alpha, alpha);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) acc[c + e] = acc[c + e] * alpha + __uint_as_float(v[e]);
+        for (int e = 0; e < 32; e += 2) {
+          const float2 r = ffma2(make_float2(acc[c + e], acc[c + e + 1]), al2,
+                                 make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+          acc[c + e] = r.x; acc[c + e + 1] = r.y;
+        }
       }
       tc_fence_before();
     }

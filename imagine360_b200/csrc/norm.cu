@@ -51,7 +51,20 @@ __global__ void gn_stats_kernel(GnSrc s, int groups, int chunk_pixels, double* _
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   if (r < R) {
-    for (long long p = p0 + r; p < p1; p += R) {
+    long long p = p0 + r;
+    for (; p + 3LL * R < p1; p += 4LL * R) {       // 4 independent 16-byte loads in flight per thread
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = gn_load(s, b, p + static_cast<long long>(k) * R, v, Wv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] += f[j] * f[j]; }
+      }
+    }
+    for (; p < p1; p += R) {
       float f[8];
       unpack8(gn_load(s, b, p, v, Wv), f);
 #pragma unroll
@@ -103,18 +116,27 @@ __global__ void gn_apply_kernel(GnSrc s, int groups, int chunk_pixels, const dou
   float a[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = sm[v * 8 + j]; sh[j] = sm[C + v * 8 + j]; }
-  for (long long p = p0 + r; p < p1; p += R) {
+  auto emit = [&](const uint4& u, long long pp) {
     float f[8];
-    unpack8(gn_load(s, b, p, v, Wv), f);
+    unpack8(u, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       f[j] = f[j] * a[j] + sh[j];
       if (do_silu) f[j] = silu(f[j]);
     }
-    *reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * npix + p) * C + v * 8) =
+    *reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * npix + pp) * C + v * 8) =
         make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
                    pack_bf16x2(f[6], f[7]));
+  };
+  long long p = p0 + r;
+  for (; p + 3LL * R < p1; p += 4LL * R) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = gn_load(s, b, p + static_cast<long long>(k) * R, v, Wv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit(u[k], p + static_cast<long long>(k) * R);
   }
+  for (; p < p1; p += R) emit(gn_load(s, b, p, v, Wv), p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -126,60 +148,98 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16
                                  float eps, const bf16* __restrict__ pre_add, int pre_div_a, int pre_mod_a,
                                  int pre_mul_a, int pre_mod_b,
                                  const float* __restrict__ post_add, int post_div, int post_mod) {
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
   const int lane = threadIdx.x & 31, nvec = C >> 3;
-  float f[MAXV][8];
-  float sum = 0.f;
-  const bf16* xr = x + row * ldx;
-  // pre-add table row = ((row / div_a) % mod_a) * mul_a + row % mod_b   (view-major PE of WarpAttn's pers tokens)
-  const bf16* pr = pre_add ? pre_add + (((row / pre_div_a) % pre_mod_a) * pre_mul_a + row % pre_mod_b) * C : nullptr;
+  const long long wstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  // narrow rows: gamma / beta stay in registers for every row this warp normalises (wide rows re-read them
+  // from L1 to keep the register footprint, and with it the number of rows in flight per SM, in check)
+  constexpr bool kCacheGB = (MAXV <= 2);
+  float gw[kCacheGB ? MAXV : 1][8], bw[kCacheGB ? MAXV : 1][8];
+  if (kCacheGB) {
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f[i]);
-      if (pr) {
-        float g[8];
-        unpack8(*reinterpret_cast<const uint4*>(pr + v * 8), g);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[i][j] = __bfloat162float(__float2bfloat16(f[i][j] + g[j]));  // bf16 add like the reference
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gw[kCacheGB ? i : 0]);
+        unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bw[kCacheGB ? i : 0]);
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sum += f[i][j];
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / C;
-  float var = 0.f;
+  uint4 nxt[MAXV];
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int v = lane + i * 32;
-    if (v < nvec) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; var += d * d; }
-    }
+    if (v < nvec) nxt[i] = *reinterpret_cast<const uint4*>(x + row * ldx + v * 8);
   }
+  for (; row < M; row += wstride) {
+    float f[MAXV][8];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-  const float rstd = rsqrtf(var / C + eps);
-  const float* po = post_add ? post_add + static_cast<long long>((row / post_div) % post_mod) * C : nullptr;
-  bf16* yr = y + row * ldy;
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) unpack8(nxt[i], f[i]);
+    }
+    const long long rn = row + wstride;          // prefetch the next row while this one is reduced
+    if (rn < M) {
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      float g[8], bb[8], o[8];
-      unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), g);
-      unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bb);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        o[j] = (f[i][j] - mean) * rstd * g[j] + bb[j];
-        if (po) o[j] = __bfloat162float(__float2bfloat16(o[j])) + po[v * 8 + j];
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        if (v < nvec) nxt[i] = *reinterpret_cast<const uint4*>(x + rn * ldx + v * 8);
       }
-      *reinterpret_cast<uint4*>(yr + v * 8) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                         pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+    // pre-add table row = ((row / div_a) % mod_a) * mul_a + row % mod_b   (view-major PE of WarpAttn's pers tokens)
+    const bf16* pr = pre_add ? pre_add + (((row / pre_div_a) % pre_mod_a) * pre_mul_a + row % pre_mod_b) * C : nullptr;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        if (pr) {
+          float g[8];
+          unpack8(*reinterpret_cast<const uint4*>(pr + v * 8), g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[i][j] = __bfloat162float(__float2bfloat16(f[i][j] + g[j]));  // bf16 add like the reference
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += f[i][j];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / C;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; var += d * d; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / C + eps);
+    const float* po = post_add ? post_add + static_cast<long long>((row / post_div) % post_mod) * C : nullptr;
+    bf16* yr = y + row * ldy;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        float o[8], gg[8], bb[8];
+        if (!kCacheGB) {
+          unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gg);
+          unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bb);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gmul = kCacheGB ? gw[kCacheGB ? i : 0][j] : gg[j];
+          const float badd = kCacheGB ? bw[kCacheGB ? i : 0][j] : bb[j];
+          o[j] = (f[i][j] - mean) * rstd * gmul + badd;
+          if (po) o[j] = __bfloat162float(__float2bfloat16(o[j])) + po[v * 8 + j];
+        }
+        *reinterpret_cast<uint4*>(yr + v * 8) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                           pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      }
     }
   }
 }
@@ -302,7 +362,10 @@ extern "C" int i360_layernorm(const void* x, long long ldx, void* y, long long l
   if (post_add && (post_div <= 0 || post_mod <= 0)) return I360_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int warps = 8;
-  const unsigned grid = static_cast<unsigned>((M + warps - 1) / warps);
+  long long blocks = (M + warps - 1) / warps;
+  const long long cap = static_cast<long long>(num_sms()) * 8;     // persistent warps: each loops over rows
+  if (blocks > cap) blocks = cap;
+  const unsigned grid = static_cast<unsigned>(blocks);
   const bf16 *xx = static_cast<const bf16*>(x), *g = static_cast<const bf16*>(gamma), *b = static_cast<const bf16*>(beta);
   const bf16* pa = static_cast<const bf16*>(pre_add);
   bf16* yy = static_cast<bf16*>(y);
@@ -311,8 +374,6 @@ extern "C" int i360_layernorm(const void* x, long long ldx, void* y, long long l
     layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(xx, ldx, yy, ldy, M, C, g, b, eps, pa, pre_div_a, pre_mod_a, pre_mul_a, pre_mod_b, post_add, post_div, post_mod);
   else if (nvec <= 32 * 5)
     layernorm_kernel<5><<<grid, warps * 32, 0, st>>>(xx, ldx, yy, ldy, M, C, g, b, eps, pa, pre_div_a, pre_mod_a, pre_mul_a, pre_mod_b, post_add, post_div, post_mod);
-  else if (nvec <= 32 * 16)
-    layernorm_kernel<16><<<grid, warps * 32, 0, st>>>(xx, ldx, yy, ldy, M, C, g, b, eps, pa, pre_div_a, pre_mod_a, pre_mul_a, pre_mod_b, post_add, post_div, post_mod);
   else
     return I360_ERR_UNSUPPORTED;
   I360_CUDA_CHECK_LAUNCH();

@@ -18,6 +18,10 @@ struct TAParams {
   float scale;
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
 // MODE 0: F <= 16, two lanes per query row (8 keys each).  MODE 1: F <= 32, one lane per row.
 template <int MODE>
 __global__ void temporal_attn_kernel(const TAParams p) {
@@ -40,14 +44,16 @@ __global__ void temporal_attn_kernel(const TAParams p) {
     const int b = static_cast<int>(pix / p.D);
     const long long row0 = (static_cast<long long>(b) * p.F) * p.D + d;   // frame f -> row0 + f*D
     // ---- stage q, k, v [F, hd] ----
+    // all 3*F*hd/8 16-byte copies of this task go out as asynchronous copies before a single wait
     for (int c = lane; c < nchunks; c += 32) {
       const int f = c / chunks_per_row, ch = c % chunks_per_row;
       const long long r = row0 + static_cast<long long>(f) * p.D;
       const int col = head * p.hd + ch * 8;
-      reinterpret_cast<uint4*>(sQ)[c] = *reinterpret_cast<const uint4*>(p.q + r * p.ldq + col);
-      reinterpret_cast<uint4*>(sK)[c] = *reinterpret_cast<const uint4*>(p.k + r * p.ldk + col);
-      reinterpret_cast<uint4*>(sV)[c] = *reinterpret_cast<const uint4*>(p.v + r * p.ldv + col);
+      cp_async16(reinterpret_cast<uint4*>(sQ) + c, p.q + r * p.ldq + col);
+      cp_async16(reinterpret_cast<uint4*>(sK) + c, p.k + r * p.ldk + col);
+      cp_async16(reinterpret_cast<uint4*>(sV) + c, p.v + r * p.ldv + col);
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     const int i = MODE == 0 ? (lane >> 1) : lane;          // my query frame
     const int j0 = MODE == 0 ? (lane & 1) * 8 : 0;         // my first key
