@@ -57,10 +57,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint (ns): the
+      "selp.u32 %0, 1, 0, p;\n\t}\n"                                     // warp sleeps in hardware instead of
+      : "=r"(ok)                                                            // burning issue slots in a spin loop
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
@@ -223,12 +223,24 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
 // gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. far
 // below the bf16 rounding of the result): 2 MUFU + ~12 FMA instead of erff's ~30-instruction expansion.  The
 // epilogue of the GEGLU GEMMs evaluates this once per output element, so its cost bounds the small-K layers.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
@@ -262,6 +274,25 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// gelu_erf on two values at once: packed FFMA2/FMUL2 for the rational + polynomial part, 2+2 MUFU (rcp, ex2).
+// Same Abramowitz-Stegun 7.1.26 formula as gelu_erf (abs error <= 1.5e-7 before the approx MUFUs' ~1e-6).
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 d = ffma2(ax, make_float2(0.3275911f * 0.70710678f, 0.3275911f * 0.70710678f), make_float2(1.f, 1.f));
+  const float2 t = make_float2(fast_rcp(d.x), fast_rcp(d.y));
+  float2 poly = ffma2(t, make_float2(1.061405429f, 1.061405429f), make_float2(-1.453152027f, -1.453152027f));
+  poly = ffma2(poly, t, make_float2(1.421413741f, 1.421413741f));
+  poly = ffma2(poly, t, make_float2(-0.284496736f, -0.284496736f));
+  poly = ffma2(poly, t, make_float2(0.254829592f, 0.254829592f));
+  poly = fmul2(poly, t);
+  const float2 xx = fmul2(x, x);
+  // exp(-z^2) with z = |x|/sqrt2  ==  exp2(x^2 * (-0.5 * log2 e))
+  const float2 ex = make_float2(fast_exp2(xx.x * -0.72134752044448170f), fast_exp2(xx.y * -0.72134752044448170f));
+  const float2 erfm = ffma2(make_float2(-poly.x, -poly.y), ex, make_float2(1.f, 1.f));     // erf(|x|/sqrt2)
+  const float2 sgn = make_float2(copysignf(erfm.x, x.x), copysignf(erfm.y, x.y));
+  const float2 hx = fmul2(x, make_float2(0.5f, 0.5f));
+  return ffma2(hx, sgn, hx);                                                               // 0.5 x (1 + erf)
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 

@@ -256,8 +256,14 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int j = 0; j < 8; ++j) { ba[j] = 0.f; bg[j] = 0.f; }
               }
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                f[g * 8 + j] = (__uint_as_float(v[g * 8 + j]) + ba[j]) * gelu_erf(__uint_as_float(vg[g * 8 + j]) + bg[j]);
+              for (int j = 0; j < 8; j += 2) {
+                const float2 val = fadd2(make_float2(__uint_as_float(v[g * 8 + j]), __uint_as_float(v[g * 8 + j + 1])),
+                                         make_float2(ba[j], ba[j + 1]));
+                const float2 gate = fadd2(make_float2(__uint_as_float(vg[g * 8 + j]), __uint_as_float(vg[g * 8 + j + 1])),
+                                          make_float2(bg[j], bg[j + 1]));
+                const float2 r = fmul2(val, gelu_erf2(gate));
+                f[g * 8 + j] = r.x; f[g * 8 + j + 1] = r.y;
+              }
             }
           } else {
             tmem_ld_wait();

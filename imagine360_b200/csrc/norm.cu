@@ -173,11 +173,14 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16
     if (v < nvec) nxt[i] = *reinterpret_cast<const uint4*>(x + row * ldx + v * 8);
   }
   for (; row < M; row += wstride) {
-    float f[MAXV][8];
+    float2 f[MAXV][4];                            // packed pairs: the loops below run on FADD2 / FFMA2 / FMUL2
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int v = lane + i * 32;
-      if (v < nvec) unpack8(nxt[i], f[i]);
+      if (v < nvec) {
+        f[i][0] = unpack_bf16x2(nxt[i].x); f[i][1] = unpack_bf16x2(nxt[i].y);
+        f[i][2] = unpack_bf16x2(nxt[i].z); f[i][3] = unpack_bf16x2(nxt[i].w);
+      }
     }
     const long long rn = row + wstride;          // prefetch the next row while this one is reduced
     if (rn < M) {
@@ -189,56 +192,66 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16
     }
     // pre-add table row = ((row / div_a) % mod_a) * mul_a + row % mod_b   (view-major PE of WarpAttn's pers tokens)
     const bf16* pr = pre_add ? pre_add + (((row / pre_div_a) % pre_mod_a) * pre_mul_a + row % pre_mod_b) * C : nullptr;
-    float sum = 0.f;
+    float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
         if (pr) {
-          float g[8];
-          unpack8(*reinterpret_cast<const uint4*>(pr + v * 8), g);
+          const uint4 u = *reinterpret_cast<const uint4*>(pr + v * 8);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[i][j] = __bfloat162float(__float2bfloat16(f[i][j] + g[j]));  // bf16 add like the reference
+          for (int j = 0; j < 4; ++j) {            // bf16 add like the reference: round the sum to bf16
+            const float2 t = fadd2(f[i][j], unpack_bf16x2(w[j]));
+            f[i][j] = unpack_bf16x2(pack_bf16x2(t.x, t.y));
+          }
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sum += f[i][j];
+        sum2 = fadd2(fadd2(f[i][0], f[i][1]), fadd2(fadd2(f[i][2], f[i][3]), sum2));
       }
     }
+    float sum = sum2.x + sum2.y;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum / C;
-    float var = 0.f;
+    const float2 nmean = make_float2(-mean, -mean);
+    float2 var2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; var += d * d; }
+        for (int j = 0; j < 4; ++j) { f[i][j] = fadd2(f[i][j], nmean); var2 = ffma2(f[i][j], f[i][j], var2); }
       }
     }
+    float var = var2.x + var2.y;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
     const float rstd = rsqrtf(var / C + eps);
+    const float2 rstd2 = make_float2(rstd, rstd);
     const float* po = post_add ? post_add + static_cast<long long>((row / post_div) % post_mod) * C : nullptr;
     bf16* yr = y + row * ldy;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
-        float o[8], gg[8], bb[8];
+        float gg[8], bb[8];
         if (!kCacheGB) {
           unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gg);
           unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bb);
         }
+        uint32_t outw[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float gmul = kCacheGB ? gw[kCacheGB ? i : 0][j] : gg[j];
-          const float badd = kCacheGB ? bw[kCacheGB ? i : 0][j] : bb[j];
-          o[j] = (f[i][j] - mean) * rstd * gmul + badd;
-          if (po) o[j] = __bfloat162float(__float2bfloat16(o[j])) + po[v * 8 + j];
+        for (int j = 0; j < 4; ++j) {
+          const float2 g2 = kCacheGB ? make_float2(gw[kCacheGB ? i : 0][2 * j], gw[kCacheGB ? i : 0][2 * j + 1]) : make_float2(gg[2 * j], gg[2 * j + 1]);
+          const float2 b2 = kCacheGB ? make_float2(bw[kCacheGB ? i : 0][2 * j], bw[kCacheGB ? i : 0][2 * j + 1]) : make_float2(bb[2 * j], bb[2 * j + 1]);
+          float2 o = ffma2(f[i][j], fmul2(g2, rstd2), b2);
+          if (po) {
+            const float2 r = unpack_bf16x2(pack_bf16x2(o.x, o.y));
+            o = fadd2(r, make_float2(po[v * 8 + 2 * j], po[v * 8 + 2 * j + 1]));
+          }
+          outw[j] = pack_bf16x2(o.x, o.y);
         }
-        *reinterpret_cast<uint4*>(yr + v * 8) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                           pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        *reinterpret_cast<uint4*>(yr + v * 8) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
       }
     }
   }

@@ -133,6 +133,132 @@ __global__ void temporal_attn_kernel(const TAParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// F <= 16: tensor-core version.  One warp per (pixel, head): S = Q K^T and O = P V are m16n8k16 bf16 MMAs
+// (mma.sync -- the problem is a 16x16 tile, far below a tcgen05 tile); the softmaxed S accumulators are re-used
+// in place as the A fragments of P.V, V is read through ldmatrix.trans, and the next task's q/k/v are prefetched
+// with cp.async into the second smem stage while the current one is computed.  ~130 instructions per task
+// instead of ~3000 scalar ones, which turns this kernel from issue-bound into HBM-bound.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_u32(smem_row)));
+}
+
+__global__ void temporal_attn_mma_kernel(const TAParams p, int hd_pad, int pitch) {
+  extern __shared__ __align__(16) uint8_t smem_ta[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int stage_elems = 3 * 16 * pitch;
+  bf16* base = reinterpret_cast<bf16*>(smem_ta) + static_cast<size_t>(warp) * 2 * stage_elems;
+  for (int i = lane; i < 2 * stage_elems / 8; i += 32) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  const long long total = static_cast<long long>(p.B) * p.D * p.heads;
+  const long long tstride = static_cast<long long>(gridDim.x) * nwarps;
+  const int cpr = p.hd >> 3, nchunks = p.F * cpr;
+  const int g = lane >> 2, q4 = lane & 3;
+
+  auto issue = [&](long long task, int stage) {
+    const int head = static_cast<int>(task % p.heads);
+    const long long pix = task / p.heads;
+    const long long row0 = (static_cast<long long>(pix / p.D) * p.F) * p.D + pix % p.D;
+    bf16* sq = base + stage * stage_elems;
+    for (int c = lane; c < nchunks; c += 32) {
+      const int f = c / cpr, ch = c % cpr;
+      const long long r = row0 + static_cast<long long>(f) * p.D;
+      const int col = head * p.hd + ch * 8;
+      cp_async16(sq + f * pitch + ch * 8, p.q + r * p.ldq + col);
+      cp_async16(sq + 16 * pitch + f * pitch + ch * 8, p.k + r * p.ldk + col);
+      cp_async16(sq + 32 * pitch + f * pitch + ch * 8, p.v + r * p.ldv + col);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  long long task = static_cast<long long>(blockIdx.x) * nwarps + warp;
+  int stage = 0;
+  if (task < total) issue(task, 0);
+  for (; task < total; task += tstride, stage ^= 1) {
+    const long long nxt = task + tstride;
+    if (nxt < total) { issue(nxt, stage ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    else             { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+    __syncwarp();
+    bf16* sQ = base + stage * stage_elems;
+    const bf16* sK = sQ + 16 * pitch;
+    const bf16* sV = sQ + 32 * pitch;
+    // ---- S = Q K^T (16 x 16), two 8-key n-tiles ----
+    float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int k0 = 0; k0 < hd_pad; k0 += 16) {
+      uint32_t a[4];
+      a[0] = *reinterpret_cast<const uint32_t*>(sQ + g * pitch + k0 + q4 * 2);
+      a[1] = *reinterpret_cast<const uint32_t*>(sQ + (g + 8) * pitch + k0 + q4 * 2);
+      a[2] = *reinterpret_cast<const uint32_t*>(sQ + g * pitch + k0 + 8 + q4 * 2);
+      a[3] = *reinterpret_cast<const uint32_t*>(sQ + (g + 8) * pitch + k0 + 8 + q4 * 2);
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sK + (nt * 8 + g) * pitch + k0 + q4 * 2);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sK + (nt * 8 + g) * pitch + k0 + 8 + q4 * 2);
+        mma_bf16_16816(sc[nt], a, b0, b1);
+      }
+    }
+    // ---- softmax over keys (row g: sc[.][0..1], row g+8: sc[.][2..3]; a row is spread over the 4 lanes of a quad) ----
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = (nt * 8 + q4 * 2 + e) < p.F;
+        sc[nt][e] = ok ? sc[nt][e] * p.scale : -INFINITY;
+        sc[nt][2 + e] = ok ? sc[nt][2 + e] * p.scale : -INFINITY;
+        mx0 = fmaxf(mx0, sc[nt][e]); mx1 = fmaxf(mx1, sc[nt][2 + e]);
+      }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        sc[nt][e] = __expf(sc[nt][e] - mx0); sum0 += sc[nt][e];
+        sc[nt][2 + e] = __expf(sc[nt][2 + e] - mx1); sum1 += sc[nt][2 + e];
+      }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+    uint32_t pa[4] = {pack_bf16x2(sc[0][0], sc[0][1]), pack_bf16x2(sc[0][2], sc[0][3]),
+                      pack_bf16x2(sc[1][0], sc[1][1]), pack_bf16x2(sc[1][2], sc[1][3])};
+    __syncwarp();      // all lanes are done reading Q: its tile becomes the output staging area
+    // ---- O = P V, 8 head-dim columns per MMA ----
+    for (int n0 = 0; n0 < p.hd; n0 += 8) {
+      uint32_t b0, b1;
+      ldmatrix_x2_trans(b0, b1, sV + (lane & 15) * pitch + n0);
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16_16816(o, pa, b0, b1);
+      *reinterpret_cast<uint32_t*>(sQ + g * pitch + n0 + q4 * 2) = pack_bf16x2(o[0] * inv0, o[1] * inv0);
+      *reinterpret_cast<uint32_t*>(sQ + (g + 8) * pitch + n0 + q4 * 2) = pack_bf16x2(o[2] * inv1, o[3] * inv1);
+    }
+    __syncwarp();
+    {
+      const int head = static_cast<int>(task % p.heads);
+      const long long pix = task / p.heads;
+      const long long row0 = (static_cast<long long>(pix / p.D) * p.F) * p.D + pix % p.D;
+      for (int c = lane; c < nchunks; c += 32) {
+        const int f = c / cpr, ch = c % cpr;
+        *reinterpret_cast<uint4*>(p.o + (row0 + static_cast<long long>(f) * p.D) * p.ldo + head * p.hd + ch * 8) =
+            *reinterpret_cast<const uint4*>(sQ + f * pitch + ch * 8);
+      }
+    }
+    // rows >= F of the staging tile were written with garbage-free zeros only if F == 16; restore the zero padding
+    if (p.F < 16) {
+      for (int c = lane; c < (16 - p.F) * (pitch / 8); c += 32)
+        reinterpret_cast<uint4*>(sQ + p.F * pitch)[c] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace i360
 
 using namespace i360;
@@ -156,6 +282,22 @@ extern "C" int i360_temporal_attention_bf16(const void* q, long long ldq, const 
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (F <= 16) {
+    const int hd_pad = (head_dim + 15) / 16 * 16;
+    const int pitch = hd_pad + 8;                       // +16 bytes per row: conflict-free fragment / ldmatrix reads
+    const size_t pw = static_cast<size_t>(2) * 3 * 16 * pitch * sizeof(bf16);
+    int w2 = 8;
+    while (w2 > 1 && pw * w2 > 110 * 1024) w2 >>= 1;
+    const size_t sm2 = pw * w2;
+    long long bl = (total + w2 - 1) / w2;
+    const long long cap2 = static_cast<long long>(num_sms()) * (sm2 > 56 * 1024 ? 2 : 4);
+    if (bl > cap2) bl = cap2;
+    static bool setm = false;
+    if (!setm) { cudaFuncSetAttribute(temporal_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); setm = true; }
+    temporal_attn_mma_kernel<<<static_cast<unsigned>(bl), w2 * 32, sm2, st>>>(p, hd_pad, pitch);
+    I360_CUDA_CHECK_LAUNCH();
+    return I360_OK;
+  }
   if (F <= 16) {
     static bool set0 = false;
     if (!set0) { cudaFuncSetAttribute(temporal_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set0 = true; }

@@ -21,6 +21,15 @@ elif kind == "conv":
     B, H, W, Ci, Co = a
     x = torch.randn(B, H, W, Ci, device="cuda").bfloat16(); wp = ops.pack_conv3x3(torch.randn(Co, Ci, 3, 3, device="cuda").bfloat16())
     fn = lambda: ops.conv3x3(x, wp)
+if kind == "temporal":
+    B, Fr, D, heads, hd = a
+    C = heads * hd
+    qkv = torch.randn(B * Fr * D, 3 * C, device="cuda").bfloat16(); out = torch.empty(B * Fr * D, C, device="cuda", dtype=torch.bfloat16)
+    fn = lambda: ops.temporal_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], out, B, Fr, D, heads, hd)
+if kind == "ln":
+    M, C = a
+    x = torch.randn(M, C, device="cuda").bfloat16(); g = torch.ones(C, device="cuda").bfloat16(); b = torch.zeros(C, device="cuda").bfloat16()
+    fn = lambda: ops.layernorm(x, g, b)
 for _ in range(4):
     fn()
 torch.cuda.synchronize()
