@@ -240,14 +240,17 @@ def kernel_roofline(pipe, inp, size, one_step):
             return r
 
     flops = {"gemm": 0.0, "conv": 0.0}
+    shapes = []     # (kind, M, N, K, act, index into timed[name])
 
     def gemm(a, w, *args, **kw):
         flops["gemm"] += 2.0 * a.shape[0] * w.shape[0] * a.shape[1]
+        shapes.append(("gemm", a.shape[0], w.shape[0], a.shape[1], kw.get("act", 0), len(timed.get("i360_gemm_bf16", []))))
         return orig_gemm(a, w, *args, **kw)
 
     def conv(x, wp, *args, **kw):
         b, h, wd, _ = x.shape
         flops["conv"] += 2.0 * b * h * wd * wp.shape[0] * wp.shape[1]
+        shapes.append(("conv", b * h * wd, wp.shape[0], wp.shape[1], 0, len(timed.get("i360_conv3x3_bf16", []))))
         return orig_conv(x, wp, *args, **kw)
 
     class LibProxy:
@@ -276,6 +279,14 @@ def kernel_roofline(pipe, inp, size, one_step):
             "avg_launch_ms": round(gc_ms / max(1, gc_n), 4), "alg_flops_per_step": flops["gemm"] + flops["conv"],
             "share_of_step_kernel_time": round(gc_ms / total, 4) if total else None}
     breakdown = {n: {"launches": c, "ms": round(ms, 3)} for n, (c, ms) in sorted(per.items(), key=lambda kv: -kv[1][1])}
+    agg = {}
+    for kind, M, N, K, act, idx in shapes:
+        ev = timed["i360_gemm_bf16" if kind == "gemm" else "i360_conv3x3_bf16"][idx]
+        key = f"{kind} M={M} N={N} K={K} act={act}"
+        c, ms, fl = agg.get(key, (0, 0.0, 0.0))
+        agg[key] = (c + 1, ms + ev[0].elapsed_time(ev[1]), fl + 2.0 * M * N * K)
+    breakdown["shapes"] = {k: {"n": c, "ms": round(ms, 3), "tflops": round(fl / ms / 1e9, 1)} for k, (c, ms, fl) in
+                           sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]}
     return roof, breakdown
 
 

@@ -3,9 +3,11 @@
 // One CTA = one 128-row query tile of one (batch item, head).  Warp roles (192 threads):
 //   warp0  TMA producer : Q once, then K_j / V_j (/ bias_j) tiles through 2-stage mbarrier rings
 //   warp1  MMA issuer   : S = Q K_j^T  -> TMEM;  O_j = P_j V_j -> TMEM   (one elected lane)
-//   warps 2..5 softmax  : one query row per thread: TMEM S -> online softmax (exp2, fp32) -> P (bf16)
-//                         into swizzled smem as the next MMA's A operand; O_j accumulated in registers
-//                         with the running-max rescale; final O / l -> bf16 -> global.
+//   warps 2..9 softmax  : TWO threads per query row (warp w and w+4 share a TMEM lane quarter): each owns 64 of
+//                         the 128 key columns of S and half of O's columns; they exchange only the row maximum
+//                         through smem.  TMEM S -> online softmax (exp2, fp32) -> P (bf16) into swizzled smem as
+//                         the next MMA's A operand; O_j accumulated in registers with the running-max rescale;
+//                         final O / l -> bf16 -> global.
 // Two CTAs are co-resident per SM (<= 113 KB smem, 256 TMEM columns each) so one CTA's softmax
 // overlaps the other's MMAs.
 //
@@ -42,7 +44,7 @@ struct AttnParams {
   int has_bias; int bias_rows, bias_cols;
 };
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;   // warp0 TMA, warp1 MMA, warps 2..9 softmax (2 threads per query row)
 
 template <int HD>
 struct AttnCfg {
@@ -68,12 +70,13 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 // full, unbiased tile of the spatial self-attention -- carries no selects and no per-element scale multiply.
 template <bool BIAS, bool MASKED>
 __device__ __forceinline__ void softmax_tile(uint32_t tS_row, const uint8_t* sB, uint8_t* sP, int row, int limit,
-                                             float scale_log2, float& m_run, float& l_run, float& alpha) {
+                                             float scale_log2, float& m_run, float& l_run, float& alpha, int cbeg,
+                                             bf16* xmax_mine, const bf16* xmax_other) {
   const float LOG2E = 1.4426950408889634f;
   const uint32_t rsw = static_cast<uint32_t>(row & 7);
   float mx = -INFINITY;
 #pragma unroll 1
-  for (int c = 0; c < 128; c += 32) {
+  for (int c = cbeg; c < cbeg + 64; c += 32) {
     uint32_t v[32];
     tmem_ld_x32(tS_row + c, v);
     tmem_ld_wait();
@@ -99,6 +102,13 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS_row, const uint8_t* sB,
     }
   }
   if (!BIAS && !MASKED) mx *= scale_log2;          // scale > 0: max commutes with the scaling
+  // the partner thread (other half of the key columns of this row) contributes its maximum through smem.  Both
+  // sides use the bf16-ROUNDED maxima (512 B exchange buffer keeps two CTAs per SM): any common shift is a valid
+  // softmax stabiliser, it only has to be identical in both halves and within ~2^0.2 of the true maximum.
+  const bf16 mxb = __float2bfloat16(mx);
+  *xmax_mine = mxb;
+  named_bar_sync(1, 256);
+  mx = fmaxf(__bfloat162float(mxb), __bfloat162float(*xmax_other));
   const float m_new = fmaxf(m_run, mx);
   alpha = fast_exp2(m_run - m_new);               // first tile: exp2(-inf) = 0
   const float2 sc2 = make_float2(scale_log2, scale_log2);
@@ -106,7 +116,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS_row, const uint8_t* sB,
   const float2 l2e2 = make_float2(LOG2E, LOG2E);
   float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll 1
-  for (int c = 0; c < 128; c += 32) {
+  for (int c = cbeg; c < cbeg + 64; c += 32) {
     uint32_t v[32];
     tmem_ld_x32(tS_row + c, v);
     tmem_ld_wait();
@@ -168,6 +178,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* b_full = bars + 12;    // TMA -> softmax: bias_j in smem
   uint64_t* b_empty = bars + 13;   // softmax -> TMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  bf16* xch = reinterpret_cast<bf16*>(bars + 16);            // [2][128] row-max exchange between the two column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, head = blockIdx.y, bi = blockIdx.z;
@@ -177,8 +188,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (BIAS) tma_prefetch_desc(&tmB);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
-    mbar_init(b_full, 1); mbar_init(b_empty, 128);
+    mbar_init(s_full, 1); mbar_init(p_full, 256); mbar_init(o_full, 1);
+    mbar_init(b_full, 1); mbar_init(b_empty, 256);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, C::kTmemCols); tmem_relinquish(); }
@@ -249,16 +260,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   } else {
     // ================================ softmax / epilogue ================================
     const int ew = warp & 3;
+    const int half = (warp - 2) >> 2;            // 0: key columns 0..63 / O columns [0, HD/2); 1: the other halves
     const int row = ew * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
+    constexpr int HH = HD / 2;
+    bf16* xmine = xch + half * 128 + row;
+    const bf16* xother = xch + (half ^ 1) * 128 + row;
     // my query token
     const int q_tok = (qt % p.q.n1) * p.q.box1 + row % p.q.box1;
     const int q_view = (qt / p.q.n1) * p.q.box3 + row / p.q.box1;
     const bool q_valid = (q_tok < p.q.d1) && (q_view < p.q.ext3);
     float m_run = -INFINITY, l_run = 0.f;
-    float acc[HD];
+    float acc[HH];
 #pragma unroll
-    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    for (int i = 0; i < HH; ++i) acc[i] = 0.f;
+
     for (int j = 0; j < p.kv_tiles; ++j) {
       const int kv_i1 = (j % p.kv.n1) * p.kv.box1, kv_i3 = (j / p.kv.n1) * p.kv.box3;
       // columns [0, limit) of this tile hold real keys (tile = 128 tokens of one view, or box3 whole views)
@@ -269,45 +285,48 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_after();
       if (BIAS) mbar_wait(b_full, j & 1);
       float alpha;
-      if (limit >= 128) softmax_tile<BIAS, false>(tS + lane_sel, sB, sP, row, limit, p.scale_log2, m_run, l_run, alpha);
-      else              softmax_tile<BIAS, true>(tS + lane_sel, sB, sP, row, limit, p.scale_log2, m_run, l_run, alpha);
+      if (limit >= 128) softmax_tile<BIAS, false>(tS + lane_sel, sB, sP, row, limit, p.scale_log2, m_run, l_run, alpha, half * 64, xmine, xother);
+      else              softmax_tile<BIAS, true>(tS + lane_sel, sB, sP, row, limit, p.scale_log2, m_run, l_run, alpha, half * 64, xmine, xother);
       fence_proxy_async_smem();       // P visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_full);
       if (BIAS) mbar_arrive(b_empty);
-      // O_j
+      // O_j: my half of the head-dim columns
       mbar_wait(o_full, j & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < HD; c += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(tO + lane_sel + c, v);
+      {
+        uint32_t v[HH];
+        if (HH == 32) tmem_ld_x32(tO + lane_sel + half * HH, v);
+        else          tmem_ld_x16(tO + lane_sel + half * HH, v);
         tmem_ld_wait();
         const float2 al2 = make_float2(alpha, alpha);
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float2 r = ffma2(make_float2(acc[c + e], acc[c + e + 1]), al2,
-                                 make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
-          acc[c + e] = r.x; acc[c + e + 1] = r.y;
+        for (int e = 0; e < HH; e += 2) {
+          const float2 r = ffma2(make_float2(acc[e], acc[e + 1]), al2, make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+          acc[e] = r.x; acc[e + 1] = r.y;
         }
       }
       tc_fence_before();
     }
-    // ---- epilogue ----
+    // ---- epilogue: combine the two halves' row sums, write my half of O ----
+    float* lsum = reinterpret_cast<float*>(sP);        // the P tile is dead after the last P.V MMA
+    lsum[half * 128 + row] = l_run;
+    named_bar_sync(1, 256);
+    const float l_tot = l_run + lsum[(half ^ 1) * 128 + row];
     if (q_valid) {
-      const float inv = 1.0f / l_run;
-      bf16* dst = p.o + p.o_col0 + head * HD + static_cast<long long>(q_tok) * p.os1 +
+      const float inv = 1.0f / l_tot;
+      bf16* dst = p.o + p.o_col0 + head * HD + half * HH + static_cast<long long>(q_tok) * p.os1 +
                   static_cast<long long>(qc2) * p.os2 +
                   static_cast<long long>((bi / p.q.A) * p.q.mul + q_view) * p.os3;
 #pragma unroll
-      for (int c = 0; c < HD; c += 8) {
+      for (int c = 0; c < HH; c += 8) {
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = acc[c + e] * inv;
         if (p.accumulate) {
           const uint4 old = *reinterpret_cast<const uint4*>(dst + c);
-          float2 t0 = unpack_bf16x2(old.x), t1 = unpack_bf16x2(old.y), t2 = unpack_bf16x2(old.z), t3 = unpack_bf16x2(old.w);
-          const float prev[8] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, t3.x, t3.y};
+          float prev[8];
+          unpack8(old, prev);
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = prev[e] + __bfloat162float(__float2bfloat16(o[e]));
         }
@@ -325,7 +344,7 @@ template <int HD, bool BIAS>
 static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const CUtensorMap& b,
                        const AttnParams& p, int heads, int batch, cudaStream_t st) {
   using C = AttnCfg<HD>;
-  const int smem = C::kQBytes + 4 * C::kKVBytes + C::kPBytes + (BIAS ? C::kBiasBytes : 0) + 256;
+  const int smem = C::kQBytes + 4 * C::kKVBytes + C::kPBytes + (BIAS ? C::kBiasBytes : 0) + 128 + 512;   // barriers + row-max exchange
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(attention_kernel<HD, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)

@@ -52,12 +52,12 @@ __global__ void gn_stats_kernel(GnSrc s, int groups, int chunk_pixels, double* _
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   if (r < R) {
     long long p = p0 + r;
-    for (; p + 3LL * R < p1; p += 4LL * R) {       // 4 independent 16-byte loads in flight per thread
-      uint4 u[4];
+    for (; p + 7LL * R < p1; p += 8LL * R) {       // 8 independent 16-byte loads in flight per thread
+      uint4 u[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = gn_load(s, b, p + static_cast<long long>(k) * R, v, Wv);
+      for (int k = 0; k < 8; ++k) u[k] = gn_load(s, b, p + static_cast<long long>(k) * R, v, Wv);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         float f[8];
         unpack8(u[k], f);
 #pragma unroll
@@ -129,12 +129,12 @@ __global__ void gn_apply_kernel(GnSrc s, int groups, int chunk_pixels, const dou
                    pack_bf16x2(f[6], f[7]));
   };
   long long p = p0 + r;
-  for (; p + 3LL * R < p1; p += 4LL * R) {
-    uint4 u[4];
+  for (; p + 7LL * R < p1; p += 8LL * R) {
+    uint4 u[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = gn_load(s, b, p + static_cast<long long>(k) * R, v, Wv);
+    for (int k = 0; k < 8; ++k) u[k] = gn_load(s, b, p + static_cast<long long>(k) * R, v, Wv);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) emit(u[k], p + static_cast<long long>(k) * R);
+    for (int k = 0; k < 8; ++k) emit(u[k], p + static_cast<long long>(k) * R);
   }
   for (; p < p1; p += R) emit(gn_load(s, b, p, v, Wv), p);
 }
@@ -166,13 +166,29 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16
       }
     }
   }
-  uint4 nxt[MAXV];
+  // PD rows are kept in flight per warp (register ring): with ~16 resident warps per SM a single prefetched row
+  // leaves too few bytes outstanding to cover HBM latency
+  constexpr int PD = (MAXV <= 2) ? 4 : 2;
+  uint4 ring[PD][MAXV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) nxt[i] = *reinterpret_cast<const uint4*>(x + row * ldx + v * 8);
+  for (int d = 0; d < PD; ++d) {
+    const long long rr = row + d * wstride;
+    if (rr < M) {
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        if (v < nvec) ring[d][i] = *reinterpret_cast<const uint4*>(x + rr * ldx + v * 8);
+      }
+    }
   }
   for (; row < M; row += wstride) {
+    uint4 nxt[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) nxt[i] = ring[0][i];
+#pragma unroll
+    for (int d = 0; d + 1 < PD; ++d)
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) ring[d][i] = ring[d + 1][i];
     float2 f[MAXV][4];                            // packed pairs: the loops below run on FADD2 / FFMA2 / FMUL2
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
@@ -182,12 +198,12 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16
         f[i][2] = unpack_bf16x2(nxt[i].z); f[i][3] = unpack_bf16x2(nxt[i].w);
       }
     }
-    const long long rn = row + wstride;          // prefetch the next row while this one is reduced
+    const long long rn = row + static_cast<long long>(PD) * wstride;   // refill the ring PD rows ahead
     if (rn < M) {
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int v = lane + i * 32;
-        if (v < nvec) nxt[i] = *reinterpret_cast<const uint4*>(x + rn * ldx + v * 8);
+        if (v < nvec) ring[PD - 1][i] = *reinterpret_cast<const uint4*>(x + rn * ldx + v * 8);
       }
     }
     // pre-add table row = ((row / div_a) % mod_a) * mul_a + row % mod_b   (view-major PE of WarpAttn's pers tokens)
