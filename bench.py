@@ -183,6 +183,12 @@ def run_native(args, size, rank, world, device):
     ms_e2e = float(t2.item())
 
     res = dict(ms=ms, ms_e2e=ms_e2e, launches=launches, clocks=clocks, h2d=h2d, d2h=d2h)
+    if os.environ.get("I360_PROFILE"):      # ncu --profile-from-start off: capture exactly one step
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        one_step(5)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     if rank == 0:
         res["roofline"], res["breakdown"] = kernel_roofline(pipe, inp, size, one_step)
     return res

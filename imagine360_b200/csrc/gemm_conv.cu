@@ -53,7 +53,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 320;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue (two groups of 4)
 
-template <int BN> struct Cfg {
+template <int BN, bool RING = false> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -61,7 +61,10 @@ template <int BN> struct Cfg {
   // buffers per epilogue group
   static constexpr int CH = 32;
   static constexpr int kStgBytes = 128 * CH * 2;
-  static constexpr int kNumStg = 4;
+  // RING: the residual tile is TMA-prefetched INTO the staging buffers (added in place, then stored), which needs
+  // 4 buffers per group so that a residual chunk can be requested ~3 chunks before it is consumed
+  static constexpr int kBufPerGrp = RING ? 4 : 2;
+  static constexpr int kNumStg = 2 * kBufPerGrp;
   static constexpr int kBudget = 226 * 1024 - kNumStg * kStgBytes - 1024 - 256;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kNumStg * kStgBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -72,13 +75,18 @@ template <int BN> struct Cfg {
 // Epilogue flavours (compile-time: the epilogue is the critical path of the small-K layers, and one generic,
 // runtime-branchy version thrashes the instruction cache)
 enum : int { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_RESID = 2, EPI_ROWVEC = 3, EPI_ACT = 4, EPI_GENERAL = 5 };
+// residual tiles go through the TMA ring for the narrow-N tiles (the K=320/640 projections, where the per-thread
+// strided residual reads were the bottleneck); BN=256 keeps 4 pipeline stages and reads the residual directly
+template <int BN, int EPI> struct UseRing { static constexpr bool value = (EPI == EPI_RESID) && (BN <= 160); };
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW,
-                 const __grid_constant__ CUtensorMap tmD, const GemmConvParams p) {
-  using C = Cfg<BN>;
+                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
+                 const GemmConvParams p) {
+  constexpr bool kRing = UseRing<BN, EPI>::value;
+  using C = Cfg<BN, kRing>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -89,6 +97,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull = bars + 2 * C::kStages;     // [2]
   uint64_t* tempty = bars + 2 * C::kStages + 2;// [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+  uint64_t* rbar = bars + 2 * C::kStages + 5;   // [2 groups][4]: residual chunk landed in staging buffer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,6 +108,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.C3 > 0) tma_prefetch_desc(&tmA3);
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    if (kRing) { for (int s = 0; s < 8; ++s) mbar_init(&rbar[s], 1); tma_prefetch_desc(&tmR); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, C::kTmemCols); tmem_relinquish(); }
@@ -191,8 +201,34 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool store_thread = (lane == 0) && (warp == 2 || warp == 6);
     const bool direct = p.conv && p.crop > 0;
     const uint32_t swz = (row >> 1) & 3;     // 64B swizzle: 16-byte chunk index ^= address bits [7,9)
-    uint8_t* gbuf = stg + grp * 2 * C::kStgBytes;
-    uint32_t kchunk = 0;                     // chunks issued by this group so far (buffer parity)
+    constexpr int NB = C::kBufPerGrp;
+    uint8_t* gbuf = stg + grp * NB * C::kStgBytes;
+    uint32_t kchunk = 0;                     // chunks consumed by this group so far (buffer = kchunk % NB)
+    // residual prefetch iterator of the group's store thread: runs NB-1 chunks ahead of consumption
+    constexpr int n_chunks_c = (EPI == EPI_GEGLU) ? (BN / 2) / C::CH : BN / C::CH;
+    int pf_t = blockIdx.x, pf_ci = grp; uint32_t pf_k = 0;
+    auto prefetch_resid = [&]() {            // request the residual of the next not-yet-requested chunk
+      while (pf_t < total_tiles && pf_ci >= n_chunks_c) { pf_t += gridDim.x; pf_ci = grp; }
+      if (pf_t >= total_tiles) return;
+      const int pn = pf_t % p.n_tiles, pm = pf_t / p.n_tiles;
+      const int col = pn * BN + pf_ci * C::CH;
+      uint8_t* dstb = gbuf + (pf_k % NB) * C::kStgBytes;
+      uint64_t* bar = &rbar[grp * 4 + (pf_k % NB)];
+      if (col < p.n_out) {
+        mbar_expect_tx(bar, C::kStgBytes);
+        if (p.conv) {
+          const int pw0 = (pm % p.n_wt) * p.TW, ph0 = ((pm / p.n_wt) % p.n_ht) * p.TH, pb0 = (pm / (p.n_wt * p.n_ht)) * p.TB;
+          tma_load_4d(dstb, &tmR, bar, col, pw0, ph0, pb0);
+        } else {
+          tma_load_2d(dstb, &tmR, bar, col, pm * BM);
+        }
+      } else {
+        mbar_arrive(bar);                    // dead chunk: keep the phase sequence in step
+      }
+      pf_ci += 2; ++pf_k;
+    };
+    const bool ring_on = kRing && !direct && p.resid != nullptr;
+    if (ring_on && store_thread) { for (int i = 0; i < NB - 1; ++i) prefetch_resid(); }
     int as = 0; uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
@@ -215,7 +251,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (!valid) { orow = 0; vec_idx = 0; }
       const float* rv = (kRowvec && p.rowvec != nullptr)
                             ? p.rowvec + static_cast<long long>(vec_idx / p.rowvec_div) * p.rowvec_ld : nullptr;
-      const bf16* rrow = (kResid && p.resid != nullptr && valid) ? p.resid + orow * p.ldr : nullptr;
+      const bf16* rrow = (kResid && !ring_on && p.resid != nullptr && valid) ? p.resid + orow * p.ldr : nullptr;
       bf16* drow = p.D + orow * p.ldd;
 
       mbar_wait(&tfull[as], aphase);
@@ -228,7 +264,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int ci = grp; ci < n_chunks; ci += 2) {
         const int ocol = oc0 + ci * CH;                 // output column of staged column 0
         const bool live = ocol < p.n_out;
-        uint8_t* buf = gbuf + (kchunk & 1) * C::kStgBytes;
+        uint8_t* buf = gbuf + (kchunk % NB) * C::kStgBytes;
         uint8_t* my = buf + row * (CH * 2);
         float f[32];
         if (live) {
@@ -303,6 +339,18 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
+          if (ring_on) {                     // residual chunk was TMA-prefetched into my staging row
+            mbar_wait(&rbar[grp * 4 + (kchunk % NB)], (kchunk / NB) & 1);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float r8[8];
+              const uint4 rr = *reinterpret_cast<const uint4*>(my + ((static_cast<uint32_t>(g) ^ swz) << 4));
+              float2 t0 = unpack_bf16x2(rr.x), t1 = unpack_bf16x2(rr.y), t2 = unpack_bf16x2(rr.z), t3 = unpack_bf16x2(rr.w);
+              r8[0] = t0.x; r8[1] = t0.y; r8[2] = t1.x; r8[3] = t1.y; r8[4] = t2.x; r8[5] = t2.y; r8[6] = t3.x; r8[7] = t3.y;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[g * 8 + j] += r8[j];
+            }
+          }
           if (p.out_scale != 1.0f) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
@@ -320,13 +368,19 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (!direct) {
+          if (ring_on && !live) mbar_wait(&rbar[grp * 4 + (kchunk % NB)], (kchunk / NB) & 1);   // consume the dead chunk's phase
           fence_proxy_async_smem();
-          if (store_thread) bulk_wait_read<0>();     // the store of the previous chunk (other buffer) is done reading
+          if (store_thread) bulk_wait_read<0>();     // every earlier store of this group is done reading its buffer
           named_bar_sync(1 + grp, 128);
-          if (store_thread && live) {
-            if (p.conv) tma_store_4d(&tmD, buf, ocol, w0, h0, b0);
-            else        tma_store_2d(&tmD, buf, ocol, m_blk * BM);
-            bulk_commit();
+          if (store_thread) {
+            if (live) {
+              if (p.conv) tma_store_4d(&tmD, buf, ocol, w0, h0, b0);
+              else        tma_store_2d(&tmD, buf, ocol, m_blk * BM);
+              bulk_commit();
+            }
+            // buffer (kchunk+NB-1) % NB == (kchunk-1) % NB was read by the store of chunk kchunk-1, which the
+            // wait above retired -> it can receive the residual of chunk kchunk+NB-1
+            if (ring_on) prefetch_resid();
           }
           ++kchunk;
         }
@@ -349,8 +403,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 template <int BN, int EPI>
 static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3,
-                  const CUtensorMap& w, const CUtensorMap& d, const GemmConvParams& p, cudaStream_t st) {
-  using C = Cfg<BN>;
+                  const CUtensorMap& w, const CUtensorMap& d, const CUtensorMap& rmap, const GemmConvParams& p,
+                  cudaStream_t st) {
+  using C = Cfg<BN, UseRing<BN, EPI>::value>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_conv_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -361,7 +416,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms()) grid = num_sms();
   if (grid <= 0) return I360_OK;
-  gemm_conv_kernel<BN, EPI><<<grid, kThreads, C::kSmemBytes, st>>>(a, a2, a3, w, d, p);
+  gemm_conv_kernel<BN, EPI><<<grid, kThreads, C::kSmemBytes, st>>>(a, a2, a3, w, d, rmap, p);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -393,24 +448,25 @@ static int pick_epi(const GemmConvParams& p) {
 
 template <int BN>
 static int dispatch_epi(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3, const CUtensorMap& w,
-                        const CUtensorMap& d, const GemmConvParams& p, cudaStream_t st) {
+                        const CUtensorMap& d, const CUtensorMap& r, const GemmConvParams& p, cudaStream_t st) {
   switch (pick_epi(p)) {
-    case EPI_PLAIN: return launch<BN, EPI_PLAIN>(a, a2, a3, w, d, p, st);
-    case EPI_GEGLU: return launch<BN, EPI_GEGLU>(a, a2, a3, w, d, p, st);
-    case EPI_RESID: return launch<BN, EPI_RESID>(a, a2, a3, w, d, p, st);
-    case EPI_ROWVEC: return launch<BN, EPI_ROWVEC>(a, a2, a3, w, d, p, st);
-    case EPI_ACT: return launch<BN, EPI_ACT>(a, a2, a3, w, d, p, st);
-    default: return launch<BN, EPI_GENERAL>(a, a2, a3, w, d, p, st);
+    case EPI_PLAIN: return launch<BN, EPI_PLAIN>(a, a2, a3, w, d, r, p, st);
+    case EPI_GEGLU: return launch<BN, EPI_GEGLU>(a, a2, a3, w, d, r, p, st);
+    case EPI_RESID: return launch<BN, EPI_RESID>(a, a2, a3, w, d, r, p, st);
+    case EPI_ROWVEC: return launch<BN, EPI_ROWVEC>(a, a2, a3, w, d, r, p, st);
+    case EPI_ACT: return launch<BN, EPI_ACT>(a, a2, a3, w, d, r, p, st);
+    default: return launch<BN, EPI_GENERAL>(a, a2, a3, w, d, r, p, st);
   }
 }
 
 static int dispatch(int bn, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3,
-                    const CUtensorMap& w, const CUtensorMap& d, const GemmConvParams& p, cudaStream_t st) {
+                    const CUtensorMap& w, const CUtensorMap& d, const CUtensorMap& r, const GemmConvParams& p,
+                    cudaStream_t st) {
   switch (bn) {
-    case 64: return dispatch_epi<64>(a, a2, a3, w, d, p, st);
-    case 128: return dispatch_epi<128>(a, a2, a3, w, d, p, st);
-    case 160: return dispatch_epi<160>(a, a2, a3, w, d, p, st);
-    case 256: return dispatch_epi<256>(a, a2, a3, w, d, p, st);
+    case 64: return dispatch_epi<64>(a, a2, a3, w, d, r, p, st);
+    case 128: return dispatch_epi<128>(a, a2, a3, w, d, r, p, st);
+    case 160: return dispatch_epi<160>(a, a2, a3, w, d, r, p, st);
+    case 256: return dispatch_epi<256>(a, a2, a3, w, d, r, p, st);
   }
   return I360_ERR_ARG;
 }
@@ -453,7 +509,12 @@ extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long 
   uint64_t dD[2] = {(uint64_t)p.n_out, (uint64_t)M}; uint64_t sD[1] = {(uint64_t)ldd * 2};
   uint32_t bD[2] = {32, BM};
   r = get_tmap_bf16(&td, D, 2, dD, sD, bD, 2); if (r) return r;
-  return dispatch(bn, ta, ta, ta, tw, td, p, static_cast<cudaStream_t>(stream));
+  CUtensorMap tr = td;
+  if (resid) {
+    uint64_t sR[1] = {(uint64_t)ldr * 2};
+    r = get_tmap_bf16(&tr, resid, 2, dD, sR, bD, 2); if (r) return r;
+  }
+  return dispatch(bn, ta, ta, ta, tw, td, tr, p, static_cast<cudaStream_t>(stream));
 }
 
 // x: NHWC [B,H,W,Cin] (H,W include any materialised halo); Wt: [Cout, 9*Cin + C2 + C3] with the
@@ -511,13 +572,15 @@ extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, co
   uint64_t dW[2] = {(uint64_t)Ktot, (uint64_t)Cout}; uint64_t sW[1] = {(uint64_t)Ktot * 2};
   uint32_t bW[2] = {BK, (uint32_t)bn};
   r = get_tmap_bf16(&tw, Wt, 2, dW, sW, bW, 3); if (r) return r;
-  CUtensorMap td;
+  CUtensorMap td, tr;
   {
     const int Wo = W - 2 * crop;
     uint64_t d[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)H, (uint64_t)B};
     uint64_t s[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, (uint64_t)H * Wo * Cout * 2};
     uint32_t b[4] = {32, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
     r = get_tmap_bf16(&td, D, 4, d, s, b, 2); if (r) return r;
+    tr = td;
+    if (resid) { r = get_tmap_bf16(&tr, resid, 4, d, s, b, 2); if (r) return r; }
   }
-  return dispatch(bn, ta, ta2, ta3, tw, td, p, static_cast<cudaStream_t>(stream));
+  return dispatch(bn, ta, ta2, ta3, tw, td, tr, p, static_cast<cudaStream_t>(stream));
 }
