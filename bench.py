@@ -284,6 +284,16 @@ def kernel_roofline(pipe, inp, size, one_step):
             "peak_source": pk["source"] + " (bf16_tflops_sustained)", "launches_per_step": gc_n,
             "avg_launch_ms": round(gc_ms / max(1, gc_n), 4), "alg_flops_per_step": flops["gemm"] + flops["conv"],
             "share_of_step_kernel_time": round(gc_ms / total, 4) if total else None}
+    # DRAM traffic per launch of the same kernel: dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu
+    # capture of this command at this workload (profiles/r01_engine_traffic.json); valid only for the C3 workload.
+    tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_engine_traffic.json")
+    if os.path.exists(tj) and size is SIZES["c3"]:
+        with open(tj) as f:
+            t = json.load(f)
+        if t.get("launches") == gc_n:
+            roof["traffic"] = t["dram_bytes_per_launch"]
+            roof["traffic_source"] = t["source"]
+            roof["alg_bytes_note"] = "tensor-bound kernel: achieved/peak are FLOP-based; traffic is DRAM bytes per launch (cold cache, ncu)"
     breakdown = {n: {"launches": c, "ms": round(ms, 3)} for n, (c, ms) in sorted(per.items(), key=lambda kv: -kv[1][1])}
     agg = {}
     for kind, M, N, K, act, idx in shapes:

@@ -21,6 +21,7 @@
 //     batch and heads (only mask[0] is used, :70).
 #include "common.cuh"
 #include "tmap.h"
+#include <stdlib.h>
 
 namespace i360 {
 
@@ -42,6 +43,7 @@ struct AttnParams {
   bf16* o; long long os1, os2, os3; int o_col0;
   int accumulate;             // out = bf16(out + bf16(O))   (IP-adapter branch sum, attention.py:148)
   int has_bias; int bias_rows, bias_cols;
+  int dbg;                    // I360_ATTN_DBG ablation bits (profiling only): 1 skip pass 1, 2 no MUFU, 4 no P store
 };
 
 constexpr int kAttnThreads = 320;   // warp0 TMA, warp1 MMA, warps 2..9 softmax (2 threads per query row)
@@ -71,12 +73,13 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 template <bool BIAS, bool MASKED>
 __device__ __forceinline__ void softmax_tile(uint32_t tS_row, const uint8_t* sB, uint8_t* sP, int row, int limit,
                                              float scale_log2, float& m_run, float& l_run, float& alpha, int cbeg,
-                                             bf16* xmax_mine, const bf16* xmax_other) {
+                                             bf16* xmax_mine, const bf16* xmax_other, int dbg = 0) {
   const float LOG2E = 1.4426950408889634f;
   const uint32_t rsw = static_cast<uint32_t>(row & 7);
   float mx = -INFINITY;
+  if (dbg & 1) mx = 8.0f;
 #pragma unroll 1
-  for (int c = cbeg; c < cbeg + 64; c += 32) {
+  for (int c = cbeg; c < cbeg + ((dbg & 1) ? 0 : 64); c += 32) {
     uint32_t v[32];
     tmem_ld_x32(tS_row + c, v);
     tmem_ld_wait();
@@ -131,7 +134,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS_row, const uint8_t* sB,
         float2 off = nm2;
         if (BIAS) off = ffma2(make_float2(bv[e], bv[e + 1]), l2e2, nm2);
         const float2 t = ffma2(make_float2(__uint_as_float(v[g * 8 + e]), __uint_as_float(v[g * 8 + e + 1])), sc2, off);
-        float2 pe = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+        float2 pe = (dbg & 2) ? make_float2(t.x * 1e-3f, t.y * 1e-3f) : make_float2(fast_exp2(t.x), fast_exp2(t.y));
         if (MASKED) {
           if (cc + e >= limit) pe.x = 0.f;
           if (cc + e + 1 >= limit) pe.y = 0.f;
@@ -139,8 +142,9 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS_row, const uint8_t* sB,
         sum2 = fadd2(sum2, pe);
         pk[e >> 1] = pack_bf16x2(pe.x, pe.y);
       }
-      *reinterpret_cast<uint4*>(sP + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ rsw) << 4)) =
-          make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      if (!(dbg & 4))
+        *reinterpret_cast<uint4*>(sP + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ rsw) << 4)) =
+            make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
   l_run = l_run * alpha + (sum2.x + sum2.y);
@@ -285,7 +289,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_after();
       if (BIAS) mbar_wait(b_full, j & 1);
       float alpha;
-      if (limit >= 128) softmax_tile<BIAS, false>(tS + lane_sel, sB, sP, row, limit, p.scale_log2, m_run, l_run, alpha, half * 64, xmine, xother);
+      if (limit >= 128) softmax_tile<BIAS, false>(tS + lane_sel, sB, sP, row, limit, p.scale_log2, m_run, l_run, alpha, half * 64, xmine, xother, p.dbg);
       else              softmax_tile<BIAS, true>(tS + lane_sel, sB, sP, row, limit, p.scale_log2, m_run, l_run, alpha, half * 64, xmine, xother);
       fence_proxy_async_smem();       // P visible to the tensor core (async proxy)
       tc_fence_before();
@@ -414,6 +418,7 @@ extern "C" int i360_attention_bf16(const I360TokenView* q, const I360TokenView* 
   p.o = static_cast<bf16*>(const_cast<void*>(o->ptr)); p.os1 = o->s1; p.os2 = o->s2; p.os3 = o->s3; p.o_col0 = o->col0;
   p.accumulate = accumulate;
   p.has_bias = bias != nullptr; p.bias_rows = bias_rows; p.bias_cols = bias_cols;
+  { const char* e = getenv("I360_ATTN_DBG"); p.dbg = e ? atoi(e) : 0; }
   CUtensorMap tq, tk, tv, tb;
   int r = make_view_map(&tq, *q, head_dim, p.q.box1, p.q.box3); if (r) return r;
   r = make_view_map(&tk, *k, head_dim, p.kv.box1, p.kv.box3); if (r) return r;
