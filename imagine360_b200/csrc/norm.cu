@@ -22,11 +22,18 @@ struct GnSrc {
   int H, Wsrc, pad; // virtual width = Wsrc + 2*pad, column wv reads (wv - pad) mod Wsrc
 };
 
-__device__ __forceinline__ uint4 gn_load(const GnSrc& s, int b, long long pix, int v, int Wv) {
-  const int h = static_cast<int>(pix / Wv);
-  int w = static_cast<int>(pix - static_cast<long long>(h) * Wv) - s.pad;
-  w = (w % s.Wsrc + s.Wsrc) % s.Wsrc;
-  const long long p = (static_cast<long long>(b) * s.H + h) * s.Wsrc + w;
+// pix is the pixel index inside one image of the virtual (padded) tensor; 32-bit on purpose (a 64-bit divide
+// per 16-byte load used to cost more issue slots than the arithmetic of the whole vector)
+__device__ __forceinline__ uint4 gn_load(const GnSrc& s, int b, int pix, int v, int Wv) {
+  long long p;
+  if (s.pad == 0) {
+    p = static_cast<long long>(b) * s.H * s.Wsrc + pix;
+  } else {
+    const int h = static_cast<int>(static_cast<unsigned>(pix) / static_cast<unsigned>(Wv));
+    int w = pix - h * Wv - s.pad;
+    if (w < 0) w += s.Wsrc; else if (w >= s.Wsrc) w -= s.Wsrc;          // pad <= Wsrc
+    p = (static_cast<long long>(b) * s.H + h) * s.Wsrc + w;
+  }
   const int nv1 = s.C1 >> 3;
   const bf16* ptr = (v < nv1) ? s.x1 + p * s.C1 + v * 8 : s.x2 + p * s.C2 + (v - nv1) * 8;
   return *reinterpret_cast<const uint4*>(ptr);
@@ -37,64 +44,73 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
+// Loads in flight per thread.  4 (not 8) keeps both kernels under 56 registers so three 384-thread CTAs stay resident
+// per SM: the ncu capture of the 8-deep version showed ONE resident CTA (88 regs) and 18 % warp occupancy.
+constexpr int kGnDepth = 4;
+
 // grid (chunks, B); block = R * nvec threads; dynamic smem = R*C*2 floats
-__global__ void gn_stats_kernel(GnSrc s, int groups, int chunk_pixels, double* __restrict__ stats) {
+__global__ void __launch_bounds__(384, 3) gn_stats_kernel(GnSrc s, int groups, int chunk_pixels, double* __restrict__ stats) {
   extern __shared__ float sm[];
   const int C = s.C1 + s.C2, nvec = C >> 3, R = blockDim.x / nvec;
   const int Wv = s.Wsrc + 2 * s.pad;
-  const long long npix = static_cast<long long>(s.H) * Wv;
+  const int npix = s.H * Wv;
   const int b = blockIdx.y;
   const int r = threadIdx.x / nvec, v = threadIdx.x % nvec;
-  const long long p0 = static_cast<long long>(blockIdx.x) * chunk_pixels;
-  long long p1 = p0 + chunk_pixels; if (p1 > npix) p1 = npix;
-  float s1[8], s2[8];
+  const int p0 = blockIdx.x * chunk_pixels;
+  int p1 = p0 + chunk_pixels; if (p1 > npix) p1 = npix;
+  float2 s1[4], s2[4];                            // packed pairs: FADD2 / FFMA2
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (int j = 0; j < 4; ++j) { s1[j] = make_float2(0.f, 0.f); s2[j] = make_float2(0.f, 0.f); }
+  auto acc = [&](const uint4& u) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      s1[j] = fadd2(s1[j], f); s2[j] = ffma2(f, f, s2[j]);
+    }
+  };
   if (r < R) {
-    long long p = p0 + r;
-    for (; p + 7LL * R < p1; p += 8LL * R) {       // 8 independent 16-byte loads in flight per thread
-      uint4 u[8];
+    int p = p0 + r;
+    for (; p + (kGnDepth - 1) * R < p1; p += kGnDepth * R) {   // kGnDepth independent 16-byte loads in flight per thread
+      uint4 u[kGnDepth];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) u[k] = gn_load(s, b, p + static_cast<long long>(k) * R, v, Wv);
+      for (int k = 0; k < kGnDepth; ++k) u[k] = gn_load(s, b, p + k * R, v, Wv);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float f[8];
-        unpack8(u[k], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] += f[j] * f[j]; }
-      }
+      for (int k = 0; k < kGnDepth; ++k) acc(u[k]);
     }
-    for (; p < p1; p += R) {
-      float f[8];
-      unpack8(gn_load(s, b, p, v, Wv), f);
+    for (; p < p1; p += R) acc(gn_load(s, b, p, v, Wv));
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] += f[j] * f[j]; }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sm[(r * C + v * 8 + j) * 2] = s1[j];
-      sm[(r * C + v * 8 + j) * 2 + 1] = s2[j];
+    for (int j = 0; j < 4; ++j) {
+      sm[(r * C + v * 8 + 2 * j) * 2] = s1[j].x;     sm[(r * C + v * 8 + 2 * j) * 2 + 1] = s2[j].x;
+      sm[(r * C + v * 8 + 2 * j + 1) * 2] = s1[j].y; sm[(r * C + v * 8 + 2 * j + 1) * 2 + 1] = s2[j].y;
     }
   }
   __syncthreads();
+  // fold the R pixel lanes per channel (conflict-free: consecutive threads read consecutive channels) ...
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int rr = 0; rr < R; ++rr) { a += sm[(rr * C + c) * 2]; q += sm[(rr * C + c) * 2 + 1]; }
+    sm[c * 2] = a; sm[c * 2 + 1] = q;             // row 0 of the table: only this thread touches channel c
+  }
+  __syncthreads();
+  // ... then the channels of each group, in fp64, into the global accumulators
   const int gs = C / groups;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double a = 0.0, q = 0.0;
-    for (int rr = 0; rr < R; ++rr)
-      for (int c = g * gs; c < (g + 1) * gs; ++c) { a += sm[(rr * C + c) * 2]; q += sm[(rr * C + c) * 2 + 1]; }
+    for (int c = g * gs; c < (g + 1) * gs; ++c) { a += sm[c * 2]; q += sm[c * 2 + 1]; }
     atomicAdd(&stats[(static_cast<long long>(b) * groups + g) * 2], a);
     atomicAdd(&stats[(static_cast<long long>(b) * groups + g) * 2 + 1], q);
   }
 }
 
 // grid (chunks, B); block = R * nvec; dynamic smem = 2*C floats (scale, shift)
-__global__ void gn_apply_kernel(GnSrc s, int groups, int chunk_pixels, const double* __restrict__ stats,
+__global__ void __launch_bounds__(384, 3) gn_apply_kernel(GnSrc s, int groups, int chunk_pixels, const double* __restrict__ stats,
                                 const bf16* __restrict__ gamma, const bf16* __restrict__ beta, float eps,
                                 int do_silu, double count, bf16* __restrict__ out) {
   extern __shared__ float sm[];
   const int C = s.C1 + s.C2, nvec = C >> 3, R = blockDim.x / nvec;
   const int Wv = s.Wsrc + 2 * s.pad;
-  const long long npix = static_cast<long long>(s.H) * Wv;
+  const int npix = s.H * Wv;
   const int b = blockIdx.y;
   const int gs = C / groups;
   const double n = count > 0.0 ? count : static_cast<double>(npix) * gs;
@@ -103,7 +119,7 @@ __global__ void gn_apply_kernel(GnSrc s, int groups, int chunk_pixels, const dou
     const double m = stats[(static_cast<long long>(b) * groups + g) * 2] / n;
     double var = stats[(static_cast<long long>(b) * groups + g) * 2 + 1] / n - m * m;
     if (var < 0.0) var = 0.0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float rstd = rsqrtf(static_cast<float>(var) + eps);   // mean / variance in fp64, rstd in fp32 (2 ulp)
     const float a = rstd * __bfloat162float(gamma[c]);
     sm[c] = a;
     sm[C + c] = __bfloat162float(beta[c]) - static_cast<float>(m) * a;
@@ -111,109 +127,102 @@ __global__ void gn_apply_kernel(GnSrc s, int groups, int chunk_pixels, const dou
   __syncthreads();
   const int r = threadIdx.x / nvec, v = threadIdx.x % nvec;
   if (r >= R) return;
-  const long long p0 = static_cast<long long>(blockIdx.x) * chunk_pixels;
-  long long p1 = p0 + chunk_pixels; if (p1 > npix) p1 = npix;
-  float a[8], sh[8];
+  const int p0 = blockIdx.x * chunk_pixels;
+  int p1 = p0 + chunk_pixels; if (p1 > npix) p1 = npix;
+  float2 a[4], sh[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { a[j] = sm[v * 8 + j]; sh[j] = sm[C + v * 8 + j]; }
-  auto emit = [&](const uint4& u, long long pp) {
-    float f[8];
-    unpack8(u, f);
+  for (int j = 0; j < 4; ++j) {
+    a[j] = make_float2(sm[v * 8 + 2 * j], sm[v * 8 + 2 * j + 1]);
+    sh[j] = make_float2(sm[C + v * 8 + 2 * j], sm[C + v * 8 + 2 * j + 1]);
+  }
+  bf16* const ob = out + static_cast<long long>(b) * npix * C + v * 8;
+  auto emit = [&](const uint4& u, int pp) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      f[j] = f[j] * a[j] + sh[j];
-      if (do_silu) f[j] = silu(f[j]);
+    for (int j = 0; j < 4; ++j) {
+      float2 f = ffma2(unpack_bf16x2(w[j]), a[j], sh[j]);
+      if (do_silu) f = silu2(f);
+      o[j] = pack_bf16x2(f.x, f.y);
     }
-    *reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * npix + pp) * C + v * 8) =
-        make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                   pack_bf16x2(f[6], f[7]));
+    *reinterpret_cast<uint4*>(ob + static_cast<long long>(pp) * C) = make_uint4(o[0], o[1], o[2], o[3]);
   };
-  long long p = p0 + r;
-  for (; p + 7LL * R < p1; p += 8LL * R) {
-    uint4 u[8];
+  int p = p0 + r;
+  for (; p + (kGnDepth - 1) * R < p1; p += kGnDepth * R) {
+    uint4 u[kGnDepth];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) u[k] = gn_load(s, b, p + static_cast<long long>(k) * R, v, Wv);
+    for (int k = 0; k < kGnDepth; ++k) u[k] = gn_load(s, b, p + k * R, v, Wv);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) emit(u[k], p + static_cast<long long>(k) * R);
+    for (int k = 0; k < kGnDepth; ++k) emit(u[k], p + k * R);
   }
   for (; p < p1; p += R) emit(gn_load(s, b, p, v, Wv), p);
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, row kept in registers (C <= 8*32*MAXV)
+// LayerNorm: LPR lanes per row (8 / 16 / 32 -> 4 / 2 / 1 rows per warp), up to 5 16-byte vectors per lane,
+// so C = 320 / 640 / 1280 keep every lane busy; the row lives in registers, gamma / beta in shared memory.
 // ---------------------------------------------------------------------------------------------
-template <int MAXV>
-__global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
-                                 long long M, int C, const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
-                                 float eps, const bf16* __restrict__ pre_add, int pre_div_a, int pre_mod_a,
-                                 int pre_mul_a, int pre_mod_b,
-                                 const float* __restrict__ post_add, int post_div, int post_mod) {
-  const int lane = threadIdx.x & 31, nvec = C >> 3;
-  const long long wstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-  long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  // narrow rows: gamma / beta stay in registers for every row this warp normalises (wide rows re-read them
-  // from L1 to keep the register footprint, and with it the number of rows in flight per SM, in check)
-  constexpr bool kCacheGB = (MAXV <= 2);
-  float gw[kCacheGB ? MAXV : 1][8], bw[kCacheGB ? MAXV : 1][8];
-  if (kCacheGB) {
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
-      if (v < nvec) {
-        unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gw[kCacheGB ? i : 0]);
-        unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bw[kCacheGB ? i : 0]);
-      }
-    }
+template <int LPR>
+__global__ void __launch_bounds__(256, 2)
+layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                 long long M, int C, const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
+                 float eps, const bf16* __restrict__ pre_add, int pre_div_a, int pre_mod_a,
+                 int pre_mul_a, int pre_mod_b,
+                 const float* __restrict__ post_add, int post_div, int post_mod) {
+  constexpr int VPL = 5, RPW = 32 / LPR, PD = 2;
+  extern __shared__ uint4 ln_gb[];                 // [nvec] gamma vectors, then [nvec] beta vectors
+  const int nvec = C >> 3;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    ln_gb[v] = *reinterpret_cast<const uint4*>(gamma + v * 8);
+    ln_gb[nvec + v] = *reinterpret_cast<const uint4*>(beta + v * 8);
   }
-  // PD rows are kept in flight per warp (register ring): with ~16 resident warps per SM a single prefetched row
-  // leaves too few bytes outstanding to cover HBM latency
-  constexpr int PD = (MAXV <= 2) ? 4 : 2;
-  uint4 ring[PD][MAXV];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
+  const long long gstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5) * RPW;
+  long long base = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  const float invC = 1.0f / C;
+  // PD row groups in flight per warp (register ring) to cover HBM latency
+  uint4 ring[PD][VPL];
 #pragma unroll
   for (int d = 0; d < PD; ++d) {
-    const long long rr = row + d * wstride;
+    const long long rr = base + d * gstride + sub;
     if (rr < M) {
 #pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int v = lane + i * 32;
+      for (int i = 0; i < VPL; ++i) {
+        const int v = l + i * LPR;
         if (v < nvec) ring[d][i] = *reinterpret_cast<const uint4*>(x + rr * ldx + v * 8);
       }
     }
   }
-  for (; row < M; row += wstride) {
-    uint4 nxt[MAXV];
+  for (; base < M; base += gstride) {              // warp-uniform loop: the shuffles below need every lane
+    const long long row = base + sub;
+    const bool valid = row < M;
+    float2 f[VPL][4];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) nxt[i] = ring[0][i];
+    for (int i = 0; i < VPL; ++i) {
+      f[i][0] = unpack_bf16x2(ring[0][i].x); f[i][1] = unpack_bf16x2(ring[0][i].y);
+      f[i][2] = unpack_bf16x2(ring[0][i].z); f[i][3] = unpack_bf16x2(ring[0][i].w);
+    }
 #pragma unroll
     for (int d = 0; d + 1 < PD; ++d)
 #pragma unroll
-      for (int i = 0; i < MAXV; ++i) ring[d][i] = ring[d + 1][i];
-    float2 f[MAXV][4];                            // packed pairs: the loops below run on FADD2 / FFMA2 / FMUL2
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
-      if (v < nvec) {
-        f[i][0] = unpack_bf16x2(nxt[i].x); f[i][1] = unpack_bf16x2(nxt[i].y);
-        f[i][2] = unpack_bf16x2(nxt[i].z); f[i][3] = unpack_bf16x2(nxt[i].w);
-      }
-    }
-    const long long rn = row + static_cast<long long>(PD) * wstride;   // refill the ring PD rows ahead
+      for (int i = 0; i < VPL; ++i) ring[d][i] = ring[d + 1][i];
+    const long long rn = base + static_cast<long long>(PD) * gstride + sub;   // refill PD groups ahead
     if (rn < M) {
 #pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int v = lane + i * 32;
+      for (int i = 0; i < VPL; ++i) {
+        const int v = l + i * LPR;
         if (v < nvec) ring[PD - 1][i] = *reinterpret_cast<const uint4*>(x + rn * ldx + v * 8);
       }
     }
     // pre-add table row = ((row / div_a) % mod_a) * mul_a + row % mod_b   (view-major PE of WarpAttn's pers tokens)
-    const bf16* pr = pre_add ? pre_add + (((row / pre_div_a) % pre_mod_a) * pre_mul_a + row % pre_mod_b) * C : nullptr;
     float2 sum2 = make_float2(0.f, 0.f);
+    if (pre_add != nullptr && valid) {
+      const bf16* pr = pre_add + (((row / pre_div_a) % pre_mod_a) * pre_mul_a + row % pre_mod_b) * C;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
-      if (v < nvec) {
-        if (pr) {
+      for (int i = 0; i < VPL; ++i) {
+        const int v = l + i * LPR;
+        if (v < nvec) {
           const uint4 u = *reinterpret_cast<const uint4*>(pr + v * 8);
           const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -222,45 +231,41 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16
             f[i][j] = unpack_bf16x2(pack_bf16x2(t.x, t.y));
           }
         }
-        sum2 = fadd2(fadd2(f[i][0], f[i][1]), fadd2(fadd2(f[i][2], f[i][3]), sum2));
       }
     }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      if (l + i * LPR < nvec) sum2 = fadd2(fadd2(f[i][0], f[i][1]), fadd2(fadd2(f[i][2], f[i][3]), sum2));
     float sum = sum2.x + sum2.y;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / C;
+    for (int o = LPR >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * invC;
     const float2 nmean = make_float2(-mean, -mean);
     float2 var2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
-      if (v < nvec) {
+    for (int i = 0; i < VPL; ++i)
+      if (l + i * LPR < nvec) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { f[i][j] = fadd2(f[i][j], nmean); var2 = ffma2(f[i][j], f[i][j], var2); }
       }
-    }
     float var = var2.x + var2.y;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-    const float rstd = rsqrtf(var / C + eps);
+    for (int o = LPR >> 1; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    if (!valid) continue;
+    const float rstd = rsqrtf(var * invC + eps);
     const float2 rstd2 = make_float2(rstd, rstd);
     const float* po = post_add ? post_add + static_cast<long long>((row / post_div) % post_mod) * C : nullptr;
     bf16* yr = y + row * ldy;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
+    for (int i = 0; i < VPL; ++i) {
+      const int v = l + i * LPR;
       if (v < nvec) {
-        float gg[8], bb[8];
-        if (!kCacheGB) {
-          unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gg);
-          unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bb);
-        }
+        const uint4 gq = ln_gb[v], bq = ln_gb[nvec + v];
+        const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w}, bw[4] = {bq.x, bq.y, bq.z, bq.w};
         uint32_t outw[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 g2 = kCacheGB ? make_float2(gw[kCacheGB ? i : 0][2 * j], gw[kCacheGB ? i : 0][2 * j + 1]) : make_float2(gg[2 * j], gg[2 * j + 1]);
-          const float2 b2 = kCacheGB ? make_float2(bw[kCacheGB ? i : 0][2 * j], bw[kCacheGB ? i : 0][2 * j + 1]) : make_float2(bb[2 * j], bb[2 * j + 1]);
-          float2 o = ffma2(f[i][j], fmul2(g2, rstd2), b2);
+          float2 o = ffma2(f[i][j], fmul2(unpack_bf16x2(gw[j]), rstd2), unpack_bf16x2(bw[j]));
           if (po) {
             const float2 r = unpack_bf16x2(pack_bf16x2(o.x, o.y));
             o = fadd2(r, make_float2(po[v * 8 + 2 * j], po[v * 8 + 2 * j + 1]));
@@ -332,10 +337,12 @@ static int gn_geometry(int C, int B, long long npix, int* block, int* chunk, int
   if (nvec <= 0 || nvec > 1024) return I360_ERR_ARG;
   int R = 384 / nvec; if (R < 1) R = 1;
   *block = R * nvec;
-  long long target = (static_cast<long long>(num_sms()) * 4 + B - 1) / B;  // CTAs per image for ~4 waves
+  // CTAs per image: ~12 CTAs per SM in total, so the 3-5 resident CTAs per SM turn over a few times and the last
+  // wave's imbalance stays small (one CTA per image left 640 CTAs on 148 SMs: 5 vs 4 per SM, 14 % idle)
+  long long target = (static_cast<long long>(num_sms()) * 12 + B - 1) / B;
   if (target < 1) target = 1;
   long long cp = (npix + target - 1) / target;
-  const long long minp = static_cast<long long>(R) * 4;
+  const long long minp = static_cast<long long>(R) * kGnDepth * 2;
   if (cp < minp) cp = minp;
   *chunk = static_cast<int>(cp);
   *chunks = static_cast<int>((npix + cp - 1) / cp);
@@ -390,21 +397,23 @@ extern "C" int i360_layernorm(const void* x, long long ldx, void* y, long long l
   if (pre_add && (pre_div_a <= 0 || pre_mod_a <= 0 || pre_mod_b <= 0)) return I360_ERR_ARG;
   if (post_add && (post_div <= 0 || post_mod <= 0)) return I360_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int warps = 8;
-  long long blocks = (M + warps - 1) / warps;
-  const long long cap = static_cast<long long>(num_sms()) * 8;     // persistent warps: each loops over rows
+  const int nvec = C / 8, warps = 8;
+  const int lpr = nvec <= 8 * 5 ? 8 : (nvec <= 16 * 5 ? 16 : 32);
+  if (nvec > 32 * 5) return I360_ERR_UNSUPPORTED;
+  const int rows_per_block = warps * (32 / lpr);
+  long long blocks = (M + rows_per_block - 1) / rows_per_block;
+  const long long cap = static_cast<long long>(num_sms()) * 2;     // persistent: 2 resident blocks per SM loop over rows
   if (blocks > cap) blocks = cap;
   const unsigned grid = static_cast<unsigned>(blocks);
   const bf16 *xx = static_cast<const bf16*>(x), *g = static_cast<const bf16*>(gamma), *b = static_cast<const bf16*>(beta);
   const bf16* pa = static_cast<const bf16*>(pre_add);
   bf16* yy = static_cast<bf16*>(y);
-  const int nvec = C / 8;
-  if (nvec <= 32 * 2)
-    layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(xx, ldx, yy, ldy, M, C, g, b, eps, pa, pre_div_a, pre_mod_a, pre_mul_a, pre_mod_b, post_add, post_div, post_mod);
-  else if (nvec <= 32 * 5)
-    layernorm_kernel<5><<<grid, warps * 32, 0, st>>>(xx, ldx, yy, ldy, M, C, g, b, eps, pa, pre_div_a, pre_mod_a, pre_mul_a, pre_mod_b, post_add, post_div, post_mod);
-  else
-    return I360_ERR_UNSUPPORTED;
+  const size_t smem = static_cast<size_t>(nvec) * 2 * sizeof(uint4);
+#define I360_LN_LAUNCH(L) layernorm_kernel<L><<<grid, warps * 32, smem, st>>>(xx, ldx, yy, ldy, M, C, g, b, eps, pa, pre_div_a, pre_mod_a, pre_mul_a, pre_mod_b, post_add, post_div, post_mod)
+  if (lpr == 8) I360_LN_LAUNCH(8);
+  else if (lpr == 16) I360_LN_LAUNCH(16);
+  else I360_LN_LAUNCH(32);
+#undef I360_LN_LAUNCH
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
