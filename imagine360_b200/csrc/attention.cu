@@ -2,14 +2,13 @@
 //
 // One CTA = one 128-row query tile of one (batch item, head).  Warp roles (192 threads):
 //   warp0  TMA producer : Q once, then K_j / V_j (/ bias_j) tiles through 2-stage mbarrier rings
-//   warp1  MMA issuer   : S = Q K_j^T  -> TMEM;  O_j = P_j V_j -> TMEM   (one elected lane)
+//   warp1  MMA issuer   : S_j = Q K_j^T -> TMEM;  O_h += P_j[:, h] V_j[h, :] -> TMEM, h = 0, 1   (one elected lane)
 //   warps 2..9 softmax  : TWO threads per query row (warp w and w+4 share a TMEM lane quarter): each owns 64 of
-//                         the 128 key columns of S and half of O's columns; they exchange only the row maximum
-//                         through smem.  TMEM S -> online softmax (exp2, fp32) -> P (bf16) into swizzled smem as
-//                         the next MMA's A operand; O_j accumulated in registers with the running-max rescale;
-//                         final O / l -> bf16 -> global.
-// Two CTAs are co-resident per SM (<= 113 KB smem, 256 TMEM columns each) so one CTA's softmax
-// overlaps the other's MMAs.
+//                         the 128 key columns of every tile as an INDEPENDENT online softmax (own max, own sum, own
+//                         TMEM accumulator), merged once at the end.  Per tile: S -> registers (one TMEM read, S
+//                         released at once so S_{j+1} overlaps), exp2 in fp32, P (bf16) into swizzled smem as the
+//                         next MMA's A operand.  The accumulators stay in TMEM (use_acc) and are rescaled lazily.
+// Two CTAs are co-resident per SM (<= 113 KB smem, 256 TMEM columns each).
 //
 // Q, K, V and O are addressed as strided 4-D token views [channels, d1, d2, d3] so that all of the
 // reference's attention variants run without any gather/transpose copy:
@@ -43,7 +42,6 @@ struct AttnParams {
   bf16* o; long long os1, os2, os3; int o_col0;
   int accumulate;             // out = bf16(out + bf16(O))   (IP-adapter branch sum, attention.py:148)
   int has_bias; int bias_rows, bias_cols;
-  int dbg;                    // I360_ATTN_DBG ablation bits (profiling only): 1 skip pass 1, 2 no MUFU, 4 no P store
 };
 
 constexpr int kAttnThreads = 320;   // warp0 TMA, warp1 MMA, warps 2..9 softmax (2 threads per query row)
@@ -57,7 +55,7 @@ struct AttnCfg {
   static constexpr int kBiasBytes = 128 * 128 * 2;
   static constexpr uint32_t kSwz = (HD == 64) ? SWZ_128B : SWZ_64B;
   static constexpr int kSBO = 8 * kRowBytes;
-  static constexpr int kTmemCols = 256;   // S: 128, O: HD
+  static constexpr int kTmemCols = 256;   // S: 128, O_half 0 / 1: HD each
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -65,90 +63,96 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
-// One KV tile of the online softmax for one query row (= one thread): two passes over the 128 fp32 logits in
-// TMEM.  Pass 1 reduces the row maximum; pass 2 evaluates p = exp2(s*scale - m) with one packed FFMA2 per two
-// logits, accumulates the row sum with FADD2 and writes bf16 P into the 128B-swizzled smem tile that is the A
-// operand of the P.V MMA.  MASKED (partial tiles) and BIAS (WarpAttn) are compile-time so the common case -- a
-// full, unbiased tile of the spatial self-attention -- carries no selects and no per-element scale multiply.
-template <bool BIAS, bool MASKED>
-__device__ __forceinline__ void softmax_tile(uint32_t tS_row, const uint8_t* sB, uint8_t* sP, int row, int limit,
-                                             float scale_log2, float& m_run, float& l_run, float& alpha, int cbeg,
-                                             bf16* xmax_mine, const bf16* xmax_other, int dbg = 0) {
+// One KV tile of the online softmax for one (query row, column half) = one thread.  The thread's 64 fp32 logits are
+// read from TMEM ONCE into registers and S is released to the MMA warp immediately (S_{j+1} = Q K_{j+1}^T then runs
+// under this tile's exponentials).  The two column halves of a row are independent online softmaxes, each with its
+// own running maximum, row sum and TMEM accumulator O_half (+= P_half V_half, accumulated by the tensor core), so
+// no per-tile exchange or CTA barrier exists; they are merged once after the last tile.  The accumulator is only
+// rescaled when the maximum grew by more than 2^8 ("lazy rescale": any common shift is a valid stabiliser, P <= 256
+// is exact enough in bf16 and fp32); that path is rare after the first tiles and warp-uniform (tcgen05.ld/st).
+// MASKED (partial tiles) and BIAS (WarpAttn) are compile-time so the common case -- a full, unbiased tile of the
+// spatial self-attention -- carries no selects and no per-element scale multiply.
+template <int HD, bool BIAS, bool MASKED>
+__device__ __forceinline__ void softmax_tile(uint32_t tS_mine, uint32_t tO_mine, const uint8_t* sB, uint8_t* sP,
+                                             int row, int limit, float scale_log2, float& m_used, float& l_run,
+                                             int cbeg, bool first, uint64_t* s_empty, uint64_t* pv_done,
+                                             uint32_t pv_parity) {
   const float LOG2E = 1.4426950408889634f;
   const uint32_t rsw = static_cast<uint32_t>(row & 7);
+  uint32_t v[64];
+  tmem_ld_x32(tS_mine, v);
+  tmem_ld_x32(tS_mine + 32, v + 32);
+  tmem_ld_wait();
+  tc_fence_before();
+  mbar_arrive(s_empty);                            // S_j is in registers: the MMA warp may overwrite it
   float mx = -INFINITY;
-  if (dbg & 1) mx = 8.0f;
-#pragma unroll 1
-  for (int c = cbeg; c < cbeg + ((dbg & 1) ? 0 : 64); c += 32) {
-    uint32_t v[32];
-    tmem_ld_x32(tS_row + c, v);
-    tmem_ld_wait();
-    if (!BIAS && !MASKED) {
+  if (!BIAS && !MASKED) {
 #pragma unroll
-      for (int e = 0; e < 32; e += 2) mx = fmax3(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-    } else {
+    for (int e = 0; e < 64; e += 2) mx = fmax3(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+    mx *= scale_log2;                              // scale > 0: max commutes with the scaling
+  } else {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float bv[8];
-        if (BIAS) {
-          const int cc = c + g * 8;
-          unpack8(*reinterpret_cast<const uint4*>(sB + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ rsw) << 4)), bv);
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float sv = __uint_as_float(v[g * 8 + e]) * scale_log2;
-          if (BIAS) sv = fmaf(bv[e], LOG2E, sv);
-          if (MASKED && (c + g * 8 + e >= limit)) sv = -INFINITY;
-          mx = fmaxf(mx, sv);
-        }
-      }
-    }
-  }
-  if (!BIAS && !MASKED) mx *= scale_log2;          // scale > 0: max commutes with the scaling
-  // the partner thread (other half of the key columns of this row) contributes its maximum through smem.  Both
-  // sides use the bf16-ROUNDED maxima (512 B exchange buffer keeps two CTAs per SM): any common shift is a valid
-  // softmax stabiliser, it only has to be identical in both halves and within ~2^0.2 of the true maximum.
-  const bf16 mxb = __float2bfloat16(mx);
-  *xmax_mine = mxb;
-  named_bar_sync(1, 256);
-  mx = fmaxf(__bfloat162float(mxb), __bfloat162float(*xmax_other));
-  const float m_new = fmaxf(m_run, mx);
-  alpha = fast_exp2(m_run - m_new);               // first tile: exp2(-inf) = 0
-  const float2 sc2 = make_float2(scale_log2, scale_log2);
-  const float2 nm2 = make_float2(-m_new, -m_new);
-  const float2 l2e2 = make_float2(LOG2E, LOG2E);
-  float2 sum2 = make_float2(0.f, 0.f);
-#pragma unroll 1
-  for (int c = cbeg; c < cbeg + 64; c += 32) {
-    uint32_t v[32];
-    tmem_ld_x32(tS_row + c, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int cc = c + g * 8;
+    for (int g = 0; g < 8; ++g) {
+      const int cc = cbeg + g * 8;
       float bv[8];
       if (BIAS) unpack8(*reinterpret_cast<const uint4*>(sB + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ rsw) << 4)), bv);
-      uint32_t pk[4];
 #pragma unroll
-      for (int e = 0; e < 8; e += 2) {
-        float2 off = nm2;
-        if (BIAS) off = ffma2(make_float2(bv[e], bv[e + 1]), l2e2, nm2);
-        const float2 t = ffma2(make_float2(__uint_as_float(v[g * 8 + e]), __uint_as_float(v[g * 8 + e + 1])), sc2, off);
-        float2 pe = (dbg & 2) ? make_float2(t.x * 1e-3f, t.y * 1e-3f) : make_float2(fast_exp2(t.x), fast_exp2(t.y));
-        if (MASKED) {
-          if (cc + e >= limit) pe.x = 0.f;
-          if (cc + e + 1 >= limit) pe.y = 0.f;
-        }
-        sum2 = fadd2(sum2, pe);
-        pk[e >> 1] = pack_bf16x2(pe.x, pe.y);
+      for (int e = 0; e < 8; ++e) {
+        float sv = __uint_as_float(v[g * 8 + e]) * scale_log2;
+        if (BIAS) sv = fmaf(bv[e], LOG2E, sv);
+        if (MASKED && (cc + e >= limit)) sv = -INFINITY;
+        v[g * 8 + e] = __float_as_uint(sv);       // keep the finished logit (log2 units)
+        mx = fmaxf(mx, sv);
       }
-      if (!(dbg & 4))
-        *reinterpret_cast<uint4*>(sP + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ rsw) << 4)) =
-            make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
-  l_run = l_run * alpha + (sum2.x + sum2.y);
-  m_run = m_new;
+  const float m_new = fmaxf(m_used, mx);
+  const bool need = m_new > m_used + 8.0f;         // also true for the first finite maximum (m_used = -inf)
+  if (__any_sync(0xffffffffu, need)) {
+    const float alpha = (m_new == m_used) ? 1.0f : fast_exp2(m_used - m_new);
+    if (!first) {
+      mbar_wait(pv_done, pv_parity);               // P_{j-1} V_{j-1} has landed in the accumulator
+      tc_fence_after();
+      const float2 al2 = make_float2(alpha, alpha);
+#pragma unroll 1
+      for (int c = 0; c < HD; c += 16) {
+        uint32_t o[16];
+        tmem_ld_x16(tO_mine + c, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          const float2 r = fmul2(make_float2(__uint_as_float(o[e]), __uint_as_float(o[e + 1])), al2);
+          o[e] = __float_as_uint(r.x); o[e + 1] = __float_as_uint(r.y);
+        }
+        tmem_st_x16(tO_mine + c, o);
+      }
+      tmem_st_wait();
+    }
+    l_run *= alpha;
+    m_used = m_new;
+  }
+  // a half row that has not seen a finite logit yet (masked / -inf bias) must not evaluate exp2(-inf + inf)
+  const float msub = (BIAS || MASKED) ? ((m_used == -INFINITY) ? 0.f : m_used) : m_used;
+  const float2 sc2 = make_float2(scale_log2, scale_log2);
+  const float2 nm2 = make_float2(-msub, -msub);
+  float2 sum2 = make_float2(0.f, 0.f);
+  uint32_t pk[32];
+#pragma unroll
+  for (int e = 0; e < 64; e += 2) {
+    const float2 sv = make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+    const float2 t = (!BIAS && !MASKED) ? ffma2(sv, sc2, nm2) : fadd2(sv, nm2);
+    const float2 pe = make_float2(fast_exp2(t.x), fast_exp2(t.y));      // masked columns: exp2(-inf) = 0
+    sum2 = fadd2(sum2, pe);
+    pk[e >> 1] = pack_bf16x2(pe.x, pe.y);
+  }
+  l_run += sum2.x + sum2.y;
+  if (!first) mbar_wait(pv_done, pv_parity);       // the tensor core has finished reading P_{j-1} from smem
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const int cc = cbeg + g * 8;
+    *reinterpret_cast<uint4*>(sP + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ rsw) << 4)) =
+        make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+  }
 }
 
 __device__ __forceinline__ void tile_coords(const AttnOperand& op, int bi, int tile, int& c1, int& c2, int& c3) {
@@ -177,12 +181,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* v_full = bars + 5;     // 2
   uint64_t* v_empty = bars + 7;    // 2
   uint64_t* s_full = bars + 9;     // MMA -> softmax: S_j in TMEM
-  uint64_t* p_full = bars + 10;    // softmax -> MMA: P_j in smem, S_j consumed, O_{j-1} consumed
-  uint64_t* o_full = bars + 11;    // MMA -> softmax: O_j in TMEM
-  uint64_t* b_full = bars + 12;    // TMA -> softmax: bias_j in smem
-  uint64_t* b_empty = bars + 13;   // softmax -> TMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  bf16* xch = reinterpret_cast<bf16*>(bars + 16);            // [2][128] row-max exchange between the two column halves
+  uint64_t* s_empty = bars + 10;   // softmax -> MMA: S_j copied to registers (256 arrivals)
+  uint64_t* p_full = bars + 11;    // 2: softmax half h -> MMA: P_j[:, h*64..] in smem, O_h rescaled if needed (128 arrivals)
+  uint64_t* pv_done = bars + 13;   // 2: MMA -> softmax half h: O_h += P_j V_j retired (P smem free, accumulator readable)
+  uint64_t* b_full = bars + 15;    // TMA -> softmax: bias_j in smem
+  uint64_t* b_empty = bars + 16;   // softmax -> TMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, head = blockIdx.y, bi = blockIdx.z;
@@ -191,8 +195,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     if (BIAS) tma_prefetch_desc(&tmB);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(p_full, 256); mbar_init(o_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+      mbar_init(&p_full[s], 128); mbar_init(&pv_done[s], 1);
+    }
+    mbar_init(s_full, 1); mbar_init(s_empty, 256);
     mbar_init(b_full, 1); mbar_init(b_empty, 256);
     fence_barrier_init();
   }
@@ -201,7 +208,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;      // O_half h at tO + h * HD
 
   int qc1, qc2, qc3;
   tile_coords(p.q, bi, qt, qc1, qc2, qc3);
@@ -235,10 +242,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);   // B (=V) is MN-major
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < p.kv_tiles; ++j) {
+      auto issue_s = [&](int j) {                   // S_j = Q K_j^T
         const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
-        // ---- S_j = Q K_j^T ----
         mbar_wait(&k_full[st], ph);
         tc_fence_after();
         const uint32_t aK = smem_u32(sK + st * C::kKVBytes);
@@ -248,36 +253,45 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                        make_smem_desc(aK + ks * 32, C::kSBO, 16, C::kSwz), idesc_s, ks != 0);
         umma_commit(&k_empty[st]);
         umma_commit(s_full);
-        // ---- O_j = P_j V_j ----
-        mbar_wait(p_full, j & 1);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < p.kv_tiles; ++j) {
+        const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+        if (j + 1 < p.kv_tiles) {                   // runs on the tensor core under the softmax of tile j
+          mbar_wait(s_empty, j & 1);
+          issue_s(j + 1);
+        }
+        // ---- O_h += P_j[:, h*64 .. h*64+64) V_j[h*64 .. h*64+64, :] ----
         mbar_wait(&v_full[st], ph);
-        tc_fence_after();
         const uint32_t aV = smem_u32(sV + st * C::kKVBytes);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_bf16_ss(tO, make_smem_desc(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 1024, 16, SWZ_128B),
-                       make_smem_desc(aV + kk * 16 * C::kRowBytes, C::kSBO, 16, C::kSwz), idesc_o, kk != 0);
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&p_full[h], j & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = h * 4; kk < h * 4 + 4; ++kk)
+            umma_bf16_ss(tO + h * HD, make_smem_desc(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 1024, 16, SWZ_128B),
+                         make_smem_desc(aV + kk * 16 * C::kRowBytes, C::kSBO, 16, C::kSwz), idesc_o,
+                         (j > 0) || (kk != h * 4));
+          umma_commit(&pv_done[h]);
+        }
         umma_commit(&v_empty[st]);
-        umma_commit(o_full);
       }
     }
   } else {
     // ================================ softmax / epilogue ================================
     const int ew = warp & 3;
-    const int half = (warp - 2) >> 2;            // 0: key columns 0..63 / O columns [0, HD/2); 1: the other halves
+    const int half = (warp - 2) >> 2;            // 0: key columns 0..63 of every tile; 1: columns 64..127
     const int row = ew * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
     constexpr int HH = HD / 2;
-    bf16* xmine = xch + half * 128 + row;
-    const bf16* xother = xch + (half ^ 1) * 128 + row;
     // my query token
     const int q_tok = (qt % p.q.n1) * p.q.box1 + row % p.q.box1;
     const int q_view = (qt / p.q.n1) * p.q.box3 + row / p.q.box1;
     const bool q_valid = (q_tok < p.q.d1) && (q_view < p.q.ext3);
-    float m_run = -INFINITY, l_run = 0.f;
-    float acc[HH];
-#pragma unroll
-    for (int i = 0; i < HH; ++i) acc[i] = 0.f;
+    float m_used = -INFINITY, l_run = 0.f;
+    const uint32_t tS_mine = tS + lane_sel + half * 64, tO_mine = tO + lane_sel + half * HD;
 
     for (int j = 0; j < p.kv_tiles; ++j) {
       const int kv_i1 = (j % p.kv.n1) * p.kv.box1, kv_i3 = (j / p.kv.n1) * p.kv.box3;
@@ -288,54 +302,53 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       if (BIAS) mbar_wait(b_full, j & 1);
-      float alpha;
-      if (limit >= 128) softmax_tile<BIAS, false>(tS + lane_sel, sB, sP, row, limit, p.scale_log2, m_run, l_run, alpha, half * 64, xmine, xother, p.dbg);
-      else              softmax_tile<BIAS, true>(tS + lane_sel, sB, sP, row, limit, p.scale_log2, m_run, l_run, alpha, half * 64, xmine, xother);
+      const uint32_t pvp = (j - 1) & 1;
+      if (limit >= 128) softmax_tile<HD, BIAS, false>(tS_mine, tO_mine, sB, sP, row, limit, p.scale_log2, m_used, l_run, half * 64, j == 0, s_empty, &pv_done[half], pvp);
+      else              softmax_tile<HD, BIAS, true>(tS_mine, tO_mine, sB, sP, row, limit, p.scale_log2, m_used, l_run, half * 64, j == 0, s_empty, &pv_done[half], pvp);
       fence_proxy_async_smem();       // P visible to the tensor core (async proxy)
-      tc_fence_before();
-      mbar_arrive(p_full);
+      tc_fence_before();              // ... and the rescaled accumulator (tcgen05.st) ordered before the arrive
+      mbar_arrive(&p_full[half]);
       if (BIAS) mbar_arrive(b_empty);
-      // O_j: my half of the head-dim columns
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-      {
-        uint32_t v[HH];
-        if (HH == 32) tmem_ld_x32(tO + lane_sel + half * HH, v);
-        else          tmem_ld_x16(tO + lane_sel + half * HH, v);
-        tmem_ld_wait();
-        const float2 al2 = make_float2(alpha, alpha);
-#pragma unroll
-        for (int e = 0; e < HH; e += 2) {
-          const float2 r = ffma2(make_float2(acc[e], acc[e + 1]), al2, make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
-          acc[e] = r.x; acc[e + 1] = r.y;
-        }
-      }
-      tc_fence_before();
     }
-    // ---- epilogue: combine the two halves' row sums, write my half of O ----
-    float* lsum = reinterpret_cast<float*>(sP);        // the P tile is dead after the last P.V MMA
-    lsum[half * 128 + row] = l_run;
+    // ---- epilogue: merge the two column halves of my row, write my half of the head-dim columns ----
+    const uint32_t lastp = (p.kv_tiles - 1) & 1;
+    mbar_wait(&pv_done[0], lastp);
+    mbar_wait(&pv_done[1], lastp);
+    tc_fence_after();
+    float2* xml = reinterpret_cast<float2*>(sP);       // the P tile is dead after the last P.V MMA
+    xml[half * 128 + row] = make_float2(m_used, l_run);
     named_bar_sync(1, 256);
-    const float l_tot = l_run + lsum[(half ^ 1) * 128 + row];
-    if (q_valid) {
-      const float inv = 1.0f / l_tot;
-      bf16* dst = p.o + p.o_col0 + head * HD + half * HH + static_cast<long long>(q_tok) * p.os1 +
-                  static_cast<long long>(qc2) * p.os2 +
-                  static_cast<long long>((bi / p.q.A) * p.q.mul + q_view) * p.os3;
+    const float2 oth = xml[(half ^ 1) * 128 + row];
+    const float m_all = fmaxf(m_used, oth.x);
+    const float w_me = (m_used == -INFINITY) ? 0.f : fast_exp2(m_used - m_all);
+    const float w_ot = (oth.x == -INFINITY) ? 0.f : fast_exp2(oth.x - m_all);
+    const float inv = 1.0f / (l_run * w_me + oth.y * w_ot);
+    const float w_lo = (half == 0 ? w_me : w_ot) * inv, w_hi = (half == 0 ? w_ot : w_me) * inv;
+    bf16* dst = p.o + p.o_col0 + head * HD + half * HH + static_cast<long long>(q_tok) * p.os1 +
+                static_cast<long long>(qc2) * p.os2 +
+                static_cast<long long>((bi / p.q.A) * p.q.mul + q_view) * p.os3;
 #pragma unroll
-      for (int c = 0; c < HH; c += 8) {
-        float o[8];
+    for (int c = 0; c < HH; c += 16) {
+      uint32_t lo[16], hi[16];
+      tmem_ld_x16(tO + lane_sel + half * HH + c, lo);
+      tmem_ld_x16(tO + lane_sel + HD + half * HH + c, hi);
+      tmem_ld_wait();
+      if (q_valid) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = acc[c + e] * inv;
-        if (p.accumulate) {
-          const uint4 old = *reinterpret_cast<const uint4*>(dst + c);
-          float prev[8];
-          unpack8(old, prev);
+        for (int g = 0; g < 16; g += 8) {
+          float o[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = prev[e] + __bfloat162float(__float2bfloat16(o[e]));
+          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(lo[g + e]) * w_lo + __uint_as_float(hi[g + e]) * w_hi;
+          if (p.accumulate) {
+            const uint4 old = *reinterpret_cast<const uint4*>(dst + c + g);
+            float prev[8];
+            unpack8(old, prev);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = prev[e] + __bfloat162float(__float2bfloat16(o[e]));
+          }
+          *reinterpret_cast<uint4*>(dst + c + g) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                              pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
         }
-        *reinterpret_cast<uint4*>(dst + c) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                        pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
       }
     }
   }
@@ -348,7 +361,7 @@ template <int HD, bool BIAS>
 static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const CUtensorMap& b,
                        const AttnParams& p, int heads, int batch, cudaStream_t st) {
   using C = AttnCfg<HD>;
-  const int smem = C::kQBytes + 4 * C::kKVBytes + C::kPBytes + (BIAS ? C::kBiasBytes : 0) + 128 + 512;   // barriers + row-max exchange
+  const int smem = C::kQBytes + 4 * C::kKVBytes + C::kPBytes + (BIAS ? C::kBiasBytes : 0) + 256;   // barriers + TMEM slot
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(attention_kernel<HD, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
@@ -418,7 +431,6 @@ extern "C" int i360_attention_bf16(const I360TokenView* q, const I360TokenView* 
   p.o = static_cast<bf16*>(const_cast<void*>(o->ptr)); p.os1 = o->s1; p.os2 = o->s2; p.os3 = o->s3; p.o_col0 = o->col0;
   p.accumulate = accumulate;
   p.has_bias = bias != nullptr; p.bias_rows = bias_rows; p.bias_cols = bias_cols;
-  { const char* e = getenv("I360_ATTN_DBG"); p.dbg = e ? atoi(e) : 0; }
   CUtensorMap tq, tk, tv, tb;
   int r = make_view_map(&tq, *q, head_dim, p.q.box1, p.q.box3); if (r) return r;
   r = make_view_map(&tk, *k, head_dim, p.kv.box1, p.kv.box3); if (r) return r;
