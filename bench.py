@@ -259,6 +259,14 @@ def kernel_roofline(pipe, inp, size, one_step):
         shapes.append(("conv", b * h * wd, wp.shape[0], wp.shape[1], 0, len(timed.get("i360_conv3x3_bf16", []))))
         return orig_conv(x, wp, *args, **kw)
 
+    orig_attn = ops.attention
+
+    def attn(q, k, v, o, heads, head_dim, batch, scale=None, bias=None, accumulate=False):
+        nq, nk = q.d1 * max(1, q.ext3), k.d1 * max(1, k.ext3)
+        shapes.append(("attn", f"batch={batch} heads={heads} hd={head_dim} Nq={nq} Nk={nk} bias={int(bias is not None)} acc={int(accumulate)}",
+                       4.0 * batch * heads * nq * nk * head_dim, 0, 0, len(timed.get("i360_attention_bf16", []))))
+        return orig_attn(q, k, v, o, heads, head_dim, batch, scale=scale, bias=bias, accumulate=accumulate)
+
     class LibProxy:
         def __getattr__(self, n):
             f = getattr(L, n)
@@ -266,13 +274,13 @@ def kernel_roofline(pipe, inp, size, one_step):
 
     proxy = LibProxy()
     orig_lib = ops.lib
-    ops.lib, ops.gemm, ops.conv3x3 = (lambda: proxy), gemm, conv
+    ops.lib, ops.gemm, ops.conv3x3, ops.attention = (lambda: proxy), gemm, conv, attn
     import imagine360_b200.host.forward as Fw
     try:
         one_step(7)
         torch.cuda.synchronize()
     finally:
-        ops.lib, ops.gemm, ops.conv3x3 = orig_lib, orig_gemm, orig_conv
+        ops.lib, ops.gemm, ops.conv3x3, ops.attention = orig_lib, orig_gemm, orig_conv, orig_attn
     per = {n: (len(v), sum(a.elapsed_time(b) for a, b in v)) for n, v in timed.items()}
     total = sum(ms for _, ms in per.values())
     gc_ms = per.get("i360_gemm_bf16", (0, 0))[1] + per.get("i360_conv3x3_bf16", (0, 0))[1]
@@ -297,10 +305,14 @@ def kernel_roofline(pipe, inp, size, one_step):
     breakdown = {n: {"launches": c, "ms": round(ms, 3)} for n, (c, ms) in sorted(per.items(), key=lambda kv: -kv[1][1])}
     agg = {}
     for kind, M, N, K, act, idx in shapes:
-        ev = timed["i360_gemm_bf16" if kind == "gemm" else "i360_conv3x3_bf16"][idx]
-        key = f"{kind} M={M} N={N} K={K} act={act}"
+        if kind == "attn":
+            ev = timed["i360_attention_bf16"][idx]
+            key, f1 = f"attn {M}", N
+        else:
+            ev = timed["i360_gemm_bf16" if kind == "gemm" else "i360_conv3x3_bf16"][idx]
+            key, f1 = f"{kind} M={M} N={N} K={K} act={act}", 2.0 * M * N * K
         c, ms, fl = agg.get(key, (0, 0.0, 0.0))
-        agg[key] = (c + 1, ms + ev[0].elapsed_time(ev[1]), fl + 2.0 * M * N * K)
+        agg[key] = (c + 1, ms + ev[0].elapsed_time(ev[1]), fl + f1)
     breakdown["shapes"] = {k: {"n": c, "ms": round(ms, 3), "tflops": round(fl / ms / 1e9, 1)} for k, (c, ms, fl) in
                            sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]}
     return roof, breakdown
