@@ -10,7 +10,7 @@ import sys
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libimagine360_b200.so"
+LIB_PATH = Path(os.environ["I360_LIB_PATH"]) if os.environ.get("I360_LIB_PATH") else _HERE / "libimagine360_b200.so"
 
 _lib = None
 

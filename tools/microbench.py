@@ -72,6 +72,19 @@ if "attn" in sys.argv or len(sys.argv) == 1:
     fn = lambda: ops.attention(ops.seq_view(equi, b * Fr, EN), ops.multiview_view(pers_kv, b, m, Fr, hw, 0),
                                ops.multiview_view(pers_kv, b, m, Fr, hw, C), ops.seq_view(out, b * Fr, EN), heads, hd, b * Fr, bias=bias)
     rec("attn warp equi<-pers enc0", timeit(fn), 4.0 * b * Fr * heads * EN * m * hw * hd, 0)
+if "xattn" in sys.argv or len(sys.argv) == 1:
+    # text / image-prompt cross attention: K/V of a clip element shared by its 16 frames
+    for (imgs, N, heads, hd, nk) in [(640, 1024, 5, 64, 77), (640, 1024, 5, 64, 64), (32, 8192, 5, 64, 77), (640, 256, 10, 64, 77)]:
+        C = heads * hd; fr = 16
+        q = torch.randn(imgs * N, C, device="cuda").bfloat16()
+        kv = torch.randn((imgs // fr) * nk, 2 * C, device="cuda").bfloat16()
+        out = torch.zeros(imgs * N, C, device="cuda", dtype=torch.bfloat16)
+        for acc in (False, True):
+            fn = lambda: ops.attention(ops.seq_view(q, imgs, N), ops.seq_view(kv, imgs // fr, nk, 0, share_div=fr),
+                                       ops.seq_view(kv, imgs // fr, nk, C, share_div=fr), ops.seq_view(out, imgs, N), heads, hd, imgs, accumulate=acc)
+            by = 2.0 * (q.numel() + out.numel() * (2 if acc else 1))
+            rec(f"xattn imgs{imgs} N{N} h{heads} nk{nk} acc{int(acc)}", timeit(fn), 4.0 * imgs * heads * N * nk * hd, by)
+        del q, kv, out
 if "norm" in sys.argv or len(sys.argv) == 1:
     for (B, H, W, C) in [(640, 32, 32, 320), (32, 64, 128, 320), (640, 16, 16, 640), (640, 8, 8, 1280)]:
         x = torch.randn(B, H, W, C, device="cuda").bfloat16()

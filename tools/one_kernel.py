@@ -21,6 +21,12 @@ elif kind == "conv":
     B, H, W, Ci, Co = a
     x = torch.randn(B, H, W, Ci, device="cuda").bfloat16(); wp = ops.pack_conv3x3(torch.randn(Co, Ci, 3, 3, device="cuda").bfloat16())
     fn = lambda: ops.conv3x3(x, wp)
+if kind == "xattn":
+    imgs, N, heads, hd, nk = a; C = heads * hd; fr = 16
+    q = torch.randn(imgs * N, C, device="cuda").bfloat16(); kv = torch.randn((imgs // fr) * nk, 2 * C, device="cuda").bfloat16()
+    out = torch.zeros(imgs * N, C, device="cuda", dtype=torch.bfloat16)
+    fn = lambda: ops.attention(ops.seq_view(q, imgs, N), ops.seq_view(kv, imgs // fr, nk, 0, share_div=fr),
+                               ops.seq_view(kv, imgs // fr, nk, C, share_div=fr), ops.seq_view(out, imgs, N), heads, hd, imgs)
 if kind == "temporal":
     B, Fr, D, heads, hd = a
     C = heads * hd
