@@ -228,7 +228,7 @@ def kernel_roofline(pipe, inp, size, one_step):
     records = []
     orig_gemm, orig_conv = ops.gemm, ops.conv3x3
     L = ops.lib()
-    names = ["i360_gemm_bf16", "i360_conv3x3_bf16", "i360_attention_bf16", "i360_temporal_attention_bf16", "i360_groupnorm_stats",
+    names = ["i360_gemm_bf16", "i360_conv3x3_bf16", "i360_attention_bf16", "i360_cross_attention_text_ip_bf16", "i360_temporal_attention_bf16", "i360_groupnorm_stats",
              "i360_groupnorm_apply", "i360_layernorm", "i360_upsample2x_nhwc", "i360_im2col3x3_s2_nhwc", "i360_axpby_bf16",
              "i360_cfg_ddim_step_bf16", "i360_avgpool_frames4_bf16", "i360_grid_sample_f32", "i360_softmax_rows_bf16"]
     timed = {}

@@ -63,22 +63,6 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
-// 2^t for a pair without the MUFU: round-to-nearest split t = n + f (magic-number add), degree-3 minimax
-// polynomial of 2^f on [-0.5, 0.5] (max rel. error 7.5e-5, well under the bf16 rounding of P) on packed FFMA2, and
-// n added straight into the exponent field.  t is clamped at -126 (result ~1e-38, i.e. 0 for the row sum).
-__device__ __forceinline__ float2 exp2_poly2(float2 t) {
-  const float kMagic = 12582912.0f;               // 1.5 * 2^23: the low mantissa bits of (t + kMagic) hold round(t)
-  const float2 tc = make_float2(fmaxf(t.x, -126.0f), fmaxf(t.y, -126.0f));
-  const float2 r = fadd2(tc, make_float2(kMagic, kMagic));
-  const float2 n = fadd2(r, make_float2(-kMagic, -kMagic));
-  const float2 f = ffma2(n, make_float2(-1.f, -1.f), tc);
-  float2 q = ffma2(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
-  q = ffma2(q, f, make_float2(0.6932609677f, 0.6932609677f));
-  q = ffma2(q, f, make_float2(0.9999280572f, 0.9999280572f));
-  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(r.x) << 23)),
-                     __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23)));
-}
-
 // One KV tile of the online softmax for one (query row, column half) = one thread.  The thread's 64 fp32 logits are
 // read from TMEM ONCE into registers and S is released to the MMA warp immediately (S_{j+1} = Q K_{j+1}^T then runs
 // under this tile's exponentials).  The two column halves of a row are independent online softmaxes, each with its

@@ -288,6 +288,22 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^t for a pair without the MUFU: round-to-nearest split t = n + f (magic-number add), degree-3 minimax
+// polynomial of 2^f on [-0.5, 0.5] (max rel. error 7.5e-5, well under the bf16 rounding of P) on packed FFMA2, and
+// n added straight into the exponent field.  t is clamped at -126 (result ~1e-38, i.e. 0 for the row sum).
+__device__ __forceinline__ float2 exp2_poly2(float2 t) {
+  const float kMagic = 12582912.0f;               // 1.5 * 2^23: the low mantissa bits of (t + kMagic) hold round(t)
+  const float2 tc = make_float2(fmaxf(t.x, -126.0f), fmaxf(t.y, -126.0f));
+  const float2 r = fadd2(tc, make_float2(kMagic, kMagic));
+  const float2 n = fadd2(r, make_float2(-kMagic, -kMagic));
+  const float2 f = ffma2(n, make_float2(-1.f, -1.f), tc);
+  float2 q = ffma2(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
+  q = ffma2(q, f, make_float2(0.6932609677f, 0.6932609677f));
+  q = ffma2(q, f, make_float2(0.9999280572f, 0.9999280572f));
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(r.x) << 23)),
+                     __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23)));
+}
+
 // gelu_erf on two values at once: packed FFMA2/FMUL2 for the rational + polynomial part, 2+2 MUFU (rcp, ex2).
 // Same Abramowitz-Stegun 7.1.26 formula as gelu_erf (abs error <= 1.5e-7 before the approx MUFUs' ~1e-6).
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {

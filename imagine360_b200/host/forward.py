@@ -152,13 +152,17 @@ def spatial_transformer(x, t3d, ctx: Context, frames: int):
         ip = ctx.ip[..., : a2.image_cross_attention_dim] if a2.image_cross_attention_dim != a2.cross_attention_dim else ctx.ip
         kv_i = ops.gemm(ip.reshape(-1, ip.shape[-1]), fused_w(a2, "kv_ip", [a2.to_k_ip, a2.to_v_ip]))
         o = torch.empty_like(t)
-        qv, ov = ops.seq_view(q, n, npix), ops.seq_view(o, n, npix)
-        ops.attention(qv, ops.seq_view(kv_t, ctx.n_ctx, nt, 0, share_div=frames),
-                      ops.seq_view(kv_t, ctx.n_ctx, nt, c, share_div=frames), ov, heads, hd, n)
         if a2.ip_scale != 1.0:
             raise NotImplementedError("ip scale != 1.0")
-        ops.attention(qv, ops.seq_view(kv_i, ctx.n_ctx, ni, 0, share_div=frames),
-                      ops.seq_view(kv_i, ctx.n_ctx, ni, c, share_div=frames), ov, heads, hd, n, accumulate=True)
+        if ops.cross_attention_text_ip_supported(hd, nt, ni) and n == ctx.n_ctx * frames:
+            # both key sets stay in shared memory; one read of q, one write of o
+            ops.cross_attention_text_ip(q, o, kv_t, nt, kv_i, ni, ctx.n_ctx, heads, hd)
+        else:
+            qv, ov = ops.seq_view(q, n, npix), ops.seq_view(o, n, npix)
+            ops.attention(qv, ops.seq_view(kv_t, ctx.n_ctx, nt, 0, share_div=frames),
+                          ops.seq_view(kv_t, ctx.n_ctx, nt, c, share_div=frames), ov, heads, hd, n)
+            ops.attention(qv, ops.seq_view(kv_i, ctx.n_ctx, ni, 0, share_div=frames),
+                          ops.seq_view(kv_i, ctx.n_ctx, ni, c, share_div=frames), ov, heads, hd, n, accumulate=True)
         wo, bo = lin_w(a2.to_out[0])
         t = ops.gemm(o, wo, bias=bo, resid=t)
         # --- GEGLU feed-forward ---

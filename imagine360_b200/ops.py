@@ -235,6 +235,27 @@ def attention(q: TokenView, k: TokenView, v: TokenView, o: TokenView, heads: int
     check(rc, "i360_attention_bf16")
 
 
+def cross_attention_text_ip_supported(head_dim: int, nt: int, ni: int) -> bool:
+    ntp, nip = -(-nt // 16) * 16, -(-ni // 16) * 16
+    return head_dim == 64 and ntp + nip <= 192 and -(-ntp // 64) + -(-nip // 64) <= 3
+
+
+def cross_attention_text_ip(q: torch.Tensor, out: torch.Tensor, kv_text: torch.Tensor, nt: int, kv_ip: torch.Tensor, ni: int,
+                            n_ctx: int, heads: int, head_dim: int, scale: float | None = None) -> None:
+    """``out = softmax(q Kt^T) Vt + softmax(q Ki^T) Vi`` per head; rows of ``q`` are ``n_ctx`` clip elements times
+    (frames x tokens); ``kv_*`` hold [K | V] of each element's text / image-prompt tokens (attention.py:119-148)."""
+    _chk_bf16(q, out, kv_text, kv_ip)
+    assert q.dim() == 2 and q.stride(1) == 1 and out.stride(1) == 1 and kv_text.stride(1) == 1 and kv_ip.stride(1) == 1
+    assert q.shape[1] == heads * head_dim and kv_text.shape == (n_ctx * nt, 2 * heads * head_dim)
+    assert kv_ip.shape == (n_ctx * ni, 2 * heads * head_dim) and q.shape[0] % n_ctx == 0
+    rc = lib().i360_cross_attention_text_ip_bf16(_p(q), c_longlong(q.stride(0)), _p(out), c_longlong(out.stride(0)),
+                                                 c_longlong(q.shape[0]), c_int(n_ctx), _p(kv_text), c_longlong(kv_text.stride(0)),
+                                                 c_int(nt), _p(kv_ip), c_longlong(kv_ip.stride(0)), c_int(ni), c_int(heads),
+                                                 c_int(head_dim), c_float(scale if scale is not None else head_dim ** -0.5),
+                                                 _stream())
+    check(rc, "i360_cross_attention_text_ip_bf16")
+
+
 def temporal_attention(q, k, v, out, B: int, F: int, D: int, heads: int, head_dim: int) -> None:
     """q/k/v/out: 2-D bf16 views with rows ordered (b, f, d) and heads*head_dim columns."""
     _chk_bf16(q, k, v, out)

@@ -91,6 +91,18 @@ int i360_attention_bf16(const I360TokenView* q, const I360TokenView* k, const I3
                         const I360TokenView* o, int heads, int head_dim, int batch, float scale, const void* bias,
                         int bias_rows, int bias_cols, int accumulate, void* stream);
 
+/* Fused text + image-prompt cross-attention: O = softmax(Q Kt^T * scale) Vt + softmax(Q Ki^T * scale) Vi, summed in
+ * fp32 and rounded once.  q, o: [rows, heads*64] (row strides in elements); rows = n_ctx * rows_per_ctx, the rows of
+ * clip element e (all of its frames) are [e * rows_per_ctx, +rows_per_ctx) and attend to text tokens
+ * kv_text[e*nt .. e*nt+nt) and image tokens kv_ip[e*ni .. e*ni+ni); kv_* = [K | V] projections, 2*heads*64 columns.
+ * Keys/values stay in shared memory while the element's queries stream through (HBM bound: one read of q, one write
+ * of o).  Limits: head_dim 64, ceil16(nt) + ceil16(ni) <= 192.  Replaces both attention calls and the sum of
+ * IPCrossAttention (animatediff/models/attention.py:119-148) on the xformers path
+ * (diffusers/models/attention_processor.py:1264). */
+int i360_cross_attention_text_ip_bf16(const void* q, long long ldq, void* o, long long ldo, long long rows, int n_ctx,
+                                      const void* kv_text, long long ld_kvt, int nt, const void* kv_ip, long long ld_kvi,
+                                      int ni, int heads, int head_dim, float scale, void* stream);
+
 /* Attention over the frame axis (F <= 32) for every (clip b, pixel d, head), rows ordered (b, f, d).
  * Replaces the baddbmm/softmax/bmm math path of VersatileAttention (animatediff/models/motion_module.py:343-429,
  * diffusers/models/attention_processor.py:562-591) and of TemporalProjection.attn_temp (resampler.py:246,:259). */

@@ -122,6 +122,51 @@ def test_cross_attention_shared_kv_and_accumulate():
     _close(out.reshape(clips * Fr, N, C), ref, "cross-attn text+ip", atol_scale=8e-3)
 
 
+@pytest.mark.parametrize("clips,Fr,N,heads,nt,ni", [
+    (2, 3, 200, 5, 77, 64),      # rows per element not a multiple of 128 (masked tail tile)
+    (3, 16, 16, 2, 77, 64),      # mid-block shape: 256 rows per element
+    (4, 16, 128, 5, 77, 64),     # > 148 items: several tiles per CTA, ranges crossing (element, head) boundaries
+    (6, 16, 256, 10, 77, 64),    # ~13 tiles per CTA
+    (2, 8, 64, 3, 77, 16), (2, 8, 64, 2, 20, 4), (1, 8, 96, 2, 128, 64), (2, 2, 24, 1, 1, 1),
+])
+def test_cross_attention_text_ip_fused(clips, Fr, N, heads, nt, ni):
+    """attn2 as ONE kernel with stationary K/V: softmax(q Kt^T) Vt + softmax(q Ki^T) Vi (attention.py:119-148)."""
+    from imagine360_b200 import ops
+    hd = 64
+    C = heads * hd
+    assert ops.cross_attention_text_ip_supported(hd, nt, ni)
+    q = _rand(clips * Fr * N, C, seed=23)
+    kv_t = _rand(clips * nt, 2 * C, seed=24)
+    kv_i = _rand(clips * ni, 2 * C, seed=25)
+    out = torch.full((clips * Fr * N, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.cross_attention_text_ip(q, out, kv_t, nt, kv_i, ni, clips, heads, hd)
+    q3 = q.reshape(clips * Fr, N, C)
+
+    def rep(t, n):
+        return t.reshape(clips, n, 2 * C).repeat_interleave(Fr, 0)
+
+    kt, ki = rep(kv_t, nt), rep(kv_i, ni)
+    ref = _sdpa(q3, kt[..., :C], kt[..., C:], heads) + _sdpa(q3, ki[..., :C], ki[..., C:], heads)
+    _close(out.reshape(clips * Fr, N, C), ref, f"fused cross-attn nt={nt} ni={ni}", atol_scale=8e-3)
+    # and against the generic kernel's two-call path (bf16 rounding of each branch before the sum)
+    out2 = torch.empty_like(out)
+    qv, ov = ops.seq_view(q, clips * Fr, N), ops.seq_view(out2, clips * Fr, N)
+    ops.attention(qv, ops.seq_view(kv_t, clips, nt, 0, share_div=Fr), ops.seq_view(kv_t, clips, nt, C, share_div=Fr), ov,
+                  heads, hd, clips * Fr)
+    ops.attention(qv, ops.seq_view(kv_i, clips, ni, 0, share_div=Fr), ops.seq_view(kv_i, clips, ni, C, share_div=Fr), ov,
+                  heads, hd, clips * Fr, accumulate=True)
+    _close(out, out2, "fused vs two-call cross-attn", rtol=1.0 / 64, atol_scale=1.2e-2)
+
+
+def test_cross_attention_text_ip_limits():
+    from imagine360_b200 import ops
+    assert not ops.cross_attention_text_ip_supported(32, 77, 64)
+    assert not ops.cross_attention_text_ip_supported(64, 128, 128)
+    q = _rand(256, 32, seed=1)
+    with pytest.raises(RuntimeError):
+        ops.cross_attention_text_ip(q, torch.empty_like(q), _rand(77, 64, seed=2), 77, _rand(64, 64, seed=3), 64, 1, 1, 32)
+
+
 @pytest.mark.parametrize("b,m,Fr,ph,eh,ew,heads", [(2, 3, 2, 4, 8, 16, 2), (1, 20, 2, 8, 16, 32, 10), (1, 4, 1, 16, 32, 64, 10),
                                                   (2, 2, 2, 2, 4, 8, 4), (1, 4, 1, 6, 12, 24, 2)])
 def test_warp_attention_with_bias(b, m, Fr, ph, eh, ew, heads):

@@ -85,6 +85,17 @@ if "xattn" in sys.argv or len(sys.argv) == 1:
             by = 2.0 * (q.numel() + out.numel() * (2 if acc else 1))
             rec(f"xattn imgs{imgs} N{N} h{heads} nk{nk} acc{int(acc)}", timeit(fn), 4.0 * imgs * heads * N * nk * hd, by)
         del q, kv, out
+if "xfused" in sys.argv or len(sys.argv) == 1:
+    # fused text + image-prompt cross attention with stationary K/V (every attn2 of the C3 step)
+    for (imgs, N, heads) in [(640, 1024, 5), (32, 8192, 5), (640, 256, 10), (32, 2048, 10), (640, 64, 20), (32, 512, 20), (640, 16, 20), (32, 128, 20)]:
+        C = heads * 64; fr = 16
+        q = torch.randn(imgs * N, C, device="cuda").bfloat16()
+        kvt = torch.randn((imgs // fr) * 77, 2 * C, device="cuda").bfloat16()
+        kvi = torch.randn((imgs // fr) * 64, 2 * C, device="cuda").bfloat16()
+        out = torch.zeros(imgs * N, C, device="cuda", dtype=torch.bfloat16)
+        fn = lambda: ops.cross_attention_text_ip(q, out, kvt, 77, kvi, 64, imgs // fr, heads, 64)
+        rec(f"xfused imgs{imgs} N{N} h{heads}", timeit(fn), 4.0 * imgs * heads * N * 141 * 64, 2.0 * (q.numel() + out.numel()))
+        del q, kvt, kvi, out
 if "norm" in sys.argv or len(sys.argv) == 1:
     for (B, H, W, C) in [(640, 32, 32, 320), (32, 64, 128, 320), (640, 16, 16, 640), (640, 8, 8, 1280)]:
         x = torch.randn(B, H, W, C, device="cuda").bfloat16()
