@@ -257,9 +257,7 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           case 3: x_softmax<3>(tS_mine, sPb, row, nvalid, p.scale_log2, &s_empty[b]); break;
           case 4: x_softmax<4>(tS_mine, sPb, row, nvalid, p.scale_log2, &s_empty[b]); break;
           case 5: x_softmax<5>(tS_mine, sPb, row, nvalid, p.scale_log2, &s_empty[b]); break;
-          case 6: x_softmax<6>(tS_mine, sPb, row, nvalid, p.scale_log2, &s_empty[b]); break;
-          case 7: x_softmax<7>(tS_mine, sPb, row, nvalid, p.scale_log2, &s_empty[b]); break;
-          default: x_softmax<8>(tS_mine, sPb, row, nvalid, p.scale_log2, &s_empty[b]); break;
+          default: x_softmax<6>(tS_mine, sPb, row, nvalid, p.scale_log2, &s_empty[b]); break;
         }
         fence_proxy_async_smem();                     // P visible to the tensor core (async proxy)
         mbar_arrive(&p_full[b]);
@@ -298,7 +296,8 @@ extern "C" int i360_cross_attention_text_ip_bf16(const void* q, long long ldq, v
   p.ntp = (nt + 15) & ~15; p.nip = (ni + 15) & ~15;
   p.nbt = (p.ntp + 63) / 64;
   const int nbi = (p.nip + 63) / 64;
-  if (p.ntp + p.nip > 192 || p.nbt + nbi > 3) return I360_ERR_UNSUPPORTED;
+  // each branch's logits row lives in one thread's registers: 96 columns keep the kernel free of local-memory spills
+  if (p.ntp > 96 || p.nip > 96 || p.nbt + nbi > 3) return I360_ERR_UNSUPPORTED;
   if (rows / n_ctx > 0x7fffffff / 2) return I360_ERR_ARG;
   p.rows_per_ctx = static_cast<int>(rows / n_ctx);
   p.tiles_per_ctx = (p.rows_per_ctx + 127) / 128;

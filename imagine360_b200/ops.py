@@ -237,7 +237,7 @@ def attention(q: TokenView, k: TokenView, v: TokenView, o: TokenView, heads: int
 
 def cross_attention_text_ip_supported(head_dim: int, nt: int, ni: int) -> bool:
     ntp, nip = -(-nt // 16) * 16, -(-ni // 16) * 16
-    return head_dim == 64 and ntp + nip <= 192 and -(-ntp // 64) + -(-nip // 64) <= 3
+    return head_dim == 64 and ntp <= 96 and nip <= 96 and -(-ntp // 64) + -(-nip // 64) <= 3
 
 
 def cross_attention_text_ip(q: torch.Tensor, out: torch.Tensor, kv_text: torch.Tensor, nt: int, kv_ip: torch.Tensor, ni: int,

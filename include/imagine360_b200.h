@@ -96,7 +96,7 @@ int i360_attention_bf16(const I360TokenView* q, const I360TokenView* k, const I3
  * clip element e (all of its frames) are [e * rows_per_ctx, +rows_per_ctx) and attend to text tokens
  * kv_text[e*nt .. e*nt+nt) and image tokens kv_ip[e*ni .. e*ni+ni); kv_* = [K | V] projections, 2*heads*64 columns.
  * Keys/values stay in shared memory while the element's queries stream through (HBM bound: one read of q, one write
- * of o).  Limits: head_dim 64, ceil16(nt) + ceil16(ni) <= 192.  Replaces both attention calls and the sum of
+ * of o).  Limits: head_dim 64, nt <= 96, ni <= 96, ceil(nt/64) + ceil(ni/64) <= 3.  Replaces both attention calls and the sum of
  * IPCrossAttention (animatediff/models/attention.py:119-148) on the xformers path
  * (diffusers/models/attention_processor.py:1264). */
 int i360_cross_attention_text_ip_bf16(const void* q, long long ldq, void* o, long long ldo, long long rows, int n_ctx,
