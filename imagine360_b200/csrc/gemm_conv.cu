@@ -65,18 +65,25 @@ template <int BN, bool RING = false> struct Cfg {
   // 4 buffers per group so that a residual chunk can be requested ~3 chunks before it is consumed
   static constexpr int kBufPerGrp = RING ? 4 : 2;
   static constexpr int kNumStg = 2 * kBufPerGrp;
-  static constexpr int kBudget = 226 * 1024 - kNumStg * kStgBytes - 1024 - 256;
+  // the 160-wide tiles (the epilogue-bound K=320/640 projections) keep the tile's bias as an fp32 table in smem (one
+  // copy per epilogue group, double buffered with the accumulator stage, filled one tile ahead through registers)
+  // instead of every thread re-loading and unpacking the same bf16 values for every chunk
+  static constexpr bool kBiasTable = BN == 160;
+  static constexpr int kTableBytes = kBiasTable ? 2 * 2 * BN * 4 : 0;   // [group][accumulator stage][BN]
+  static constexpr int kBudget = 227 * 1024 - kNumStg * kStgBytes - kTableBytes - 1024 - 256;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kNumStg * kStgBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNumStg * kStgBytes + kTableBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
 };
 
 // Epilogue flavours (compile-time: the epilogue is the critical path of the small-K layers, and one generic,
 // runtime-branchy version thrashes the instruction cache)
-enum : int { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_RESID = 2, EPI_ROWVEC = 3, EPI_ACT = 4, EPI_GENERAL = 5 };
+enum : int { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_RESID = 2, EPI_ROWVEC = 3, EPI_ACT = 4, EPI_GENERAL = 5, EPI_RESID_DIRECT = 6 };
 // residual tiles go through the TMA ring for the narrow-N tiles (the K=320/640 projections, where the per-thread
-// strided residual reads were the bottleneck); BN=256 keeps 4 pipeline stages and reads the residual directly
+// strided residual reads were the bottleneck); BN=256 keeps 4 pipeline stages and reads the residual directly, and
+// so do the cropped pano tiles (EPI_RESID_DIRECT, chosen by the host), whose rows are not a TMA box of the output.
+// Ring or not is a compile-time property, so the ring kernels carry no (predicated-off) direct-read instructions.
 template <int BN, int EPI> struct UseRing { static constexpr bool value = (EPI == EPI_RESID) && (BN <= 160); };
 
 template <int BN, int EPI>
@@ -91,7 +98,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* stg = smem + C::kStages * C::kStageBytes;            // 2 staging buffers (1024-aligned)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + C::kNumStg * C::kStgBytes);
+  float* sbias = reinterpret_cast<float*>(stg + C::kNumStg * C::kStgBytes);   // [2 groups][2][BN] (kBiasTable only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + C::kNumStg * C::kStgBytes + C::kTableBytes);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + C::kStages;         // [kStages]
   uint64_t* tfull = bars + 2 * C::kStages;     // [2]
@@ -192,14 +200,14 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // would need a negative start coordinate, which TMA stores reject: those use predicated global stores.
     constexpr int CH = C::CH;
     constexpr bool kGeglu = (EPI == EPI_GEGLU);
-    constexpr bool kResid = (EPI == EPI_RESID) || (EPI == EPI_GENERAL);
+    constexpr bool kResid = (EPI == EPI_RESID) || (EPI == EPI_RESID_DIRECT) || (EPI == EPI_GENERAL);
     constexpr bool kRowvec = (EPI == EPI_ROWVEC) || (EPI == EPI_GENERAL);
     constexpr bool kAct = (EPI == EPI_ACT) || (EPI == EPI_GENERAL);
     const int ew = warp & 3;                 // TMEM lane quarter this warp may read
     const int grp = (warp - 2) >> 2;         // epilogue group 0/1: chunks grp, grp+2, ...
     const int row = ew * 32 + lane;          // row inside the 128-row tile
     const bool store_thread = (lane == 0) && (warp == 2 || warp == 6);
-    const bool direct = p.conv && p.crop > 0;
+    const bool direct = !kRing && p.conv && p.crop > 0;
     const uint32_t swz = (row >> 1) & 3;     // 64B swizzle: 16-byte chunk index ^= address bits [7,9)
     constexpr int NB = C::kBufPerGrp;
     uint8_t* gbuf = stg + grp * NB * C::kStgBytes;
@@ -227,8 +235,19 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       pf_ci += 2; ++pf_k;
     };
-    const bool ring_on = kRing && !direct && p.resid != nullptr;
+    constexpr bool ring_on = kRing;          // host dispatch guarantees: residual present, tile rows are a TMA box
     if (ring_on && store_thread) { for (int i = 0; i < NB - 1; ++i) prefetch_resid(); }
+    const bool has_bias = p.bias != nullptr;
+    const int gtid = (warp & 3) * 32 + lane;             // thread index inside the epilogue group
+    float nb0 = 0.f, nb1 = 0.f;                          // bias of columns gtid, gtid + 128 of the NEXT tile
+    auto load_bias = [&](int tt) {
+      if (tt < total_tiles) {
+        const int c0 = (tt % p.n_tiles) * BN + gtid;
+        nb0 = (c0 < p.N) ? __bfloat162float(p.bias[c0]) : 0.f;
+        nb1 = (gtid + 128 < BN && c0 + 128 < p.N) ? __bfloat162float(p.bias[c0 + 128]) : 0.f;
+      }
+    };
+    if (C::kBiasTable && !kGeglu && has_bias) load_bias(blockIdx.x);
     int as = 0; uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
@@ -254,6 +273,16 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bf16* rrow = (kResid && !ring_on && p.resid != nullptr && valid) ? p.resid + orow * p.ldr : nullptr;
       bf16* drow = p.D + orow * p.ldd;
 
+      const float* tbias = sbias + (grp * 2 + as) * BN;
+      if (C::kBiasTable && !kGeglu && has_bias) {
+        // this tile's values were fetched into registers during the previous tile; the buffer last served tile
+        // t-2, which every thread of the group left before the barrier of tile t-1
+        float* tw = sbias + (grp * 2 + as) * BN;
+        tw[gtid] = nb0;
+        if (gtid + 128 < BN) tw[gtid + 128] = nb1;
+        named_bar_sync(1 + grp, 128);
+        load_bias(t + gridDim.x);                      // lands under this tile's chunks
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
@@ -266,8 +295,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool live = ocol < p.n_out;
         uint8_t* buf = gbuf + (kchunk % NB) * C::kStgBytes;
         uint8_t* my = buf + row * (CH * 2);
-        float f[32];
         if (live) {
+          float2 f2[16];                     // 32 consecutive output columns as 16 packed pairs
           uint32_t v[32];
           tmem_ld_x16(t_acc + ci * CH, v);
           tmem_ld_x16(t_acc + ci * CH + 16, v + 16);
@@ -279,62 +308,75 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int wc = n_blk * BN + ci * CH;          // packed weight/bias row of value column 0
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              float ba[8], bg[8];
-              if (p.bias) {
+              float2 ba[4], bg[4];
+              if (has_bias) {
                 const uint4 x = *reinterpret_cast<const uint4*>(p.bias + wc + g * 8);
                 const uint4 y = *reinterpret_cast<const uint4*>(p.bias + wc + BN / 2 + g * 8);
-                float2 t0 = unpack_bf16x2(x.x), t1 = unpack_bf16x2(x.y), t2 = unpack_bf16x2(x.z), t3 = unpack_bf16x2(x.w);
-                ba[0] = t0.x; ba[1] = t0.y; ba[2] = t1.x; ba[3] = t1.y; ba[4] = t2.x; ba[5] = t2.y; ba[6] = t3.x; ba[7] = t3.y;
-                t0 = unpack_bf16x2(y.x); t1 = unpack_bf16x2(y.y); t2 = unpack_bf16x2(y.z); t3 = unpack_bf16x2(y.w);
-                bg[0] = t0.x; bg[1] = t0.y; bg[2] = t1.x; bg[3] = t1.y; bg[4] = t2.x; bg[5] = t2.y; bg[6] = t3.x; bg[7] = t3.y;
+                ba[0] = unpack_bf16x2(x.x); ba[1] = unpack_bf16x2(x.y); ba[2] = unpack_bf16x2(x.z); ba[3] = unpack_bf16x2(x.w);
+                bg[0] = unpack_bf16x2(y.x); bg[1] = unpack_bf16x2(y.y); bg[2] = unpack_bf16x2(y.z); bg[3] = unpack_bf16x2(y.w);
               } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { ba[j] = 0.f; bg[j] = 0.f; }
+                for (int j = 0; j < 4; ++j) { ba[j] = make_float2(0.f, 0.f); bg[j] = make_float2(0.f, 0.f); }
               }
 #pragma unroll
-              for (int j = 0; j < 8; j += 2) {
-                const float2 val = fadd2(make_float2(__uint_as_float(v[g * 8 + j]), __uint_as_float(v[g * 8 + j + 1])),
-                                         make_float2(ba[j], ba[j + 1]));
-                const float2 gate = fadd2(make_float2(__uint_as_float(vg[g * 8 + j]), __uint_as_float(vg[g * 8 + j + 1])),
-                                          make_float2(bg[j], bg[j + 1]));
-                const float2 r = fmul2(val, gelu_erf2(gate));
-                f[g * 8 + j] = r.x; f[g * 8 + j + 1] = r.y;
+              for (int j = 0; j < 4; ++j) {
+                const float2 val = fadd2(make_float2(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])), ba[j]);
+                const float2 gate = fadd2(make_float2(__uint_as_float(vg[g * 8 + 2 * j]), __uint_as_float(vg[g * 8 + 2 * j + 1])), bg[j]);
+                f2[g * 4 + j] = fmul2(val, gelu_erf2(gate));
               }
             }
           } else {
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 16; ++j) f2[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            if (has_bias) {
+              if (C::kBiasTable) {           // fp32 table in smem (zero past N): broadcast LDS.128, packed adds
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = ocol + g * 8;
-              if (col < p.N) {
-                if (p.bias) {
-                  const uint4 bb = *reinterpret_cast<const uint4*>(p.bias + col);
-                  float2 t0 = unpack_bf16x2(bb.x), t1 = unpack_bf16x2(bb.y), t2 = unpack_bf16x2(bb.z), t3 = unpack_bf16x2(bb.w);
-                  f[g * 8 + 0] += t0.x; f[g * 8 + 1] += t0.y; f[g * 8 + 2] += t1.x; f[g * 8 + 3] += t1.y;
-                  f[g * 8 + 4] += t2.x; f[g * 8 + 5] += t2.y; f[g * 8 + 6] += t3.x; f[g * 8 + 7] += t3.y;
+                for (int q = 0; q < 8; ++q) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(tbias + ci * CH + q * 4);
+                  f2[2 * q] = fadd2(f2[2 * q], make_float2(b4.x, b4.y));
+                  f2[2 * q + 1] = fadd2(f2[2 * q + 1], make_float2(b4.z, b4.w));
                 }
-                if (kRowvec && rv) {
-                  const float4 r0 = *reinterpret_cast<const float4*>(rv + col);
-                  const float4 r1 = *reinterpret_cast<const float4*>(rv + col + 4);
-                  f[g * 8 + 0] += r0.x; f[g * 8 + 1] += r0.y; f[g * 8 + 2] += r0.z; f[g * 8 + 3] += r0.w;
-                  f[g * 8 + 4] += r1.x; f[g * 8 + 5] += r1.y; f[g * 8 + 6] += r1.z; f[g * 8 + 7] += r1.w;
-                }
-                if (kAct) {
-                  if (p.act == 2) {
+              } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) f[g * 8 + j] = gelu_erf(f[g * 8 + j]);
-                  } else if (p.act == 3) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) f[g * 8 + j] = silu(f[g * 8 + j]);
+                for (int g = 0; g < 4; ++g) {
+                  if (ocol + g * 8 < p.N) {
+                    const uint4 bb = *reinterpret_cast<const uint4*>(p.bias + ocol + g * 8);
+                    f2[g * 4 + 0] = fadd2(f2[g * 4 + 0], unpack_bf16x2(bb.x)); f2[g * 4 + 1] = fadd2(f2[g * 4 + 1], unpack_bf16x2(bb.y));
+                    f2[g * 4 + 2] = fadd2(f2[g * 4 + 2], unpack_bf16x2(bb.z)); f2[g * 4 + 3] = fadd2(f2[g * 4 + 3], unpack_bf16x2(bb.w));
                   }
                 }
-                if (kResid && rrow) {
+              }
+            }
+            if (kRowvec && rv) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int col = ocol + g * 8;
+                if (col < p.N) {
+                  const float4 r0 = *reinterpret_cast<const float4*>(rv + col);
+                  const float4 r1 = *reinterpret_cast<const float4*>(rv + col + 4);
+                  f2[g * 4 + 0] = fadd2(f2[g * 4 + 0], make_float2(r0.x, r0.y)); f2[g * 4 + 1] = fadd2(f2[g * 4 + 1], make_float2(r0.z, r0.w));
+                  f2[g * 4 + 2] = fadd2(f2[g * 4 + 2], make_float2(r1.x, r1.y)); f2[g * 4 + 3] = fadd2(f2[g * 4 + 3], make_float2(r1.z, r1.w));
+                }
+              }
+            }
+            if (kAct) {
+              if (p.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f2[j] = gelu_erf2(f2[j]);
+              } else if (p.act == 3) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f2[j] = make_float2(silu(f2[j].x), silu(f2[j].y));
+              }
+            }
+            if (kResid && !kRing && rrow) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int col = ocol + g * 8;
+                if (col < p.N) {
                   const uint4 rr = *reinterpret_cast<const uint4*>(rrow + col);
-                  float2 t0 = unpack_bf16x2(rr.x), t1 = unpack_bf16x2(rr.y), t2 = unpack_bf16x2(rr.z), t3 = unpack_bf16x2(rr.w);
-                  f[g * 8 + 0] += t0.x; f[g * 8 + 1] += t0.y; f[g * 8 + 2] += t1.x; f[g * 8 + 3] += t1.y;
-                  f[g * 8 + 4] += t2.x; f[g * 8 + 5] += t2.y; f[g * 8 + 6] += t3.x; f[g * 8 + 7] += t3.y;
+                  f2[g * 4 + 0] = fadd2(f2[g * 4 + 0], unpack_bf16x2(rr.x)); f2[g * 4 + 1] = fadd2(f2[g * 4 + 1], unpack_bf16x2(rr.y));
+                  f2[g * 4 + 2] = fadd2(f2[g * 4 + 2], unpack_bf16x2(rr.z)); f2[g * 4 + 3] = fadd2(f2[g * 4 + 3], unpack_bf16x2(rr.w));
                 }
               }
             }
@@ -343,22 +385,20 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&rbar[grp * 4 + (kchunk % NB)], (kchunk / NB) & 1);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              float r8[8];
               const uint4 rr = *reinterpret_cast<const uint4*>(my + ((static_cast<uint32_t>(g) ^ swz) << 4));
-              float2 t0 = unpack_bf16x2(rr.x), t1 = unpack_bf16x2(rr.y), t2 = unpack_bf16x2(rr.z), t3 = unpack_bf16x2(rr.w);
-              r8[0] = t0.x; r8[1] = t0.y; r8[2] = t1.x; r8[3] = t1.y; r8[4] = t2.x; r8[5] = t2.y; r8[6] = t3.x; r8[7] = t3.y;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[g * 8 + j] += r8[j];
+              f2[g * 4 + 0] = fadd2(f2[g * 4 + 0], unpack_bf16x2(rr.x)); f2[g * 4 + 1] = fadd2(f2[g * 4 + 1], unpack_bf16x2(rr.y));
+              f2[g * 4 + 2] = fadd2(f2[g * 4 + 2], unpack_bf16x2(rr.z)); f2[g * 4 + 3] = fadd2(f2[g * 4 + 3], unpack_bf16x2(rr.w));
             }
           }
           if (p.out_scale != 1.0f) {
+            const float2 sc = make_float2(p.out_scale, p.out_scale);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+            for (int j = 0; j < 16; ++j) f2[j] = fmul2(f2[j], sc);
           }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const uint4 packed = make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
-                                            pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
+            const uint4 packed = make_uint4(pack_bf16x2(f2[g * 4 + 0].x, f2[g * 4 + 0].y), pack_bf16x2(f2[g * 4 + 1].x, f2[g * 4 + 1].y),
+                                            pack_bf16x2(f2[g * 4 + 2].x, f2[g * 4 + 2].y), pack_bf16x2(f2[g * 4 + 3].x, f2[g * 4 + 3].y));
             if (direct) {
               const int col = ocol + g * 8;
               if (valid && col < p.n_out) *reinterpret_cast<uint4*>(drow + col) = packed;
@@ -440,7 +480,7 @@ static int pick_epi(const GemmConvParams& p) {
   if (p.act == 1) return EPI_GEGLU;
   const bool r = p.resid != nullptr, v = p.rowvec != nullptr, a = p.act != 0;
   if (!r && !v && !a) return EPI_PLAIN;
-  if (r && !v && !a) return EPI_RESID;
+  if (r && !v && !a) return (p.conv && p.crop > 0) ? EPI_RESID_DIRECT : EPI_RESID;
   if (!r && v && !a) return EPI_ROWVEC;
   if (!r && !v && a) return EPI_ACT;
   return EPI_GENERAL;
@@ -455,6 +495,7 @@ static int dispatch_epi(const CUtensorMap& a, const CUtensorMap& a2, const CUten
     case EPI_RESID: return launch<BN, EPI_RESID>(a, a2, a3, w, d, r, p, st);
     case EPI_ROWVEC: return launch<BN, EPI_ROWVEC>(a, a2, a3, w, d, r, p, st);
     case EPI_ACT: return launch<BN, EPI_ACT>(a, a2, a3, w, d, r, p, st);
+    case EPI_RESID_DIRECT: return launch<BN, EPI_RESID_DIRECT>(a, a2, a3, w, d, r, p, st);
     default: return launch<BN, EPI_GENERAL>(a, a2, a3, w, d, r, p, st);
   }
 }

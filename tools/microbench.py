@@ -16,6 +16,15 @@ def timeit(fn, iters=10, warm=3):
     ts.sort()
     return ts[len(ts) // 2]
 
+def timeit_hot(fn, heat, n=20):
+    """average launch time inside a long busy stretch (sustained clocks): `heat` keeps the GPU busy ~0.5 s first"""
+    for _ in range(heat): fn()
+    s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+    s.record()
+    for _ in range(n): fn()
+    e.record(); torch.cuda.synchronize()
+    return s.elapsed_time(e) / n
+
 res = []
 def rec(name, ms, flops, bytes_):
     r = dict(name=name, ms=ms, tflops=flops / ms / 1e9, gbs=bytes_ / ms / 1e6)
@@ -33,6 +42,19 @@ if "gemm" in sys.argv or len(sys.argv) == 1:
         ms = timeit(lambda: torch.matmul(a, w.t()))
         rec(f"  torch.matmul {M}x{N}x{K}", ms, 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N))
         del a, w, out
+if "gemmr" in sys.argv:
+    # the in-step flavour of the projection GEMMs: bias + residual epilogue
+    for (M, N, K) in [(655360, 320, 320), (262144, 320, 320), (163840, 640, 640), (65536, 640, 640), (40960, 1280, 1280), (655360, 320, 1280), (163840, 640, 2560)]:
+        a = torch.randn(M, K, device="cuda").bfloat16(); w = torch.randn(N, K, device="cuda").bfloat16()
+        b = torch.randn(N, device="cuda").bfloat16(); r = torch.randn(M, N, device="cuda").bfloat16()
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        for nm, fn in (("plain", lambda: ops.gemm(a, w, out=out)), ("bias", lambda: ops.gemm(a, w, bias=b, out=out)),
+                       ("bias+resid", lambda: ops.gemm(a, w, bias=b, resid=r, out=out))):
+            by = 2.0 * (M * K + N * K + M * N * (2 if "resid" in nm else 1))
+            ms = timeit(fn)
+            rec(f"gemm {M}x{N}x{K} {nm}", ms, 2.0 * M * N * K, by)
+            rec(f"gemm {M}x{N}x{K} {nm} HOT", timeit_hot(fn, int(300 / ms)), 2.0 * M * N * K, by)
+        del a, w, b, r, out
 if "conv" in sys.argv or len(sys.argv) == 1:
     for (B, H, W, Ci, Co) in [(640, 32, 32, 320, 320), (640, 16, 16, 640, 640), (640, 8, 8, 1280, 1280),
                               (640, 4, 4, 1280, 1280), (32, 64, 132, 320, 320), (32, 32, 68, 640, 640),

@@ -11,6 +11,12 @@ if kind == "gemm":
     x = torch.randn(M, K, device="cuda").bfloat16(); w = torch.randn(N, K, device="cuda").bfloat16()
     out = torch.empty(M, N // 2 if act == 1 else N, device="cuda", dtype=torch.bfloat16)
     fn = lambda: ops.gemm(x, w, act=act, out=out)
+elif kind == "gemmr":
+    M, N, K = a[:3]
+    x = torch.randn(M, K, device="cuda").bfloat16(); w = torch.randn(N, K, device="cuda").bfloat16()
+    b = torch.randn(N, device="cuda").bfloat16(); r = torch.randn(M, N, device="cuda").bfloat16()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    fn = lambda: ops.gemm(x, w, bias=b, resid=r, out=out)
 elif kind == "attn":
     imgs, N, heads, hd = a
     C = heads * hd
