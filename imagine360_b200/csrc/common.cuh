@@ -304,24 +304,24 @@ __device__ __forceinline__ float2 exp2_poly2(float2 t) {
                      __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23)));
 }
 
-// gelu_erf on two values at once: packed FFMA2/FMUL2 for the rational + polynomial part, 2+2 MUFU (rcp, ex2).
-// Same Abramowitz-Stegun 7.1.26 formula as gelu_erf (abs error <= 1.5e-7 before the approx MUFUs' ~1e-6).
+// gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) on two values at once, for the GEGLU epilogue, which is MUFU / issue bound.
+// erf from Abramowitz-Stegun 7.1.28:  erf(z) = 1 - 1 / (1 + a1 z + ... + a6 z^6)^16,  z >= 0,  |error| <= 3e-7
+// (far below the bf16 rounding of the result): ONE MUFU op (rcp) per element instead of rcp + ex2, the rest is packed
+// FFMA2 / FMUL2 (6-term Horner with 1/sqrt2 folded into the coefficients, four squarings).  With r = 1 - erf(|x|/sqrt2):
+// gelu(x) = max(x, 0) - 0.5 |x| r  for either sign of x.  Large |x|: the power overflows to +inf, r = 0, exact limit.
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
-  const float2 d = ffma2(ax, make_float2(0.3275911f * 0.70710678f, 0.3275911f * 0.70710678f), make_float2(1.f, 1.f));
-  const float2 t = make_float2(fast_rcp(d.x), fast_rcp(d.y));
-  float2 poly = ffma2(t, make_float2(1.061405429f, 1.061405429f), make_float2(-1.453152027f, -1.453152027f));
-  poly = ffma2(poly, t, make_float2(1.421413741f, 1.421413741f));
-  poly = ffma2(poly, t, make_float2(-0.284496736f, -0.284496736f));
-  poly = ffma2(poly, t, make_float2(0.254829592f, 0.254829592f));
-  poly = fmul2(poly, t);
-  const float2 xx = fmul2(x, x);
-  // exp(-z^2) with z = |x|/sqrt2  ==  exp2(x^2 * (-0.5 * log2 e))
-  const float2 ex = make_float2(fast_exp2(xx.x * -0.72134752044448170f), fast_exp2(xx.y * -0.72134752044448170f));
-  const float2 erfm = ffma2(make_float2(-poly.x, -poly.y), ex, make_float2(1.f, 1.f));     // erf(|x|/sqrt2)
-  const float2 sgn = make_float2(copysignf(erfm.x, x.x), copysignf(erfm.y, x.y));
-  const float2 hx = fmul2(x, make_float2(0.5f, 0.5f));
-  return ffma2(hx, sgn, hx);                                                               // 0.5 x (1 + erf)
+  float2 p = ffma2(ax, make_float2(5.38297500e-6f, 5.38297500e-6f), make_float2(4.88906061e-5f, 4.88906061e-5f));   // a6/8, a5/(4 sqrt2)
+  p = ffma2(p, ax, make_float2(3.80035750e-5f, 3.80035750e-5f));        // a4 / 4
+  p = ffma2(p, ax, make_float2(3.27762634e-3f, 3.27762634e-3f));        // a3 / (2 sqrt2)
+  p = ffma2(p, ax, make_float2(2.11410062e-2f, 2.11410062e-2f));        // a2 / 2
+  p = ffma2(p, ax, make_float2(4.98673469e-2f, 4.98673469e-2f));        // a1 / sqrt2
+  p = ffma2(p, ax, make_float2(1.f, 1.f));
+  p = fmul2(p, p); p = fmul2(p, p); p = fmul2(p, p); p = fmul2(p, p);   // ^16
+  const float2 r = make_float2(fast_rcp(p.x), fast_rcp(p.y));
+  const float2 m = fmul2(ax, make_float2(0.5f, 0.5f));
+  const float2 h = ffma2(x, make_float2(0.5f, 0.5f), m);                 // max(x, 0) = 0.5 x + 0.5 |x|, exact
+  return ffma2(make_float2(-m.x, -m.y), r, h);
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 // Packed SiLU for the HBM-bound GroupNorm+SiLU pass: ONE MUFU op per element (ex2 of -|y|) and the reciprocal of

@@ -65,14 +65,15 @@ template <int BN, bool RING = false> struct Cfg {
   // 4 buffers per group so that a residual chunk can be requested ~3 chunks before it is consumed
   static constexpr int kBufPerGrp = RING ? 4 : 2;
   static constexpr int kNumStg = 2 * kBufPerGrp;
-  // the 160-wide tiles (the epilogue-bound K=320/640 projections) keep the tile's bias as an fp32 table in smem (one
-  // copy per epilogue group, double buffered with the accumulator stage, filled one tile ahead through registers)
-  // instead of every thread re-loading and unpacking the same bf16 values for every chunk
-  static constexpr bool kBiasTable = BN == 160;
-  static constexpr int kTableBytes = kBiasTable ? 2 * 2 * BN * 4 : 0;   // [group][accumulator stage][BN]
-  static constexpr int kBudget = 227 * 1024 - kNumStg * kStgBytes - kTableBytes - 1024 - 256;
+  // The epilogue-bound tile shapes (160-wide K=320/640 projections, 256-wide GEGLU) keep the tile's bias as an fp32
+  // table in smem -- one copy per epilogue group, filled one tile ahead through registers -- instead of every
+  // thread re-loading and unpacking the same bf16 values for every chunk.
+  static constexpr bool kBiasTable = (BN == 160) || (BN == 256);
+  static constexpr int kTableBytes = kBiasTable ? 2 * BN * 4 : 0;       // [group][BN]
+  // dynamic smem is declared __align__(1024) (checked at run time), so no alignment slack is reserved
+  static constexpr int kBudget = 227 * 1024 - kNumStg * kStgBytes - kTableBytes - 256;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kNumStg * kStgBytes + kTableBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNumStg * kStgBytes + kTableBytes + 256 /*barriers*/;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
 };
@@ -94,11 +95,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const GemmConvParams p) {
   constexpr bool kRing = UseRing<BN, EPI>::value;
   using C = Cfg<BN, kRing>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0) __trap();            // 128B-swizzled TMA / UMMA tiles need 1024-byte aligned stages
+  uint8_t* smem = smem_raw;
   uint8_t* stg = smem + C::kStages * C::kStageBytes;            // 2 staging buffers (1024-aligned)
-  float* sbias = reinterpret_cast<float*>(stg + C::kNumStg * C::kStgBytes);   // [2 groups][2][BN] (kBiasTable only)
+  float* sbias = reinterpret_cast<float*>(stg + C::kNumStg * C::kStgBytes);   // [2 groups][BN] (kBiasTable only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg + C::kNumStg * C::kStgBytes + C::kTableBytes);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + C::kStages;         // [kStages]
@@ -243,11 +245,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto load_bias = [&](int tt) {
       if (tt < total_tiles) {
         const int c0 = (tt % p.n_tiles) * BN + gtid;
-        nb0 = (c0 < p.N) ? __bfloat162float(p.bias[c0]) : 0.f;
-        nb1 = (gtid + 128 < BN && c0 + 128 < p.N) ? __bfloat162float(p.bias[c0 + 128]) : 0.f;
+        nb0 = (has_bias && c0 < p.N) ? __bfloat162float(p.bias[c0]) : 0.f;
+        nb1 = (has_bias && gtid + 128 < BN && c0 + 128 < p.N) ? __bfloat162float(p.bias[c0 + 128]) : 0.f;
       }
     };
-    if (C::kBiasTable && !kGeglu && has_bias) load_bias(blockIdx.x);
+    if (C::kBiasTable && (has_bias || kGeglu)) load_bias(blockIdx.x);
     int as = 0; uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
@@ -273,11 +275,13 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bf16* rrow = (kResid && !ring_on && p.resid != nullptr && valid) ? p.resid + orow * p.ldr : nullptr;
       bf16* drow = p.D + orow * p.ldd;
 
-      const float* tbias = sbias + (grp * 2 + as) * BN;
-      if (C::kBiasTable && !kGeglu && has_bias) {
-        // this tile's values were fetched into registers during the previous tile; the buffer last served tile
-        // t-2, which every thread of the group left before the barrier of tile t-1
-        float* tw = sbias + (grp * 2 + as) * BN;
+      const float* tbias = sbias + grp * BN;
+      if (C::kBiasTable && (has_bias || kGeglu)) {
+        // this tile's values were fetched into registers during the previous tile.  Every thread of the group has
+        // finished reading the previous tile's table once it passed that tile's last chunk barrier; the cropped
+        // direct-store mode has no chunk barriers, hence the extra one.
+        if (direct) named_bar_sync(1 + grp, 128);
+        float* tw = sbias + grp * BN;
         tw[gtid] = nb0;
         if (gtid + 128 < BN) tw[gtid + 128] = nb1;
         named_bar_sync(1 + grp, 128);
@@ -309,7 +313,15 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float2 ba[4], bg[4];
-              if (has_bias) {
+              if (C::kBiasTable) {
+                // fp32 table (zeros when the layer has no bias): broadcast LDS.128, no unpacking, no branches
+                const float4 x0 = *reinterpret_cast<const float4*>(tbias + ci * CH + g * 8);
+                const float4 x1 = *reinterpret_cast<const float4*>(tbias + ci * CH + g * 8 + 4);
+                const float4 y0 = *reinterpret_cast<const float4*>(tbias + BN / 2 + ci * CH + g * 8);
+                const float4 y1 = *reinterpret_cast<const float4*>(tbias + BN / 2 + ci * CH + g * 8 + 4);
+                ba[0] = make_float2(x0.x, x0.y); ba[1] = make_float2(x0.z, x0.w); ba[2] = make_float2(x1.x, x1.y); ba[3] = make_float2(x1.z, x1.w);
+                bg[0] = make_float2(y0.x, y0.y); bg[1] = make_float2(y0.z, y0.w); bg[2] = make_float2(y1.x, y1.y); bg[3] = make_float2(y1.z, y1.w);
+              } else if (has_bias) {
                 const uint4 x = *reinterpret_cast<const uint4*>(p.bias + wc + g * 8);
                 const uint4 y = *reinterpret_cast<const uint4*>(p.bias + wc + BN / 2 + g * 8);
                 ba[0] = unpack_bf16x2(x.x); ba[1] = unpack_bf16x2(x.y); ba[2] = unpack_bf16x2(x.z); ba[3] = unpack_bf16x2(x.w);
