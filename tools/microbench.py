@@ -80,10 +80,12 @@ if "attn" in sys.argv or len(sys.argv) == 1:
         ms = timeit(fn)
         fl = 4.0 * imgs * heads * N * N * hd
         rec(f"attn self imgs{imgs} N{N} h{heads} d{hd}", ms, fl, 2.0 * 4 * imgs * N * C)
-        q4 = qkv.view(imgs, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
-        ms = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q4[0], q4[1], q4[2]))
-        rec(f"  torch sdpa imgs{imgs} N{N}", ms, fl, 0)
-        del qkv, out, q4
+        if "sdpa" in sys.argv:
+            q4 = qkv.view(imgs, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+            ms = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q4[0], q4[1], q4[2]))
+            rec(f"  torch sdpa imgs{imgs} N{N}", ms, fl, 0)
+            del q4
+        del qkv, out
     # WarpAttn level enc0: equi 2048 tokens <- 20 views x 256, heads 10 (C=320), hd 32, bias
     b, Fr, m, hw, EN, heads, hd = 2, 16, 20, 256, 2048, 10, 32
     C = heads * hd
