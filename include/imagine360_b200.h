@@ -141,6 +141,27 @@ int i360_avgpool_frames4_bf16(const void* x, void* out, int B, int F, long long 
 int i360_grid_sample_f32(const float* img, const float* grid, float* out, int N, int C, int Hi, int Wi, int Ho, int Wo,
                          int nearest, void* stream);
 
+/* ---- geometric pre-processing (the CPU step right before the denoising path) ---- */
+
+/* OpenCV's fixed-point bicubic weight table for 8-bit remaps (imgproc/src/imgwarp.cpp: interpolateCubic,
+ * initInterTab2D(INTER_CUBIC, fixpt)): out[(fy*32 + fx)*16 + ky*4 + kx], int16, scale 2^15.  Host only, no GPU. */
+int i360_remap_cubic_table_i16(short* out_1024x16);
+
+/* cv2.remap(src, mapx, mapy, INTER_CUBIC, borderMode=BORDER_WRAP) for uint8 RGB frames, bit-exact, batched:
+ * src [n_img, H, W, 3]; maps [n_map, h, w] float32 (device).  paired = 0: every frame is sampled with every map
+ * (outputs [n_img, n_map, ...]: process_equi, inference_dual_p2e.py:113-144, Equirec2Perspec.py:61); paired = 1:
+ * frame i with map i (outputs [n_img, 1, ...]: get_anchor_target, video_mask.py:158-173; pers2pano_vid,
+ * inference_dual_p2e.py:293-301, Perspec2Equirec.py:74).  keep: optional uint8 [n_map, h, w], pixels with keep == 0
+ * are zeroed (`persp * mask`, Perspec2Equirec.py:78).  table: device copy of i360_remap_cubic_table_i16.
+ * out_u8 [.., h, w, 3] and/or out_f32: f32_mode 1 = [.., 3, h, w] (u8 / 127.5) - 1; 2 = [.., 1, h, w] any(u8 > 0). */
+int i360_remap_cubic_wrap_u8(const void* src, int n_img, int H, int W, const float* mapx, const float* mapy,
+                             const void* keep, int n_map, int h, int w, int paired, const short* table, void* out_u8,
+                             float* out_f32, int f32_mode, void* stream);
+
+/* float32 frames [n, 3, H, W] -> uint8 [n, H, W, 3]: truncate((x + 1) * 127.5) (back_norm != 0) or truncate(x * 255),
+ * float32 arithmetic like torch + numpy .astype(uint8) (inference_dual_p2e.py:122-129; video_mask.py:168-169). */
+int i360_frames_to_u8_nhwc(const float* x, void* out, long long n, int H, int W, int back_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,5 +129,16 @@ if "norm" in sys.argv or len(sys.argv) == 1:
         ms = timeit(lambda: ops.layernorm(x.view(-1, C), g, bta))
         rec(f"layernorm {B*H*W}x{C}", ms, 0, 2.0 * 2 * x.numel())
         del x
+if "remap" in sys.argv:
+    # process_equi at the production sizes: 16 frames x 20 views, 512x1024 pano -> 256x256 views (and 1024x2048 -> 512x512)
+    import numpy as np
+    from imagine360_b200.host import preprocess as P
+    for (Hh, Ww, pres) in [(512, 1024, 256), (1024, 2048, 512)]:
+        vid = torch.rand(16, 3, Hh, Ww, device="cuda") * 2 - 1
+        th = np.linspace(-180, 180, 20)[None]; ph = np.linspace(-60, 60, 20)[None]
+        P.process_equi(vid, th, ph, pers_resolution=pres)          # builds + caches the 20 maps on the host
+        ms = timeit(lambda: P.process_equi(vid, th, ph, pers_resolution=pres))
+        by = vid.numel() * 4 + 2 * vid.numel() + 16 * 20 * 3 * pres * pres * 4 + 20 * pres * pres * 8
+        rec(f"process_equi 16x{Hh}x{Ww} -> 20 x {pres}^2", ms, 0, by)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/microbench.json", "w"), indent=1)
