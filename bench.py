@@ -318,6 +318,45 @@ def kernel_roofline(pipe, inp, size, one_step):
     return roof, breakdown
 
 
+def preprocess_roofline(device, frames=16, pano_hw=(512, 1024), res=256, cpu=True):
+    """SURVEY.md 8(f) row 1: ``process_equi`` (16 frames x 20 views, bicubic BORDER_WRAP remap) on the GPU, HBM bound;
+    algorithmic bytes = float frames in + uint8 frames out and in again + float views out + maps.  The CPU figure beside
+    it is the numpy oracle (kind "port") on ONE frame x TWO views, scaled to the 16 x 20 job."""
+    import numpy as np
+    from imagine360_b200.host import preprocess as P
+    H, W = pano_hw
+    vid = torch.rand(frames, 3, H, W, device=device) * 2 - 1
+    th, ph = np.linspace(-180, 180, 20)[None], np.linspace(-60, 60, 20)[None]
+    for _ in range(3):
+        P.process_equi(vid, th, ph, pers_resolution=res)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.int8, device=device)
+    ts = []
+    for _ in range(5):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        P.process_equi(vid, th, ph, pers_resolution=res)
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ms = sorted(ts)[len(ts) // 2]
+    by = vid.numel() * 4 + 2 * vid.numel() + frames * 20 * 3 * res * res * 4 + 20 * res * res * 8
+    pk = peaks()
+    out = {"workload": f"process_equi {frames}x{H}x{W} -> 20 views x {res}^2 (uint8 bicubic remap, BORDER_WRAP)", "ms": ms,
+           "views_per_s": frames * 20 / (ms * 1e-3), "alg_bytes": by, "alg_gbs": by / ms / 1e6, "hbm_frac": by / ms / 1e6 / pk["hbm_gbs"],
+           "gpu_launches": 2}
+    if cpu:
+        import time
+        from oracle import remap as R
+        x = vid[:1].cpu().numpy()
+        t0 = time.perf_counter()
+        R.process_equi(x, th[0, :2], ph[0, :2], pers_resolution=res)
+        sec = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 2 / sec, "unit": "views/s", "cores": 1, "kind": "port",
+                               "sample": "numpy oracle (maps + fixed-point remap), 1 frame x 2 views", "sample_seconds": sec}
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (reference algorithm) on the host cores, bounded sample
 # ----------------------------------------------------------------------------------------------------------
@@ -431,6 +470,11 @@ def main():
             out["vae_decode"] = vae_decode_roofline(device)
         except Exception as ex:  # keep the headline line even if the side measurement fails
             out["vae_decode"] = {"error": repr(ex)}
+    if world == 1 and args.size == "c3":
+        try:
+            out["preprocess"] = preprocess_roofline(device, cpu=not args.no_cpu_baseline)
+        except Exception as ex:
+            out["preprocess"] = {"error": repr(ex)}
     if not args.no_cpu_baseline and world == 1:
         run, flops, sample = cpu_sample_step()
         sec = run()

@@ -4,7 +4,7 @@
     # or:  python -c "import imagine360_b200.dropin as d; d.install(); import runpy; runpy.run_path('inference_dual_p2e.py', run_name='__main__')" --config ...
 
 If the reference tree is importable (``animatediff``, ``src``, ``diffusers`` on sys.path) its modules are imported and
-ONLY the six symbols on the hot-path boundary are rebound; everything else (CLI helpers, video
+ONLY the symbols on the hot-path boundary are rebound; everything else (CLI helpers, video
 I/O, CLIP/SAM glue) keeps coming from the reference.  Without the reference tree, stand-in modules exposing just the
 boundary symbols are registered under the same names.
 """
@@ -20,6 +20,12 @@ BOUNDARY = {
     "src.models.MVGenModel": {"MultiViewBaseModel": ("imagine360_b200.host.mvgen", "MultiViewBaseModel")},
     "src.utils.Perspective_and_Equirectangular": {"e2p": ("imagine360_b200.dropin", "e2p"), "p2e": ("imagine360_b200.dropin", "p2e")},
     "src.utils.pano": {"pad_pano": ("imagine360_b200.host.geometry", "pad_pano"), "unpad_pano": ("imagine360_b200.host.geometry", "unpad_pano")},
+    # geometric pre-processing right before the path: the script's own process_equi /
+    # pers2pano_vid reach the GPU through these two classes; get_anchor_target / get_maxrec_cord are rebound whole
+    "src.utils.pano_utils.Equirec2Perspec": {"Equirectangular": ("imagine360_b200.host.preprocess", "Equirectangular")},
+    "src.utils.pano_utils.Perspec2Equirec": {"Perspective": ("imagine360_b200.host.preprocess", "Perspective")},
+    "animatediff.utils.video_mask": {"get_anchor_target": ("imagine360_b200.host.preprocess", "get_anchor_target")},
+    "src.modules.utils": {"get_maxrec_cord": ("imagine360_b200.host.preprocess", "get_maxrec_cord")},
     "diffusers": {"AutoencoderKL": ("imagine360_b200.host.vae", "AutoencoderKL"), "DDIMScheduler": ("imagine360_b200.host.ddim", "DDIMScheduler")},
 }
 

@@ -206,6 +206,46 @@ def pers2pano_frames(persframes, ph_list, pano_H=256, pano_W=512, fov=90, th=0):
     return (pano.cpu().numpy(), mask.cpu().numpy()) if as_np else (pano, mask)
 
 
+class Equirectangular:
+    """``src.utils.pano_utils.Equirec2Perspec.Equirectangular`` (Equirec2Perspec.py:6-62) over the GPU remap: keeps the
+    uint8 panorama on the device, ``GetPerspective`` returns a numpy uint8 view like the reference."""
+
+    def __init__(self, img_name, text2light=False):
+        if isinstance(img_name, str):
+            raise NotImplementedError("pass the decoded uint8 frame (file reading is out of scope of the GPU path)")
+        img = np.roll(img_name, -60, axis=0) if text2light else img_name
+        self._height, self._width, _ = img.shape
+        self._img = torch.from_numpy(np.ascontiguousarray(img)).cuda()[None]
+
+    def GetPerspective(self, FOV, THETA, PHI, height, width):
+        key = ("e2p1", float(FOV), float(THETA), float(PHI), height, width, self._height, self._width)
+        if key not in _maps:
+            mx, my = e2p_maps(FOV, THETA, PHI, height, width, self._height, self._width)
+            _maps[key] = (torch.from_numpy(mx)[None].cuda(), torch.from_numpy(my)[None].cuda())
+            if len(_maps) > 64:
+                _maps.pop(next(iter(_maps)))
+        out, _ = remap_cubic_wrap(self._img, *_maps[key])
+        return out[0, 0].cpu().numpy()
+
+
+class Perspective:
+    """``src.utils.pano_utils.Perspec2Equirec.Perspective`` (Perspec2Equirec.py:6-83): ``GetEquirec`` -> (persp * mask
+    int64 [H, W, 3], mask int64 [H, W, 3]) like the reference."""
+
+    def __init__(self, img_name, FOV, THETA, PHI):
+        if isinstance(img_name, str):
+            raise NotImplementedError("pass the decoded uint8 frame (file reading is out of scope of the GPU path)")
+        self._height, self._width, _ = img_name.shape
+        self._img = torch.from_numpy(np.ascontiguousarray(img_name)).cuda()[None]
+        self.wFOV, self.THETA, self.PHI = FOV, THETA, PHI
+
+    def GetEquirec(self, height, width):
+        mx, my, inside = _cached_p2e(self.wFOV, self.THETA, [float(self.PHI)], self._height, self._width, height, width, self._img.device)
+        out, _ = remap_cubic_wrap(self._img, mx, my, keep=inside)
+        mask = np.repeat(inside[0].cpu().numpy().astype(np.int64)[:, :, np.newaxis], 3, axis=2)
+        return out[0, 0].cpu().numpy().astype(np.int64), mask
+
+
 def get_maxrec_cord(input):
     """Largest all-ones axis-aligned rectangle of a 0/1 mask -> (top_left_y, top_left_x, rect_width, rect_height);
     candidates are visited in the reference's order so ties resolve identically."""

@@ -52,6 +52,10 @@ def test_dropin_install_registers_boundary():
     from imagine360_b200.host import mvgen, pipeline, vae, ddim
     assert AnimationPipeline is pipeline.AnimationPipeline and MultiViewBaseModel is mvgen.MultiViewBaseModel
     assert AutoencoderKL is vae.AutoencoderKL and DDIMScheduler is ddim.DDIMScheduler
+    from animatediff.utils.video_mask import get_anchor_target
+    from src.utils.pano_utils.Equirec2Perspec import Equirectangular
+    from imagine360_b200.host import preprocess
+    assert get_anchor_target is preprocess.get_anchor_target and Equirectangular is preprocess.Equirectangular
     assert set(done) == set(d.BOUNDARY)
     for name in list(sys.modules):
         if name.split(".")[0] in ("animatediff", "src", "diffusers") and not getattr(sys.modules[name], "__file__", None):

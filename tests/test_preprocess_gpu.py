@@ -94,3 +94,18 @@ def test_get_anchor_target_matches_oracle_and_reference_golden():
             assert torch.equal(a.cpu(), b), n
     assert np.array_equal(got[4].cpu().numpy(), G["at_rel"])
     assert np.allclose(got[0].cpu().numpy()[..., ::8, ::8], G["at_anchor_s8"], atol=1e-5)
+
+
+def test_reference_named_classes_match_golden():
+    """Equirectangular.GetPerspective / Perspective.GetEquirec mirrors against outputs of the unmodified classes."""
+    from imagine360_b200.host import preprocess as P
+    from oracle import remap as R
+    eq = P.Equirectangular(G["pano"])
+    for (t, p), ref in zip(G["e2p_views"], G["e2p_out"]):
+        got = eq.GetPerspective(90, t, p, 16, 16)
+        assert got.dtype == np.uint8 and np.array_equal(got, R.get_perspective(G["pano"], 90, t, p, 16, 16))
+        assert np.count_nonzero(got != ref) <= 2
+    for p, ref, mref in zip(G["p2e_phis"], G["p2e_out"], G["p2e_mask"]):
+        got, mask = P.Perspective(G["pers"], 90, 0, p).GetEquirec(32, 64)
+        assert got.dtype == ref.dtype and mask.dtype == mref.dtype and got.shape == ref.shape
+        assert np.count_nonzero(got != ref) <= 4 and np.count_nonzero(mask != mref) <= 3

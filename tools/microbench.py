@@ -44,7 +44,10 @@ if "gemm" in sys.argv or len(sys.argv) == 1:
         del a, w, out
 if "gemmr" in sys.argv:
     # the in-step flavour of the projection GEMMs: bias + residual epilogue
-    for (M, N, K) in [(655360, 320, 320), (262144, 320, 320), (163840, 640, 640), (65536, 640, 640), (40960, 1280, 1280), (655360, 320, 1280), (163840, 640, 2560)]:
+    shapes = [(655360, 320, 320), (262144, 320, 320), (163840, 640, 640), (65536, 640, 640), (40960, 1280, 1280), (655360, 320, 1280), (163840, 640, 2560)]
+    if "gemmq" in sys.argv:     # QKV / wide projections (tile-width experiments)
+        shapes = [(655360, 960, 320), (262144, 960, 320), (163840, 1920, 640), (65536, 1920, 640), (163840, 640, 640), (65536, 640, 640), (163840, 640, 2560)]
+    for (M, N, K) in shapes:
         a = torch.randn(M, K, device="cuda").bfloat16(); w = torch.randn(N, K, device="cuda").bfloat16()
         b = torch.randn(N, device="cuda").bfloat16(); r = torch.randn(M, N, device="cuda").bfloat16()
         out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
