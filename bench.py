@@ -293,9 +293,11 @@ def kernel_roofline(pipe, inp, size, one_step):
             "avg_launch_ms": round(gc_ms / max(1, gc_n), 4), "alg_flops_per_step": flops["gemm"] + flops["conv"],
             "share_of_step_kernel_time": round(gc_ms / total, 4) if total else None}
     # DRAM traffic per launch of the same kernel: dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu
-    # capture of this command at this workload (profiles/r01_engine_traffic.json); valid only for the C3 workload.
-    tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_engine_traffic.json")
-    if os.path.exists(tj) and size is SIZES["c3"]:
+    # capture of this command at this workload (profiles/*_engine_traffic.json, latest); valid only for the C3 workload.
+    import glob
+    cands = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_engine_traffic.json")))
+    tj = cands[-1] if cands else ""          # latest capture (r01 < r01b < r02 ...)
+    if tj and size is SIZES["c3"]:
         with open(tj) as f:
             t = json.load(f)
         if t.get("launches") == gc_n:

@@ -132,6 +132,15 @@ if "norm" in sys.argv or len(sys.argv) == 1:
         ms = timeit(lambda: ops.layernorm(x.view(-1, C), g, bta))
         rec(f"layernorm {B*H*W}x{C}", ms, 0, 2.0 * 2 * x.numel())
         del x
+if "temporal" in sys.argv:
+    # VersatileAttention over the frame axis: rows (b, f, d), q/k/v column slices of the fused projection
+    for (B, D, heads, hd) in [(40, 1024, 8, 40), (2, 8192, 8, 40), (40, 256, 8, 80), (2, 2048, 8, 80), (40, 64, 8, 160), (2, 512, 8, 160)]:
+        C = heads * hd; Fr = 16
+        qkv = torch.randn(B * Fr * D, 3 * C, device="cuda").bfloat16()
+        out = torch.empty(B * Fr * D, C, device="cuda", dtype=torch.bfloat16)
+        fn = lambda: ops.temporal_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], out, B, Fr, D, heads, hd)
+        rec(f"temporal B{B} D{D} C{C}", timeit(fn), 4.0 * B * D * heads * Fr * Fr * hd, 2.0 * 4 * B * Fr * D * C)
+        del qkv, out
 if "remap" in sys.argv:
     # process_equi at the production sizes: 16 frames x 20 views, 512x1024 pano -> 256x256 views (and 1024x2048 -> 512x512)
     import numpy as np
