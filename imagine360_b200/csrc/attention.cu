@@ -44,6 +44,9 @@ struct AttnParams {
   int has_bias; int bias_rows, bias_cols;
 };
 
+#ifndef I360_POLY_MASK
+#define I360_POLY_MASK 0x22   // which of every 8 logit pairs evaluate 2^t on the FMA pipe instead of the MUFU (bit i = pair i)
+#endif
 constexpr int kAttnThreads = 320;   // warp0 TMA, warp1 MMA, warps 2..9 softmax (2 threads per query row)
 
 template <int HD>
@@ -141,9 +144,11 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS_mine, uint32_t tO_mine,
   for (int e = 0; e < 64; e += 2) {
     const float2 sv = make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1]));
     const float2 t = (!BIAS && !MASKED) ? ffma2(sv, sc2, nm2) : fadd2(sv, nm2);
-    // 3 of every 8 pairs of the plain path evaluate 2^t on the FMA / integer pipes instead of the MUFU (16 ex2 per
-    // clock per SM is the softmax bottleneck: 128x128 exps = 1024 clocks per tile against 512 clocks of MMA)
-    const bool poly = !BIAS && !MASKED && (((e >> 1) & 7) == 1 || ((e >> 1) & 7) == 4 || ((e >> 1) & 7) == 6);
+    // 2 of every 8 pairs of the plain path evaluate 2^t on the FMA / integer pipes instead of the MUFU.  ncu: the
+    // kernel is bound by issue slots (65 % busy, ~511 instructions per thread and tile) and the MUFU pipe (16 ex2 per
+    // clock per SM) together; a polynomial pair costs ~10 issue slots against 2 MUFU instructions, and 2/8 balances the
+    // two (pano level 0: 3/8 3.61 ms, 2/8 3.51 ms, 1/8 3.57 ms, 0/8 3.73 ms)
+    const bool poly = !BIAS && !MASKED && ((I360_POLY_MASK >> ((e >> 1) & 7)) & 1);
     const float2 pe = poly ? exp2_poly2(t) : make_float2(fast_exp2(t.x), fast_exp2(t.y));   // masked: exp2(-inf) = 0
     sum2 = fadd2(sum2, pe);
     pk[e >> 1] = pack_bf16x2(pe.x, pe.y);
