@@ -128,18 +128,22 @@ remap_cubic_wrap_kernel(const RemapParams p) {
 }
 
 // float32 frames [n, 3, H, W] in (-1, 1) (or (0, 1)) -> uint8 [n, H, W, 3], exactly like
-// ((x + 1) * 127.5).permute(1, 2, 0).numpy().astype(np.uint8)  /  (x * 255)...  (inference_dual_p2e.py:122-129):
-// float32 arithmetic, then C truncation toward zero.
+// ((x + 1) * 127.5).permute(1, 2, 0).numpy().astype(np.uint8)  /  (x * 255)...  (inference_dual_p2e.py:122-129) and like
+// save_videos_grid's (x * 255).numpy().astype(np.uint8) after the optional (x + 1) / 2 (animatediff/utils/util.py:55-72):
+// float32 arithmetic, then C truncation toward zero.  Frame n of the input starts at x + n * frame_stride.
 __global__ void __launch_bounds__(256)
-frames_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, long long n, long long hw, int back_norm) {
+frames_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, long long n, long long hw, int back_norm,
+                    long long frame_stride, long long chan_stride) {
   const long long total = n * hw;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long img = idx / hw, pix = idx % hw;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float v = x[(img * 3 + c) * hw + pix];
-      const float s = back_norm ? __fmul_rn(__fadd_rn(v, 1.0f), 127.5f) : __fmul_rn(v, 255.0f);
+      const float v = x[img * frame_stride + c * chan_stride + pix];
+      // mode 0: x * 255; 1: (x + 1) * 127.5; 2: ((x + 1) / 2) * 255 (save_videos_grid with rescale) -- fp32 op by op
+      const float s = back_norm == 1 ? __fmul_rn(__fadd_rn(v, 1.0f), 127.5f)
+                    : back_norm == 2 ? __fmul_rn(__fdiv_rn(__fadd_rn(v, 1.0f), 2.0f), 255.0f) : __fmul_rn(v, 255.0f);
       out[idx * 3 + c] = static_cast<uint8_t>(static_cast<int>(s));     // truncation; inputs are in range by contract
     }
   }
@@ -214,14 +218,16 @@ extern "C" int i360_remap_cubic_wrap_u8(const void* src, int n_img, int H, int W
   return I360_OK;
 }
 
-extern "C" int i360_frames_to_u8_nhwc(const float* x, void* out, long long n, int H, int W, int back_norm, void* stream) {
-  if (!x || !out || n <= 0 || H <= 0 || W <= 0) return I360_ERR_ARG;
+extern "C" int i360_frames_to_u8_nhwc(const float* x, long long frame_stride, long long chan_stride, void* out, long long n,
+                                      int H, int W, int mode, void* stream) {
+  if (!x || !out || n <= 0 || H <= 0 || W <= 0 || mode < 0 || mode > 2) return I360_ERR_ARG;
+  const int back_norm = mode;
   const long long total = n * H * W;
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
   frames_to_u8_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, static_cast<uint8_t*>(out), n, static_cast<long long>(H) * W, back_norm);
+      x, static_cast<uint8_t*>(out), n, static_cast<long long>(H) * W, back_norm, frame_stride, chan_stride);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }

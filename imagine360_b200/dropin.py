@@ -26,6 +26,8 @@ BOUNDARY = {
     "src.utils.pano_utils.Perspec2Equirec": {"Perspective": ("imagine360_b200.host.preprocess", "Perspective")},
     "animatediff.utils.video_mask": {"get_anchor_target": ("imagine360_b200.host.preprocess", "get_anchor_target")},
     "src.modules.utils": {"get_maxrec_cord": ("imagine360_b200.host.preprocess", "get_maxrec_cord")},
+    # output side (section 8(f) row 3): uint8 conversion of the decoded video on the GPU
+    "animatediff.utils.util": {"save_videos_grid": ("imagine360_b200.host.preprocess", "save_videos_grid")},
     "diffusers": {"AutoencoderKL": ("imagine360_b200.host.vae", "AutoencoderKL"), "DDIMScheduler": ("imagine360_b200.host.ddim", "DDIMScheduler")},
 }
 

@@ -144,9 +144,37 @@ def frames_to_u8(x: torch.Tensor, back_norm: bool) -> torch.Tensor:
         return y.permute(0, 2, 3, 1).to(torch.uint8).contiguous()
     x = x.contiguous()
     out = torch.empty((n, H, W, 3), dtype=torch.uint8, device=x.device)
-    check(lib().i360_frames_to_u8_nhwc(_p(x), _p(out), c_longlong(n), c_int(H), c_int(W), c_int(1 if back_norm else 0), _stream()),
-          "i360_frames_to_u8_nhwc")
+    check(lib().i360_frames_to_u8_nhwc(_p(x), c_longlong(3 * H * W), c_longlong(H * W), _p(out), c_longlong(n), c_int(H), c_int(W),
+                                       c_int(1 if back_norm else 0), _stream()), "i360_frames_to_u8_nhwc")
     return out
+
+
+def video_to_frames_u8(videos: torch.Tensor, rescale: bool = False) -> torch.Tensor:
+    """Output side: the uint8 conversion of ``save_videos_grid`` (animatediff/utils/util.py:55-72)
+    on the GPU for a single video: videos [1, c=3, t, h, w] float32 in (0, 1) (or (-1, 1) with ``rescale``) ->
+    uint8 [t, h, w, 3], bit-identical to ``((x + 1) / 2 if rescale else x) * 255`` + ``.numpy().astype(np.uint8)``.
+    (``make_grid`` is the identity for one video; the mp4 container is written by imageio on the CPU.)"""
+    b, c, t, h, w = videos.shape
+    if b != 1 or c != 3:
+        raise NotImplementedError("grid layout of several videos is CPU post-processing (out of scope)")
+    dev = _device_of(videos)
+    x = videos.to(dev, torch.float32).contiguous()
+    out = torch.empty((t, h, w, 3), dtype=torch.uint8, device=dev)
+    check(lib().i360_frames_to_u8_nhwc(_p(x), c_longlong(h * w), c_longlong(t * h * w), _p(out), c_longlong(t), c_int(h), c_int(w),
+                                       c_int(2 if rescale else 0), _stream()), "i360_frames_to_u8_nhwc")
+    return out
+
+
+def save_videos_grid(videos: torch.Tensor, path: str, rescale=False, n_rows=6, fps=8, n_frames=None):
+    """Reference signature; frames are converted on the GPU, one D2H copy of uint8 instead of float32, then imageio."""
+    import os
+    frames = video_to_frames_u8(videos, rescale)
+    if n_frames is not None:
+        frames = frames[:n_frames]
+    frames = list(frames.cpu().numpy())
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    import imageio
+    imageio.mimsave(path, frames, fps=fps)
 
 
 def remap_cubic_wrap(src_u8: torch.Tensor, mapx: torch.Tensor, mapy: torch.Tensor, keep: torch.Tensor | None = None,

@@ -158,9 +158,13 @@ int i360_remap_cubic_wrap_u8(const void* src, int n_img, int H, int W, const flo
                              const void* keep, int n_map, int h, int w, int paired, const short* table, void* out_u8,
                              float* out_f32, int f32_mode, void* stream);
 
-/* float32 frames [n, 3, H, W] -> uint8 [n, H, W, 3]: truncate((x + 1) * 127.5) (back_norm != 0) or truncate(x * 255),
- * float32 arithmetic like torch + numpy .astype(uint8) (inference_dual_p2e.py:122-129; video_mask.py:168-169). */
-int i360_frames_to_u8_nhwc(const float* x, void* out, long long n, int H, int W, int back_norm, void* stream);
+/* float32 frames -> uint8 [n, H, W, 3] with float32 arithmetic and C truncation like torch + numpy .astype(uint8):
+ * mode 0: x * 255; 1: (x + 1) * 127.5 (inference_dual_p2e.py:122-129; video_mask.py:168-169);
+ * 2: ((x + 1) / 2) * 255 (save_videos_grid with rescale, animatediff/utils/util.py:55-72; mode 0 = without).
+ * Channel c of frame i starts at x + i * frame_stride + c * chan_stride (elements), rows are contiguous: covers both
+ * [n, 3, H, W] frames and the [c, t, h, w] video layout the pipeline returns. */
+int i360_frames_to_u8_nhwc(const float* x, long long frame_stride, long long chan_stride, void* out, long long n, int H,
+                           int W, int mode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -293,3 +293,12 @@ def get_anchor_target(pixel_values, ph_list, fov=90, th=0):
         rel.append(torch.tensor([int(h / 2 - (ty + ty + rh) / 2), int(w / 2 - (tx + tx + rw) / 2), rh, rw, h, w]))
     return (torch.stack(anchors, dim=1), anchor_pers, pixel_values.clone(), torch.stack(masks, dim=1),
             torch.stack(rel, dim=0).unsqueeze(0).repeat(b, 1, 1), torch.stack(pitchs, dim=1))
+
+
+def video_to_frames_u8(videos: np.ndarray, rescale: bool = False) -> np.ndarray:
+    """uint8 conversion of save_videos_grid (animatediff/utils/util.py:55-72) for one video [1, 3, t, h, w] float32 ->
+    [t, h, w, 3] (make_grid of a single image is the identity)."""
+    x = np.transpose(videos[0].astype(np.float32), (1, 2, 3, 0))
+    if rescale:
+        x = (x + np.float32(1.0)) / np.float32(2.0)
+    return (x * np.float32(255)).astype(np.uint8)

@@ -109,3 +109,22 @@ def test_reference_named_classes_match_golden():
         got, mask = P.Perspective(G["pers"], 90, 0, p).GetEquirec(32, 64)
         assert got.dtype == ref.dtype and mask.dtype == mref.dtype and got.shape == ref.shape
         assert np.count_nonzero(got != ref) <= 4 and np.count_nonzero(mask != mref) <= 3
+
+
+@pytest.mark.parametrize("rescale", [False, True])
+def test_video_to_frames_u8_bit_exact(rescale):
+    """output side (8(f) row 3): save_videos_grid's uint8 conversion, against the oracle and against torch's own ops"""
+    from imagine360_b200.host import preprocess as P
+    from oracle import remap as R
+    g = torch.Generator().manual_seed(5)
+    v = torch.rand(1, 3, 5, 24, 40, generator=g)
+    if rescale:
+        v = v * 2 - 1
+    v[0, 0, 0, 0, :4] = torch.tensor([1.0, 0.0, 0.999999, 0.5]) if not rescale else torch.tensor([1.0, -1.0, 0.999999, 0.0])
+    out = P.video_to_frames_u8(v.cuda(), rescale)
+    assert out.dtype == torch.uint8 and out.shape == (5, 24, 40, 3)
+    assert np.array_equal(out.cpu().numpy(), R.video_to_frames_u8(v.numpy(), rescale))
+    x = v[0].permute(1, 0, 2, 3)
+    x = (x + 1.0) / 2.0 if rescale else x
+    ref = (x.permute(0, 2, 3, 1) * 255).numpy().astype(np.uint8)        # the reference's expression on one frame at a time
+    assert np.array_equal(out.cpu().numpy(), ref)
