@@ -8,6 +8,7 @@
 // copies), one warp per (pixel, head), fp32 math, one coalesced pass in and out.
 #include "common.cuh"
 #include "tmap.h"
+#include <stdlib.h>
 
 namespace i360 {
 
@@ -149,41 +150,65 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_u32(smem_row)));
 }
 
+// STAGES smem stages per warp: the tasks of the next STAGES-1 iterations are in flight while one is computed.  The kernel
+// is a pure HBM stream with ~4 KB per task, so bytes in flight per SM (Little's law against ~2 us of loaded-HBM
+// latency) set its bandwidth: 16 warps x 1 task ahead = 61 KB gave 3.9 TB/s; 3 stages put 2 tasks per warp in flight.
+template <int STAGES>
 __global__ void temporal_attn_mma_kernel(const TAParams p, int hd_pad, int pitch) {
   extern __shared__ __align__(16) uint8_t smem_ta[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int stage_elems = 3 * 16 * pitch;
-  bf16* base = reinterpret_cast<bf16*>(smem_ta) + static_cast<size_t>(warp) * 2 * stage_elems;
-  for (int i = lane; i < 2 * stage_elems / 8; i += 32) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+  bf16* base = reinterpret_cast<bf16*>(smem_ta) + static_cast<size_t>(warp) * STAGES * stage_elems;
+  for (int i = lane; i < STAGES * stage_elems / 8; i += 32) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
   __syncwarp();
   const long long total = static_cast<long long>(p.B) * p.D * p.heads;
   const long long tstride = static_cast<long long>(gridDim.x) * nwarps;
   const int cpr = p.hd >> 3, nchunks = p.F * cpr;
   const int g = lane >> 2, q4 = lane & 3;
 
+  // the (frame, 16-byte chunk) pairs this lane copies are the same for every task: the runtime divisions by the
+  // chunks-per-row count are done once here instead of ~6 times per task
+  constexpr int kMaxCopies = 10;                         // 16 frames x head_dim 160 / 8 / 32 lanes
+  int cp_smem[kMaxCopies]; int cp_frame[kMaxCopies]; int cp_col[kMaxCopies];
+  int n_copies = 0;
+#pragma unroll
+  for (int k = 0; k < kMaxCopies; ++k) {
+    const int c = lane + 32 * k;
+    const int f = c / cpr, ch = c - f * cpr;
+    cp_frame[k] = f; cp_col[k] = ch * 8; cp_smem[k] = f * pitch + ch * 8;
+    if (c < nchunks) n_copies = k + 1;
+  }
   auto issue = [&](long long task, int stage) {
     const int head = static_cast<int>(task % p.heads);
     const long long pix = task / p.heads;
     const long long row0 = (static_cast<long long>(pix / p.D) * p.F) * p.D + pix % p.D;
     bf16* sq = base + stage * stage_elems;
-    for (int c = lane; c < nchunks; c += 32) {
-      const int f = c / cpr, ch = c % cpr;
-      const long long r = row0 + static_cast<long long>(f) * p.D;
-      const int col = head * p.hd + ch * 8;
-      cp_async16(sq + f * pitch + ch * 8, p.q + r * p.ldq + col);
-      cp_async16(sq + 16 * pitch + f * pitch + ch * 8, p.k + r * p.ldk + col);
-      cp_async16(sq + 32 * pitch + f * pitch + ch * 8, p.v + r * p.ldv + col);
+#pragma unroll
+    for (int k = 0; k < kMaxCopies; ++k) {
+      if (k < n_copies) {
+        const long long r = row0 + static_cast<long long>(cp_frame[k]) * p.D;
+        const int col = head * p.hd + cp_col[k];
+        cp_async16(sq + cp_smem[k], p.q + r * p.ldq + col);
+        cp_async16(sq + 16 * pitch + cp_smem[k], p.k + r * p.ldk + col);
+        cp_async16(sq + 32 * pitch + cp_smem[k], p.v + r * p.ldv + col);
+      }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
   long long task = static_cast<long long>(blockIdx.x) * nwarps + warp;
   int stage = 0;
-  if (task < total) issue(task, 0);
-  for (; task < total; task += tstride, stage ^= 1) {
-    const long long nxt = task + tstride;
-    if (nxt < total) { issue(nxt, stage ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-    else             { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+  // prologue: STAGES-1 tasks in flight; every iteration commits exactly one (possibly empty) group, so that
+  // "all but the newest STAGES-1 groups are complete" always means "the current task's tile has landed"
+#pragma unroll
+  for (int k = 0; k < STAGES - 1; ++k) {
+    if (task + k * tstride < total) issue(task + k * tstride, k);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (; task < total; task += tstride, stage = (stage + 1 == STAGES) ? 0 : stage + 1) {
+    const long long nxt = task + (STAGES - 1) * tstride;
+    if (nxt < total) issue(nxt, (stage + STAGES - 1) % STAGES);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
     __syncwarp();
     bf16* sQ = base + stage * stage_elems;
     const bf16* sK = sQ + 16 * pitch;
@@ -244,10 +269,11 @@ __global__ void temporal_attn_mma_kernel(const TAParams p, int hd_pad, int pitch
       const int head = static_cast<int>(task % p.heads);
       const long long pix = task / p.heads;
       const long long row0 = (static_cast<long long>(pix / p.D) * p.F) * p.D + pix % p.D;
-      for (int c = lane; c < nchunks; c += 32) {
-        const int f = c / cpr, ch = c % cpr;
-        *reinterpret_cast<uint4*>(p.o + (row0 + static_cast<long long>(f) * p.D) * p.ldo + head * p.hd + ch * 8) =
-            *reinterpret_cast<const uint4*>(sQ + f * pitch + ch * 8);
+#pragma unroll
+      for (int k = 0; k < kMaxCopies; ++k) {
+        if (k < n_copies)
+          *reinterpret_cast<uint4*>(p.o + (row0 + static_cast<long long>(cp_frame[k]) * p.D) * p.ldo + head * p.hd + cp_col[k]) =
+              *reinterpret_cast<const uint4*>(sQ + cp_smem[k]);
       }
     }
     // rows >= F of the staging tile were written with garbage-free zeros only if F == 16; restore the zero padding
@@ -285,16 +311,33 @@ extern "C" int i360_temporal_attention_bf16(const void* q, long long ldq, const 
   if (F <= 16) {
     const int hd_pad = (head_dim + 15) / 16 * 16;
     const int pitch = hd_pad + 8;                       // +16 bytes per row: conflict-free fragment / ldmatrix reads
-    const size_t pw = static_cast<size_t>(2) * 3 * 16 * pitch * sizeof(bf16);
-    int w2 = 8;
-    while (w2 > 1 && pw * w2 > 110 * 1024) w2 >>= 1;
+    // Warps per SM are what buys bandwidth here (each warp keeps one ~4 KB task in flight while it computes another;
+    // measured: 16 -> 20 warps per SM = -7.5 % at head_dim 40, 8 -> 10 = -15 % at head_dim 80), so the launch takes as
+    // many warps as ~216 KB of smem and 80 registers per thread allow, in one or two CTAs per SM.  A third stage at the
+    // cost of warps (12 per SM) was slower (I360_TA_STAGES3 keeps it for experiments).
+    const size_t per_stage = static_cast<size_t>(3) * 16 * pitch * sizeof(bf16);
+    const bool three = getenv("I360_TA_STAGES3") != nullptr && per_stage * 3 * 6 <= 110 * 1024;
+    const size_t pw = per_stage * (three ? 3 : 2);
+    int total_w = static_cast<int>((216 * 1024) / pw);
+    if (total_w > 24) total_w = 24;
+    if (total_w < 1) return I360_ERR_UNSUPPORTED;
+    int ctas = total_w > 12 ? 2 : 1;
+    int w2 = total_w / ctas;
+    if (const char* e = getenv("I360_TA_WARPS")) { w2 = atoi(e); ctas = (pw * w2 * 2 <= 220 * 1024) ? 2 : 1; }
+    if (three) { w2 = 6; ctas = 2; }
     const size_t sm2 = pw * w2;
+    if (sm2 > 227 * 1024 || w2 < 1 || w2 > 32) return I360_ERR_UNSUPPORTED;
     long long bl = (total + w2 - 1) / w2;
-    const long long cap2 = static_cast<long long>(num_sms()) * (sm2 > 56 * 1024 ? 2 : 4);
+    const long long cap2 = static_cast<long long>(num_sms()) * ctas;
     if (bl > cap2) bl = cap2;
     static bool setm = false;
-    if (!setm) { cudaFuncSetAttribute(temporal_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); setm = true; }
-    temporal_attn_mma_kernel<<<static_cast<unsigned>(bl), w2 * 32, sm2, st>>>(p, hd_pad, pitch);
+    if (!setm) {
+      cudaFuncSetAttribute(temporal_attn_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(temporal_attn_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      setm = true;
+    }
+    if (three) temporal_attn_mma_kernel<3><<<static_cast<unsigned>(bl), w2 * 32, sm2, st>>>(p, hd_pad, pitch);
+    else       temporal_attn_mma_kernel<2><<<static_cast<unsigned>(bl), w2 * 32, sm2, st>>>(p, hd_pad, pitch);
     I360_CUDA_CHECK_LAUNCH();
     return I360_OK;
   }
