@@ -150,31 +150,59 @@ def run_native(args, size, rank, world, device):
                 feats_pers=cond.feats_pers[:, :1].contiguous())
     for k, v in tens.items():
         host[k] = v.detach().cpu().pin_memory()
-    dev_buf = {k: torch.empty_like(v, device=device) for k, v in host.items()}
+    # Two sets of device input buffers and a copy stream: the H2D copy of step i+1's inputs and the D2H read of step
+    # i's result run under the kernels of the neighbouring step, as a serving loop would do it.  Every step still moves
+    # its own inputs from pinned host memory and its result back to the host inside the timed region.
+    dev_bufs = [{k: torch.empty_like(v, device=device) for k, v in host.items()} for _ in range(2)]
     out_host = [torch.empty_like(host["pano_latent"]).pin_memory(), torch.empty_like(host["pers_latent"]).pin_memory()]
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = sum(v.numel() * v.element_size() for v in out_host)
     from imagine360_b200.host.pipeline import Conditioning
+    copy_stream = torch.cuda.Stream(device=device)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]      # inputs of the buffer set have landed
+    free = [torch.cuda.Event(), torch.cuda.Event()]       # the step that read the buffer set has finished
 
-    def e2e_step(i):
-        for k in host:
-            dev_buf[k].copy_(host[k], non_blocking=True)
-        c = Conditioning(dev_buf["text_pano"], dev_buf["text_pers"], dev_buf["feats_pano"],
-                         dev_buf["feats_pers"].expand(-1, size["views"], -1, -1, -1), cond.rel_pos, cond.pitch, cond.fps)
-        a, b = pipe.denoise(dev_buf["pano_latent"], dev_buf["pers_latent"], dev_buf["pano_mask"], dev_buf["pers_masks"],
-                            dev_buf["pano_masked"], dev_buf["pers_masked"], c, inp["cameras"], STEPS_PER_CLIP, 7.5,
+    def stage_inputs(j):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[j % 2])
+            for k in host:
+                dev_bufs[j % 2][k].copy_(host[k], non_blocking=True)
+            ready[j % 2].record(copy_stream)
+
+    def e2e_step(i, last):
+        main = torch.cuda.current_stream()
+        buf = dev_bufs[i % 2]
+        main.wait_event(ready[i % 2])
+        if not last:
+            stage_inputs(i + 1)
+        c = Conditioning(buf["text_pano"], buf["text_pers"], buf["feats_pano"],
+                         buf["feats_pers"].expand(-1, size["views"], -1, -1, -1), cond.rel_pos, cond.pitch, cond.fps)
+        a, b = pipe.denoise(buf["pano_latent"], buf["pers_latent"], buf["pano_mask"], buf["pers_masks"],
+                            buf["pano_masked"], buf["pers_masked"], c, inp["cameras"], STEPS_PER_CLIP, 7.5,
                             step_range=(i % STEPS_PER_CLIP, i % STEPS_PER_CLIP + 1))
-        out_host[0].copy_(a, non_blocking=True)
-        out_host[1].copy_(b, non_blocking=True)
+        free[i % 2].record(main)
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            a.record_stream(copy_stream); b.record_stream(copy_stream)
+            out_host[0].copy_(a, non_blocking=True)
+            out_host[1].copy_(b, non_blocking=True)
 
-    e2e_step(0)
+    for j in range(2):
+        free[j].record(torch.cuda.current_stream())
+    stage_inputs(0)
+    e2e_step(0, True)
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
+    copy_stream.wait_event(s)
+    stage_inputs(1)
     for i in range(args.steps):
-        e2e_step(i + 1)
+        e2e_step(i + 1, i + 1 == args.steps)
+    torch.cuda.current_stream().wait_stream(copy_stream)      # the last D2H belongs to the timed region
     e.record()
     torch.cuda.synchronize()
     t2 = torch.tensor([s.elapsed_time(e) / args.steps], device=device)
