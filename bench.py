@@ -472,11 +472,11 @@ def main():
                           "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
-    if world > 1:
-        torch.distributed.init_process_group("nccl")
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = f"cuda:{local}"
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device(device))
     r = run_native(args, size, rank, world, device)
     if rank != 0:
         if world > 1:
