@@ -25,6 +25,10 @@
 
 namespace i360 {
 
+#ifndef I360_XPOLY_MASK
+#define I360_XPOLY_MASK 0x00   // which of every 8 logit pairs take the polynomial exp2 (bit i = pair i).  None: this
+                               // kernel is latency / issue bound, not MUFU bound (0x52: 0.298 ms, 0x22: 0.282, 0x00: 0.277)
+#endif
 constexpr int kXThreads = 320;
 constexpr int kXQStages = 4;
 constexpr int kXKVBytes = 192 * 128;        // K (and V) rows of both branches, 128 B each, 128B-swizzled
@@ -84,9 +88,9 @@ __device__ __forceinline__ void x_softmax(uint32_t tS_mine, uint8_t* sPb, int ro
 #pragma unroll
   for (int e = 0; e < NC; e += 2) {
     const float2 t = ffma2(make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), sc2, nm2);
-    // 3 of 8 pairs on the FMA pipe (polynomial) instead of the MUFU; never in the chunk that holds -inf
+    // optionally some pairs on the FMA pipe (polynomial) instead of the MUFU; never in the chunk that holds -inf
     const int pi = (e >> 1) & 7;
-    const bool poly = (e < NC - 16) && (pi == 1 || pi == 4 || pi == 6);
+    const bool poly = (e < NC - 16) && ((I360_XPOLY_MASK >> pi) & 1);
     const float2 pe = poly ? exp2_poly2(t) : make_float2(fast_exp2(t.x), fast_exp2(t.y));
     sum2 = fadd2(sum2, pe);
     v[e] = __float_as_uint(pe.x); v[e + 1] = __float_as_uint(pe.y);
