@@ -13,6 +13,7 @@
 //    src/modules/transformer.py:155-159) and after (temporal sinusoidal PE, motion_module.py:350).
 #include "common.cuh"
 #include "tmap.h"
+#include <stdlib.h>
 
 namespace i360 {
 
@@ -337,9 +338,13 @@ static int gn_geometry(int C, int B, long long npix, int* block, int* chunk, int
   if (nvec <= 0 || nvec > 1024) return I360_ERR_ARG;
   int R = 384 / nvec; if (R < 1) R = 1;
   *block = R * nvec;
-  // CTAs per image: ~12 CTAs per SM in total, so the 3-5 resident CTAs per SM turn over a few times and the last
-  // wave's imbalance stays small (one CTA per image left 640 CTAs on 148 SMs: 5 vs 4 per SM, 14 % idle)
-  long long target = (static_cast<long long>(num_sms()) * 12 + B - 1) / B;
+  // CTAs per image: ~8 CTAs per SM in total, so the 3 resident CTAs per SM turn over a few times and the last wave's
+  // imbalance stays small (one CTA per image left 640 CTAs on 148 SMs: 5 vs 4 per SM, 14 % idle).  Swept on one box
+  // (I360_GN_CTAS_PER_SM, GroupNorm+SiLU stats + apply): 12 -> 8 = 0.259 -> 0.251 ms (640x32x32x320), 0.126 -> 0.120
+  // (32x64x128x320), 0.156 -> 0.142 (640x16x16x640), 0.116 -> 0.093 (640x8x8x1280); 3-4 and >= 18 are slower.
+  static int per_sm = 0;
+  if (per_sm == 0) { const char* e = getenv("I360_GN_CTAS_PER_SM"); per_sm = e ? atoi(e) : 8; if (per_sm < 1) per_sm = 8; }
+  long long target = (static_cast<long long>(num_sms()) * per_sm + B - 1) / B;
   if (target < 1) target = 1;
   long long cp = (npix + target - 1) / target;
   const long long minp = static_cast<long long>(R) * kGnDepth * 2;
