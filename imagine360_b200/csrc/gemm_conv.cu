@@ -55,8 +55,11 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 320;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue (two groups of 4)
 
-template <int BN, bool RING = false> struct Cfg {
-  static constexpr int kABytes = BM * BK * 2;
+// MT: M sub-tiles per CTA tile (1 or 2).  MT = 2 (GEMM mode, BN = 128 only) computes a 256 x 128 tile as two 128-row
+// accumulators that share the weight tile in smem: 683 instead of 569 FLOP per byte loaded from L2 for the N = 640 /
+// 1920 projections, which are bound by L2 -> SM traffic at the tensor-core pace; epilogue group g owns accumulator g.
+template <int BN, bool RING = false, int MT = 1> struct Cfg {
+  static constexpr int kABytes = MT * BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // epilogue staging: output columns leave in 32-column chunks (64-byte rows, 64B swizzle) through 2 smem
@@ -76,8 +79,10 @@ template <int BN, bool RING = false> struct Cfg {
   static constexpr int kBudget = 227 * 1024 - kNumStg * kStgBytes - kTableBytes - 256;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kNumStg * kStgBytes + kTableBytes + 256 /*barriers*/;
-  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
-                                   : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kAccCols = MT * BN;        // TMEM columns of one accumulator stage
+  static constexpr int kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128
+                                   : (2 * kAccCols <= 256) ? 256 : 512;
+  static_assert(2 * kAccCols <= 512, "two accumulator stages must fit TMEM");
 };
 
 // Epilogue flavours (compile-time: the epilogue is the critical path of the small-K layers, and one generic,
@@ -89,14 +94,14 @@ enum : int { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_RESID = 2, EPI_ROWVEC = 3, EPI_AC
 // Ring or not is a compile-time property, so the ring kernels carry no (predicated-off) direct-read instructions.
 template <int BN, int EPI> struct UseRing { static constexpr bool value = (EPI == EPI_RESID) && (BN <= 192); };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                  const GemmConvParams p) {
   constexpr bool kRing = UseRing<BN, EPI>::value;
-  using C = Cfg<BN, kRing>;
+  using C = Cfg<BN, kRing, MT>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if ((base & 1023u) != 0) __trap();            // 128B-swizzled TMA / UMMA tiles need 1024-byte aligned stages
@@ -150,7 +155,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sb = sa + C::kABytes;
           mbar_expect_tx(&full[stage], C::kStageBytes);
           if (p.conv) tma_load_4d(sa, ma, &full[stage], c0, w0 + dw, h0 + dh, b0);
-          else        tma_load_2d(sa, ma, &full[stage], c0, m_blk * BM);
+          else        tma_load_2d(sa, ma, &full[stage], c0, m_blk * (BM * MT));
           tma_load_2d(sb, &tmW, &full[stage], kcoord, n0);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         };
@@ -175,7 +180,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_base + as * C::kAccCols;
         for (int kb = 0; kb < p.k_iters; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -186,6 +191,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t da = make_smem_desc(sa + k * 32, 1024, 16, SWZ_128B);
             const uint64_t db = make_smem_desc(sb + k * 32, 1024, 16, SWZ_128B);
             umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+            if (MT == 2)      // rows 128..255 of the tile: second accumulator, same weight tile
+              umma_bf16_ss(d_tmem + BN, make_smem_desc(sa + BM * BK * 2 + k * 32, 1024, 16, SWZ_128B), db, idesc, (kb | k) != 0);
           }
           umma_commit(&empty[stage]);   // frees the smem slot once these MMAs retire
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -218,9 +225,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t kchunk = 0;                     // chunks consumed by this group so far (buffer = kchunk % NB)
     // residual prefetch iterator of the group's store thread: runs NB-1 chunks ahead of consumption
     constexpr int n_chunks_c = (EPI == EPI_GEGLU) ? (BN / 2) / C::CH : BN / C::CH;
-    int pf_t = blockIdx.x, pf_ci = grp; uint32_t pf_k = 0;
+    constexpr int kCi0 = 0, kCiStep = (MT == 2) ? 1 : 2;   // MT = 2: the group walks every chunk of ITS accumulator
+    const int ci_first = (MT == 2) ? kCi0 : grp;
+    const int row_off = (MT == 2) ? grp * BM : 0;          // tile row of this group's accumulator row 0
+    int pf_t = blockIdx.x, pf_ci = ci_first; uint32_t pf_k = 0;
     auto prefetch_resid = [&]() {            // request the residual of the next not-yet-requested chunk
-      while (pf_t < total_tiles && pf_ci >= n_chunks_c) { pf_t += gridDim.x; pf_ci = grp; }
+      while (pf_t < total_tiles && pf_ci >= n_chunks_c) { pf_t += gridDim.x; pf_ci = ci_first; }
       if (pf_t >= total_tiles) return;
       const int pn = pf_t % p.n_tiles, pm = pf_t / p.n_tiles;
       const int col = pn * BN + pf_ci * C::CH;
@@ -232,12 +242,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int pw0 = (pm % p.n_wt) * p.TW, ph0 = ((pm / p.n_wt) % p.n_ht) * p.TH, pb0 = (pm / (p.n_wt * p.n_ht)) * p.TB;
           tma_load_4d(dstb, &tmR, bar, col, pw0, ph0, pb0);
         } else {
-          tma_load_2d(dstb, &tmR, bar, col, pm * BM);
+          tma_load_2d(dstb, &tmR, bar, col, pm * (BM * MT) + row_off);
         }
       } else {
         mbar_arrive(bar);                    // dead chunk: keep the phase sequence in step
       }
-      pf_ci += 2; ++pf_k;
+      pf_ci += kCiStep; ++pf_k;
     };
     constexpr bool ring_on = kRing;          // host dispatch guarantees: residual present, tile rows are a TMA box
     if (ring_on && store_thread) { for (int i = 0; i < NB - 1; ++i) prefetch_resid(); }
@@ -268,7 +278,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           vec_idx = b;
         }
       } else {
-        const int r = m_blk * BM + row;
+        const int r = m_blk * (BM * MT) + row_off + row;
         valid = r < p.M; orow = r; vec_idx = r;
       }
       if (!valid) { orow = 0; vec_idx = 0; }
@@ -291,12 +301,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * C::kAccCols + (MT == 2 ? grp * BN : 0);
       constexpr int n_chunks = kGeglu ? (BN / 2) / CH : BN / CH;
       const int oc0 = kGeglu ? n_blk * (BN / 2) : n_blk * BN;     // first OUTPUT column of this tile
 
 #pragma unroll 1
-      for (int ci = grp; ci < n_chunks; ci += 2) {
+      for (int ci = ci_first; ci < n_chunks; ci += kCiStep) {
         const int ocol = oc0 + ci * CH;                 // output column of staged column 0
         const bool live = ocol < p.n_out;
         uint8_t* buf = gbuf + (kchunk % NB) * C::kStgBytes;
@@ -429,7 +439,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (store_thread) {
             if (live) {
               if (p.conv) tma_store_4d(&tmD, buf, ocol, w0, h0, b0);
-              else        tma_store_2d(&tmD, buf, ocol, m_blk * BM);
+              else        tma_store_2d(&tmD, buf, ocol, m_blk * (BM * MT) + row_off);
               bulk_commit();
             }
             // buffer (kchunk+NB-1) % NB == (kchunk-1) % NB was read by the store of chunk kchunk-1, which the
@@ -455,14 +465,14 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-template <int BN, int EPI>
+template <int BN, int EPI, int MT = 1>
 static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3,
                   const CUtensorMap& w, const CUtensorMap& d, const CUtensorMap& rmap, const GemmConvParams& p,
                   cudaStream_t st) {
-  using C = Cfg<BN, UseRing<BN, EPI>::value>;
+  using C = Cfg<BN, UseRing<BN, EPI>::value, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_conv_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_conv_kernel<BN, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              C::kSmemBytes) != cudaSuccess)
       return I360_ERR_CUDA;
     attr_set = true;
@@ -470,7 +480,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms()) grid = num_sms();
   if (grid <= 0) return I360_OK;
-  gemm_conv_kernel<BN, EPI><<<grid, kThreads, C::kSmemBytes, st>>>(a, a2, a3, w, d, rmap, p);
+  gemm_conv_kernel<BN, EPI, MT><<<grid, kThreads, C::kSmemBytes, st>>>(a, a2, a3, w, d, rmap, p);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -564,11 +574,19 @@ extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long 
   if (resid && (ldr % 8)) return I360_ERR_ARG;
   if (act == 1 && (N % 128)) return I360_ERR_ARG;
   if (act == 1 && (resid || rowvec)) return I360_ERR_UNSUPPORTED;
-  const int bn = pick_bn(N, act);
+  int bn = pick_bn(N, act);
+  // 256 x 128 tiles (two M sub-tiles sharing the weight tile) for the L2-bound mid-size projections: N a multiple of
+  // 128 but not of 256 (640, 1920), K >= 512, plain / bias / bias + residual epilogues, enough rows to fill the GPU
+  // (opt-in until it has been through the GPU suite and an A/B on the step: I360_GEMM_MT2=1)
+  static const bool mt2_on = getenv("I360_GEMM_MT2") != nullptr && atoi(getenv("I360_GEMM_MT2")) != 0;
+  const bool mt2 = mt2_on && act == 0 && !rowvec && out_scale == 1.0f && (N % 128 == 0) && (N % 256 != 0) && N >= 640 && K >= 512 &&
+                   M >= 256 * 148 && !bn_override(N);
+  if (mt2) bn = 128;
+  const int bm = mt2 ? 2 * BM : BM;
   GemmConvParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K; p.conv = 0;
-  p.m_tiles = (M + BM - 1) / BM; p.n_tiles = (N + bn - 1) / bn; p.k_iters = (K + BK - 1) / BK;
+  p.m_tiles = (M + bm - 1) / bm; p.n_tiles = (N + bn - 1) / bn; p.k_iters = (K + BK - 1) / BK;
   p.D = static_cast<bf16*>(D); p.ldd = ldd;
   p.bias = static_cast<const bf16*>(bias);
   p.resid = static_cast<const bf16*>(resid); p.ldr = ldr;
@@ -576,7 +594,7 @@ extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long 
   p.act = act; p.out_scale = out_scale; p.n_out = (act == 1) ? N / 2 : N;
   CUtensorMap ta, tw;
   uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}; uint64_t sA[1] = {(uint64_t)lda * 2};
-  uint32_t bA[2] = {BK, BM};
+  uint32_t bA[2] = {BK, (uint32_t)bm};
   uint64_t dW[2] = {(uint64_t)K, (uint64_t)N}; uint64_t sW[1] = {(uint64_t)ldw * 2};
   uint32_t bW[2] = {BK, (uint32_t)bn};
   int r = get_tmap_bf16(&ta, A, 2, dA, sA, bA, 3); if (r) return r;
@@ -589,6 +607,10 @@ extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long 
   if (resid) {
     uint64_t sR[1] = {(uint64_t)ldr * 2};
     r = get_tmap_bf16(&tr, resid, 2, dD, sR, bD, 2); if (r) return r;
+  }
+  if (mt2) {
+    if (resid) return launch<128, EPI_RESID, 2>(ta, ta, ta, tw, td, tr, p, static_cast<cudaStream_t>(stream));
+    return launch<128, EPI_PLAIN, 2>(ta, ta, ta, tw, td, tr, p, static_cast<cudaStream_t>(stream));
   }
   return dispatch(bn, ta, ta, ta, tw, td, tr, p, static_cast<cudaStream_t>(stream));
 }

@@ -27,10 +27,11 @@ def _rand(*shape, seed, scale=1.0):
 
 
 def _slabs(M, n=8):
-    """first, last and a few interior 4096-row slabs of an M-row matrix"""
-    step = max(1, (M // 4096) // n)
-    idx = sorted(set([0, M // 4096 - 1] + list(range(0, M // 4096, step))))
-    return [(i * 4096, min(M, (i + 1) * 4096)) for i in idx]
+    """first, last and a few interior 4096-row slabs of an M-row matrix (the last slab runs to the end: row tails)"""
+    nb = max(1, M // 4096)
+    step = max(1, nb // n)
+    idx = sorted(set([0, nb - 1] + list(range(0, nb, step))))
+    return [(i * 4096, M if i == nb - 1 else (i + 1) * 4096) for i in idx]
 
 
 @pytest.mark.parametrize("M,N,K,flavour", [
@@ -40,6 +41,10 @@ def _slabs(M, n=8):
     (262144, 320, 320, "bias+resid"),     # pano level-0
     (163840, 640, 2560, "bias+resid"),    # level-1 FF output
     (40960, 10240, 1280, "geglu"),        # level-2 GEGLU (tensor bound)
+    (163840, 640, 640, "bias"),           # level-1 projections: 256 x 128 tiles (two M sub-tiles per CTA)
+    (65536, 1920, 640, "bias+resid"),     # pano level-1 QKV width with the residual ring on 256-row tiles
+    (40001, 640, 512, "bias+resid"),      # row tail: the last 256-row tile is partly / its second half entirely out of range
+    (37889, 1920, 1024, "plain"),
 ])
 def test_gemm_full_size(M, N, K, flavour):
     from imagine360_b200 import ops
