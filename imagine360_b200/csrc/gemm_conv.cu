@@ -577,10 +577,11 @@ extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long 
   int bn = pick_bn(N, act);
   // 256 x 128 tiles (two M sub-tiles sharing the weight tile) for the L2-bound mid-size projections: N a multiple of
   // 128 but not of 256 (640, 1920), K >= 512, plain / bias / bias + residual epilogues, enough rows to fill the GPU
-  // (opt-in until it has been through the GPU suite and an A/B on the step: I360_GEMM_MT2=1)
-  static const bool mt2_on = getenv("I360_GEMM_MT2") != nullptr && atoi(getenv("I360_GEMM_MT2")) != 0;
+  // Measured against the 160 / 192-wide tiles on one box: N = 640: -2..-5 % (K = 640 and 2560, with and without the
+  // residual ring); N = 1920: -3 % without, +5 % with a residual (3-stage ring) -> not used there.  I360_GEMM_MT2=0 disables.
+  static const bool mt2_on = getenv("I360_GEMM_MT2") == nullptr || atoi(getenv("I360_GEMM_MT2")) != 0;
   const bool mt2 = mt2_on && act == 0 && !rowvec && out_scale == 1.0f && (N % 128 == 0) && (N % 256 != 0) && N >= 640 && K >= 512 &&
-                   M >= 256 * 148 && !bn_override(N);
+                   M >= 256 * 148 && !(resid && N > 640) && !bn_override(N);
   if (mt2) bn = 128;
   const int bm = mt2 ? 2 * BM : BM;
   GemmConvParams p;
