@@ -71,3 +71,14 @@ def test_ddim_schedule_matches_reference():
     for n in (50, 25):
         s.set_timesteps(n)
         assert torch.equal(s.timesteps, g[f"timesteps_{n}"])
+
+
+def test_fused_cross_attention_limits_are_host_checkable():
+    """the host picks the fused text + image-prompt kernel only inside its limits (head_dim 64, <= 96 keys per branch,
+    at most three 64-key P blocks); everything else takes the generic two-call path"""
+    from imagine360_b200 import ops
+    assert ops.cross_attention_text_ip_supported(64, 77, 64)          # the production shape
+    assert ops.cross_attention_text_ip_supported(64, 77, 16) and ops.cross_attention_text_ip_supported(64, 1, 1)
+    assert not ops.cross_attention_text_ip_supported(32, 77, 64)      # WarpAttn's head_dim
+    assert not ops.cross_attention_text_ip_supported(64, 128, 64)     # > 96 keys in one branch
+    assert not ops.cross_attention_text_ip_supported(64, 96, 96)      # 2 + 2 P blocks
