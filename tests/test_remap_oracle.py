@@ -84,3 +84,30 @@ def test_host_maps_and_rectangle_match_oracle():
         m = (rng.random((rng.integers(2, 30), rng.integers(2, 40))) < 0.8).astype(np.int64)
         assert tuple(P.get_maxrec_cord(m)) == tuple(R.get_maxrec_cord(m))
     assert tuple(P.get_maxrec_cord(G["maxrec_mask"])) == tuple(G["maxrec_out"])
+
+
+def test_max_rectangle_against_brute_force():
+    """the stack scan (oracle and product) finds a rectangle of maximal area that is all ones"""
+    from imagine360_b200.host import preprocess as P
+    rng = np.random.default_rng(9)
+    for _ in range(25):
+        h, w = int(rng.integers(1, 9)), int(rng.integers(1, 10))
+        m = (rng.random((h, w)) < 0.7).astype(np.int64)
+        best = 0
+        for y0 in range(h):
+            for x0 in range(w):
+                for y1 in range(y0 + 1, h + 1):
+                    for x1 in range(x0 + 1, w + 1):
+                        if m[y0:y1, x0:x1].all():
+                            best = max(best, (y1 - y0) * (x1 - x0))
+        for fn in (R.get_maxrec_cord, P.get_maxrec_cord):
+            ty, tx, rw, rh = (int(v) for v in fn(m))
+            assert rw * rh == best
+            if best:
+                assert m[ty:ty + rh, tx:tx + rw].all()
+
+
+def test_wrap_index_matches_python_modulo():
+    p = np.arange(-300, 300)
+    for n in (1, 2, 7, 64):
+        assert np.array_equal(R._wrap(p, n), np.mod(p, n))
