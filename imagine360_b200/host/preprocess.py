@@ -4,8 +4,8 @@ Host-side mirror of the reference functions that resample 8-bit frames between t
 perspective views with ``cv2.remap(INTER_CUBIC, BORDER_WRAP)`` on the CPU, one (frame, view) pair at a time:
 
   * ``process_equi``        inference_dual_p2e.py:113-144   (F x 20 remaps, maps recomputed for every pair)
-  * ``pers2pano_frames``    inference_dual_p2e.py:293-301   (per-frame loop of ``pers2pano_vid``; the camera estimation
-                                                              models before it are third-party and stay out of scope)
+  * ``pers2pano_vid`` / ``pers2pano_frames``  inference_dual_p2e.py:256-305 (the camera estimation models it calls are
+                                                              third-party objects passed in by the caller, as in the reference)
   * ``get_anchor_target``   animatediff/utils/video_mask.py:158-217
   * ``get_maxrec_cord``     src/modules/utils.py:39-73      (pure-Python O(H*W) scan -> numpy run-lengths + stack)
 
@@ -232,6 +232,44 @@ def pers2pano_frames(persframes, ph_list, pano_H=256, pano_W=512, fov=90, th=0):
     pano = pano[:, 0]
     mask = (1 - inside).unsqueeze(-1)
     return (pano.cpu().numpy(), mask.cpu().numpy()) if as_np else (pano, mask)
+
+
+def fit_pitch_linear(pitches) -> list:
+    """The temporal smoothing of the per-frame pitch estimates in ``pers2pano_vid`` (inference_dual_p2e.py:286-291):
+    ordinary least squares of pitch over the frame index, evaluated at the frame indices.  Uses scikit-learn's
+    ``LinearRegression`` when it is installed (the reference's own dependency: same float64 result bit for bit), else
+    the centred closed form sklearn solves."""
+    y = np.asarray(pitches, dtype=np.float64).reshape(-1)
+    x = np.arange(len(y), dtype=np.float64).reshape(-1, 1)
+    try:
+        from sklearn.linear_model import LinearRegression
+        return LinearRegression().fit(x, y).predict(x).tolist()
+    except ImportError:
+        xm, ym = x.mean(), y.mean()
+        denom = ((x[:, 0] - xm) ** 2).sum()
+        coef = ((x[:, 0] - xm) * (y - ym)).sum() / denom if denom > 0 else 0.0
+        return (x[:, 0] * coef + (ym - xm * coef)).tolist()
+
+
+def pers2pano_vid(model, modelname, persframes, pano_H=256, pano_W=512, fov=90, th=0, ph=0):
+    """Reference signature (inference_dual_p2e.py:256-305).  The camera-estimation model is the caller's (third party:
+    GeoCalib / PerspectiveFields, called exactly like the reference does); the pitch fit runs on the host and the F
+    perspective -> panorama resamplings are one GPU launch.  Returns (ph_list, pano_frames, pano_mask, pano_frames).
+    Without a model the constant ``ph`` is used for every frame (the reference's own else-branch cannot run: it fits
+    a regression on an empty index list)."""
+    n = persframes.shape[0]
+    estimates = []
+    for i in range(n):
+        if modelname == "geocalib":
+            img = torch.Tensor(persframes[i] / 255).permute(2, 0, 1).cuda()
+            results = model.calibrate(img)
+            _roll, pitch = torch.rad2deg(results["gravity"].rp).unbind(-1)
+            estimates.append(pitch.item())
+        elif modelname == "perspectivefields":
+            estimates.append(model.inference(img_bgr=persframes[i])["pred_pitch"].cpu().numpy())
+    ph_list = fit_pitch_linear(estimates) if len(estimates) == n and n > 0 else [ph] * n
+    frames, mask = pers2pano_frames(persframes, ph_list, pano_H=pano_H, pano_W=pano_W, fov=fov, th=th)
+    return ph_list, frames, mask, frames
 
 
 class Equirectangular:

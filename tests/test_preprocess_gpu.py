@@ -128,3 +128,35 @@ def test_video_to_frames_u8_bit_exact(rescale):
     x = (x + 1.0) / 2.0 if rescale else x
     ref = (x.permute(0, 2, 3, 1) * 255).numpy().astype(np.uint8)        # the reference's expression on one frame at a time
     assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_pers2pano_vid_with_a_stub_camera_model():
+    """reference signature: per-frame pitch from the caller's GeoCalib-like model, least-squares fit over the frame
+    index, then one batched perspective -> panorama resampling; against the oracle fed with the same fitted pitches"""
+    import types
+    from imagine360_b200.host import preprocess as P
+    from oracle import remap as R
+    rng = np.random.default_rng(21)
+    frames = rng.integers(0, 256, (4, 32, 32, 3), dtype=np.uint8)
+    pitches_deg = [3.0, 4.5, 2.0, 6.0]
+
+    class Stub:
+        def __init__(self):
+            self.i = 0
+
+        def calibrate(self, img):
+            assert img.is_cuda and img.shape == (3, 32, 32) and float(img.max()) <= 1.0
+            rp = torch.deg2rad(torch.tensor([0.0, pitches_deg[self.i]], dtype=torch.float64))
+            self.i += 1
+            return {"camera": None, "gravity": types.SimpleNamespace(rp=rp)}
+
+    ph_list, pano, mask, pano2 = P.pers2pano_vid(Stub(), "geocalib", frames, pano_H=48, pano_W=96)
+    assert len(ph_list) == 4 and pano is pano2 and pano.shape == (4, 48, 96, 3) and mask.shape == (4, 48, 96, 1)
+    x = np.arange(4)
+    slope, icpt = np.polyfit(x, np.rad2deg(np.deg2rad(np.array(pitches_deg))), 1)
+    assert np.allclose(ph_list, slope * x + icpt, atol=1e-9)
+    rp, rm = R.pers2pano_frames(frames, ph_list, 48, 96)
+    assert np.array_equal(pano, rp) and np.array_equal(mask, rm)
+    # no model: constant pitch for every frame
+    ph2, pano3, _, _ = P.pers2pano_vid(None, "none", frames[:2], pano_H=48, pano_W=96, ph=5.0)
+    assert ph2 == [5.0, 5.0] and np.array_equal(pano3, R.pers2pano_frames(frames[:2], ph2, 48, 96)[0])

@@ -111,3 +111,19 @@ def test_wrap_index_matches_python_modulo():
     p = np.arange(-300, 300)
     for n in (1, 2, 7, 64):
         assert np.array_equal(R._wrap(p, n), np.mod(p, n))
+
+
+def test_pitch_fit_matches_sklearn():
+    """pers2pano_vid's temporal smoothing of the pitch estimates (inference_dual_p2e.py:286-291)"""
+    sk = pytest.importorskip("sklearn.linear_model")
+    from imagine360_b200.host import preprocess as P
+    rng = np.random.default_rng(4)
+    for n in (2, 5, 16, 24):
+        y = rng.normal(size=n) * 7 + 3
+        x = np.arange(n).reshape(-1, 1)
+        ref = sk.LinearRegression().fit(x, y).predict(x)
+        assert np.array_equal(np.array(P.fit_pitch_linear(y)), ref)
+        # and the closed form used when scikit-learn is absent agrees to rounding
+        xm, ym = x.mean(), y.mean()
+        coef = ((x[:, 0] - xm) * (y - ym)).sum() / ((x[:, 0] - xm) ** 2).sum()
+        assert np.allclose(x[:, 0] * coef + (ym - xm * coef), ref, rtol=0, atol=1e-12)
