@@ -49,7 +49,12 @@ def camera_lists(cameras):
         if isinstance(v, torch.Tensor):
             v = v.detach().reshape(-1).cpu().double().tolist()
         out.append(tuple(float(x) for x in np.asarray(v, dtype=np.float64).reshape(-1)))
-    return tuple(out)
+    # the reference accepts a scalar for any of the three (index_list_or_scalar,
+    # src/utils/Perspective_and_Equirectangular/utils.py:18-23): broadcast it over the cameras
+    n = max(len(o) for o in out)
+    if any(len(o) not in (1, n) for o in out):
+        raise ValueError(f"camera lists of different lengths: {[len(o) for o in out]}")
+    return tuple(o * n if len(o) == 1 and n > 1 else o for o in out)
 
 
 def _rot(axis, angle):

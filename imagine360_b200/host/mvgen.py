@@ -15,7 +15,7 @@ import torch.nn.functional as F
 from .. import ops
 from . import forward as Fw
 from . import geometry as G
-from .unet3d import BF16, Attention, GEGLU, cached, fused_w, geglu_w, lin_w
+from .unet3d import BF16, GEGLU, _EPOCH, _sig, cached, fused_w, geglu_w, lin_w
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -218,10 +218,24 @@ class MultiViewBaseModel(nn.Module):
                                                 for blk in unet.up_blocks if blk.upsamplers is not None])
         self._adapter_cache = {}
 
-    # -- step-invariant adapter tokens, keyed on the feature tensors' identity -----------------------------
+    # -- step-invariant adapter tokens ------------------------------------------------------------------
+    def _adapter_params(self):
+        ps = []
+        for u in (self.unet, self.pano_unet):
+            for name in ("temporal_proj", "image_proj_model", "add_cond_embedding", "add_cond_embedding2", "cond_rp_proj"):
+                mod = getattr(u, name, None)
+                if mod is not None:
+                    ps.extend(mod.parameters())
+        return ps
+
     def _adapter(self, feats_pano, feats_pers, rel_pos, pitch):
-        key = (feats_pano.data_ptr(), feats_pano._version, feats_pers.data_ptr(), feats_pers._version,
-               rel_pos.data_ptr(), pitch.data_ptr(), tuple(feats_pers.shape))
+        """Clean IP tokens of both branches, recomputed only when the conditioning tensors or the adapter weights change.
+        The cache entry holds strong references to the keyed tensors: while it lives their storage cannot be freed
+        and handed to the next clip's tensors, so (data_ptr, _version, shape, strides) identifies the CONTENTS
+        (a freed-and-reallocated block with new contents would otherwise reproduce the same key)."""
+        keyed = (feats_pano, feats_pers, rel_pos, pitch)
+        key = (tuple((t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype) for t in keyed),
+               _sig(self._adapter_params()), _EPOCH[0])
         hit = self._adapter_cache.get("k")
         if hit is not None and hit[0] == key:
             return hit[1]
@@ -236,7 +250,7 @@ class MultiViewBaseModel(nn.Module):
             ip_pers = ip_tokens_clean(self.unet, fp)
         rp = relpos_tokens(self.pano_unet, rel_pos, pitch, ip_pano.shape[1]) if self.pano_unet.use_relative_postions == "WithAdapter" else None
         val = (ip_pano.contiguous(), ip_pers.contiguous(), rp)
-        self._adapter_cache["k"] = (key, val)
+        self._adapter_cache["k"] = (key, val, keyed)      # keyed: keeps the storages alive (see above)
         return val
 
     @torch.no_grad()
@@ -244,6 +258,17 @@ class MultiViewBaseModel(nn.Module):
                 use_ip_plus_cross_attention, fps_tensor_pano, fps_tensor_pers, reference_images_clip_feat_pano,
                 reference_images_clip_feat_pers, relative_position_tensor, pitchs_tensor, antipodal_draws=None,
                 ip_noise=None):
+        """Reference signature (MVGenModel.py:59-69); runs :meth:`_forward` with ``latents.device`` current."""
+        with ops.on_device(latents.device):
+            return self._forward(latents, pano_latent, timestep, prompt_embd, pano_prompt_embd, cameras, use_fps_condition,
+                                 use_ip_plus_cross_attention, fps_tensor_pano, fps_tensor_pers, reference_images_clip_feat_pano,
+                                 reference_images_clip_feat_pers, relative_position_tensor, pitchs_tensor, antipodal_draws,
+                                 ip_noise)
+
+    def _forward(self, latents, pano_latent, timestep, prompt_embd, pano_prompt_embd, cameras, use_fps_condition,
+                 use_ip_plus_cross_attention, fps_tensor_pano, fps_tensor_pers, reference_images_clip_feat_pano,
+                 reference_images_clip_feat_pers, relative_position_tensor, pitchs_tensor, antipodal_draws=None,
+                 ip_noise=None):
         """One dual-branch denoise step (MVGenModel.py:59-481).  ``antipodal_draws`` / ``ip_noise`` let tests inject the
         outcomes of the reference's ``random.random() < 0.4`` (src/utils/utils.py:15) and ``torch.randn_like``
         (MVGenModel.py:12) draws; by default they are drawn here in the reference's order."""

@@ -8,6 +8,7 @@ Same constructor and ``__call__`` signature / ``video_batch`` contract as the re
 from __future__ import annotations
 
 import random
+import sys
 from dataclasses import dataclass
 from types import SimpleNamespace
 
@@ -17,6 +18,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from . import geometry as G
+from .unet3d import refresh_packed_weights
 
 BF16 = torch.bfloat16
 
@@ -38,6 +40,66 @@ class Conditioning:
     fps: int = 8
 
 
+class ResizeLongestSide:
+    """``segment_anything.utils.transforms.ResizeLongestSide.apply_image`` restated (third-party package, not vendored
+    in the reference tree and absent offline; requirements.txt pins no version): resize a uint8 HxWxC image so its
+    longest side is ``target_length`` -- ``int(x * scale + 0.5)`` sizes, PIL bilinear (what torchvision's
+    ``resize(to_pil_image(image), size)`` does)."""
+
+    def __init__(self, target_length: int):
+        self.target_length = target_length
+
+    @staticmethod
+    def get_preprocess_shape(oldh: int, oldw: int, long_side_length: int):
+        scale = long_side_length * 1.0 / max(oldh, oldw)
+        return int(oldh * scale + 0.5), int(oldw * scale + 0.5)
+
+    def apply_image(self, image: np.ndarray) -> np.ndarray:
+        from PIL import Image
+        h, w = self.get_preprocess_shape(image.shape[0], image.shape[1], self.target_length)
+        return np.array(Image.fromarray(image).resize((w, h), Image.BILINEAR))
+
+
+class SamPredictor:
+    """The three ``segment_anything.SamPredictor`` members the reference pipeline touches (``transform``,
+    ``set_torch_image``, ``get_image_embedding``; pipeline...dual.py:171-174,:675-718), restated for boxes without the
+    package.  ``sam_model`` is what ``sam_model_registry["vit_b"]()`` returns: ``.image_encoder`` (with ``.img_size``),
+    ``.pixel_mean`` / ``.pixel_std`` buffers; ``Sam.preprocess`` (normalise, zero-pad right/bottom to the square
+    input) is used when the model has it."""
+
+    def __init__(self, sam_model):
+        self.model = sam_model
+        self.transform = ResizeLongestSide(sam_model.image_encoder.img_size)
+        self.features = None
+
+    def _preprocess(self, x):
+        if callable(getattr(self.model, "preprocess", None)):
+            return self.model.preprocess(x)
+        x = (x - self.model.pixel_mean) / self.model.pixel_std
+        size = self.model.image_encoder.img_size
+        return F.pad(x, (0, size - x.shape[-1], 0, size - x.shape[-2]))
+
+    @torch.no_grad()
+    def set_torch_image(self, transformed_image, original_image_size):
+        size = self.model.image_encoder.img_size
+        assert transformed_image.dim() == 4 and transformed_image.shape[1] == 3 and max(transformed_image.shape[2:]) == size, \
+            f"set_torch_image input must be BCHW with long side {size}."
+        self.features = self.model.image_encoder(self._preprocess(transformed_image))
+
+    def get_image_embedding(self):
+        if self.features is None:
+            raise RuntimeError("An image must be set with .set_image(...) to generate an embedding.")
+        return self.features
+
+
+def _make_sam_predictor(image_encoder):
+    try:                                  # the real package wins when it is installed (same three members)
+        from segment_anything import SamPredictor as _Real
+        return _Real(image_encoder)
+    except ImportError:
+        return SamPredictor(image_encoder)
+
+
 class AnimationPipeline:
     def __init__(self, vae, text_encoder, tokenizer, pers_unet, pano_unet, mv_base_model, scheduler, image_encoder=None,
                  image_encoder_name="CLIP"):
@@ -46,6 +108,10 @@ class AnimationPipeline:
         self.image_encoder, self.image_encoder_name = image_encoder, image_encoder_name
         self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1) if vae is not None else 8
         self.device = torch.device("cpu")
+        # pipeline...dual.py:171-174: the pipeline itself wraps the raw SAM model
+        if image_encoder_name == "SAM" and image_encoder is not None and not callable(getattr(image_encoder, "embed_frames", None)):
+            self.SAMpredictor = _make_sam_predictor(image_encoder)
+            self.SAMProcessor = self.SAMpredictor.transform
 
     def to(self, device):
         self.device = torch.device(device)
@@ -103,16 +169,29 @@ class AnimationPipeline:
     @torch.no_grad()
     def denoise(self, pano_latent, pers_latent, pano_mask, pers_masks, pano_masked, pers_masked, cond: Conditioning, cameras,
                 num_inference_steps=50, guidance_scale=7.5, on_step=None, step_range=None, inject=None):
+        with ops.on_device(pano_latent.device):
+            return self._denoise(pano_latent, pers_latent, pano_mask, pers_masks, pano_masked, pers_masked, cond, cameras,
+                                 num_inference_steps, guidance_scale, on_step, step_range, inject)
+
+    def _denoise(self, pano_latent, pers_latent, pano_mask, pers_masks, pano_masked, pers_masked, cond: Conditioning, cameras,
+                 num_inference_steps=50, guidance_scale=7.5, on_step=None, step_range=None, inject=None):
         """The `for t in timesteps` loop (pipeline...dual.py:734-809) -> (pano_latent, pers_latent).
         ``step_range=(i0, i1)`` runs only loop iterations i0..i1-1 of the ``num_inference_steps`` schedule.
         ``inject(i) -> dict(antipodal_draws=[7 bools], ip_noise=(pano, pers))`` overrides the per-step random draws (tests)."""
         dev = pano_latent.device
         m = pers_latent.shape[1]
         self.scheduler.set_timesteps(num_inference_steps, device=dev)
-        fps_pano = torch.tensor([cond.fps, cond.fps], device=dev)
-        fps_pers = fps_pano[:, None].repeat(1, m)
-        rel_pos = cond.rel_pos.to(dev)[None].repeat(2, 1, 1)
-        pitch = cond.pitch.to(dev)[None].repeat(2, 1)
+        # CFG-doubled per-clip tensors live on the Conditioning object: they are the same objects for every step (and
+        # every denoise() call) of a clip, which is what lets the model's adapter cache recognise the clip
+        derived = cond.__dict__.get("_derived")
+        if derived is None or derived[0] != (dev, m, cond.rel_pos.data_ptr(), cond.rel_pos._version, cond.pitch.data_ptr(),
+                                             cond.pitch._version, cond.fps):
+            fps_pano = torch.tensor([cond.fps, cond.fps], device=dev)
+            derived = ((dev, m, cond.rel_pos.data_ptr(), cond.rel_pos._version, cond.pitch.data_ptr(), cond.pitch._version, cond.fps),
+                       fps_pano, fps_pano[:, None].repeat(1, m), cond.rel_pos.to(dev)[None].repeat(2, 1, 1),
+                       cond.pitch.to(dev)[None].repeat(2, 1))
+            cond.__dict__["_derived"] = derived
+        _, fps_pano, fps_pers, rel_pos, pitch = derived
         static_pano = torch.cat([pano_mask.to(BF16), pano_masked.to(BF16)], dim=1)
         static_pers = torch.cat([pers_masks.to(BF16), pers_masked.to(BF16)], dim=2)
         pano_latent, pers_latent = pano_latent.to(BF16).contiguous(), pers_latent.to(BF16).contiguous()
@@ -152,27 +231,64 @@ class AnimationPipeline:
 
     # ------------------------------------------------------------------------------------------------
     def _encode_prompt(self, prompt, device, negative_prompt):
-        """:227-299 through the caller-supplied CLIP tokenizer / text encoder (third-party, out of scope)."""
+        """:227-299 through the caller-supplied CLIP tokenizer / text encoder -> cat([uncond, cond]) [2 * len(prompt), 77, D]."""
+        cfg = getattr(self.text_encoder, "config", None)
+        use_mask = bool(getattr(cfg, "use_attention_mask", False))
+
         def enc(texts):
-            ids = self.tokenizer(texts, padding="max_length", max_length=self.tokenizer.model_max_length, truncation=True,
-                                 return_tensors="pt").input_ids
-            return self.text_encoder(ids.to(device))[0]
+            inputs = self.tokenizer(texts, padding="max_length", max_length=self.tokenizer.model_max_length, truncation=True,
+                                    return_tensors="pt")
+            mask = inputs.attention_mask.to(device) if use_mask else None
+            return self.text_encoder(inputs.input_ids.to(device), attention_mask=mask)[0]
+        negative_prompt = ["" if n is None else n for n in negative_prompt]
         return torch.cat([enc(negative_prompt), enc(prompt)])
 
     def _sam_features(self, anchor_pixels):
-        """:675-718 through the caller-supplied SAM predictor (third-party, out of scope)."""
-        if self.image_encoder is None or not callable(getattr(self.image_encoder, "embed_frames", None)):
-            raise NotImplementedError("pass an image_encoder exposing embed_frames(frames[f,3,h,w]) -> [f, 4096, 256]")
-        return self.image_encoder.embed_frames(anchor_pixels)
+        """pipeline...dual.py:675-718 for one anchor video [f, 3, h, w] in (-1, 1) -> SAM features [f, (h w), c]:
+        uint8 conversion, long side resized to the encoder's input size, batches of 8 frames through
+        ``set_torch_image`` / ``get_image_embedding``, ``f c h w -> f (h w) c``.  An ``image_encoder`` exposing
+        ``embed_frames(frames) -> [f, hw, c]`` (e.g. a pre-computed-feature source) is used directly instead."""
+        if callable(getattr(self.image_encoder, "embed_frames", None)):
+            return self.image_encoder.embed_frames(anchor_pixels)
+        if self.image_encoder_name != "SAM" or not hasattr(self, "SAMpredictor"):
+            msg = "imagine360_b200: use_ip_plus_cross_attention needs image_encoder_name='SAM' and a SAM model (or embed_frames)"
+            print(msg, file=sys.stderr, flush=True)       # the caller swallows exceptions (inference_dual_p2e.py:596-597)
+            raise ValueError(msg)
+        image_array = ((anchor_pixels.to(torch.float32) + 1.0) / 2.0 * 255).to(torch.uint8).cpu().numpy().transpose(0, 2, 3, 1)
+        frames = torch.stack([torch.as_tensor(self.SAMProcessor.apply_image(np.ascontiguousarray(img)), device=anchor_pixels.device)
+                              .permute(2, 0, 1).contiguous() for img in image_array])
+        batch = 8
+        if frames.shape[0] % batch != 0:
+            msg = f"imagine360_b200: the SAM branch needs a multiple of {batch} frames, got {frames.shape[0]} (pipeline...dual.py:685)"
+            print(msg, file=sys.stderr, flush=True)
+            raise ValueError(msg)
+        embeds = []
+        for i in range(0, frames.shape[0], batch):
+            self.SAMpredictor.set_torch_image(frames[i:i + batch], tuple(frames[0].shape[:2]))
+            e = self.SAMpredictor.get_image_embedding()                       # [8, c, h, w]
+            embeds.append(e.flatten(2).transpose(1, 2))
+        return torch.cat(embeds, dim=0)
 
     @torch.no_grad()
     def __call__(self, prompt, num_inference_steps=50, guidance_scale_text=7.5, guidance_scale_adapter=7.5, negative_prompt=None,
                  eta=0.0, generator=None, output_type="tensor", return_dict=True, latents_dtype=BF16, video_batch=None,
                  use_outpaint=False, use_ip_plus_cross_attention=False, use_fps_condition=False, ip_plus_condition="image", **kwargs):
-        if not (use_outpaint and use_ip_plus_cross_attention and use_fps_condition and ip_plus_condition == "video"):
-            raise NotImplementedError("only the configuration of configs/prompt-dual.yaml is on the native path")
+        if not (use_outpaint and use_ip_plus_cross_attention and use_fps_condition and ip_plus_condition == "video") \
+                or latents_dtype != BF16:
+            msg = "imagine360_b200: only the configuration of configs/prompt-dual.yaml (outpaint + video IP adapter + fps, bf16) is on the native path"
+            print(msg, file=sys.stderr, flush=True)           # the caller swallows exceptions (inference_dual_p2e.py:596-597)
+            raise NotImplementedError(msg)
         device = self._execution_device
-        vb = video_batch
+        with ops.on_device(device):
+            # LoRA merges edit ``weight.data`` in place without bumping the tensor version (inference_dual_p2e.py:193):
+            # one content check per clip keeps the packed weights honest
+            refresh_packed_weights(self.mv_base_model)
+            if isinstance(self.vae, torch.nn.Module):
+                refresh_packed_weights(self.vae)
+            video = self._generate(prompt, num_inference_steps, guidance_scale_text, negative_prompt, latents_dtype, video_batch, device)
+        return AnimationPipelineOutput(videos=video) if return_dict else video
+
+    def _generate(self, prompt, num_inference_steps, guidance_scale_text, negative_prompt, latents_dtype, vb, device):
         pano_px, pano_mask = vb["pano_pixel_values"], vb["pano_mask"]
         pers_px, pers_masks = vb["pers_pixel_values"], vb["pers_masks"]
         cameras, f, m = vb["cameras"], vb["video_length"], pers_px.shape[2]
@@ -185,15 +301,16 @@ class AnimationPipeline:
         pers_masked, pers_masks_l = self.prepare_masked_latents_pers(f, pers_px_m, pers_masks.to(device))
         text_pano = self._encode_prompt([prompt], device, [negative_prompt]).to(latents_dtype)
         text_pers = self._encode_prompt([prompt] * m, device, [negative_prompt] * m).to(latents_dtype)
-        feats = self._sam_features(vb["anchor_pixels_values"].to(device)[0]).to(latents_dtype)[None]
-        feats_p = self._sam_features(vb["anchor_pixels_values_pers"].to(device)[0]).to(latents_dtype)[None]
+        anchor, anchor_pers = vb["anchor_pixels_values"].to(device), vb["anchor_pixels_values_pers"].to(device)
+        assert anchor.shape[0] == 1, "Batch size must be one"                                  # :672
+        feats = self._sam_features(anchor[0]).to(latents_dtype)[None]
+        feats_p = self._sam_features(anchor_pers[0]).to(latents_dtype)[None]
         cond = Conditioning(text_pano, text_pers, torch.cat([feats, feats]),
                             torch.cat([feats_p, feats_p]).unsqueeze(1).expand(-1, m, -1, -1, -1),
                             vb["relative_position"].to(device).reshape(f, 6), vb["pitchs"].to(device).reshape(f), vb["fps"])
         pano_latent, _ = self.denoise(pano_latent, pers_latent, pano_mask_l, pers_masks_l, pano_masked, pers_masked, cond, cameras,
                                       num_inference_steps, guidance_scale_text)
-        video = self.decode_video(pano_latent).cpu()
-        return AnimationPipelineOutput(videos=video) if return_dict else video
+        return self.decode_video(pano_latent).cpu()
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -34,6 +34,20 @@ def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_tensor_device(fn):
+    """Run ``fn`` with the device of its first CUDA tensor argument current (kernels launch on the current device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
+        for t in a:
+            if torch.is_tensor(t) and t.is_cuda:
+                with torch.cuda.device(t.device):
+                    return fn(*a, **k)
+        return fn(*a, **k)
+    return wrapped
+
+
 def _p(t):
     return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
 
@@ -135,6 +149,7 @@ def _cached_p2e(fov, theta, phis, ph, pw, H, W, device):
 # ------------------------------------------------------------------------------------------------------
 # kernels
 # ------------------------------------------------------------------------------------------------------
+@_on_tensor_device
 def frames_to_u8(x: torch.Tensor, back_norm: bool) -> torch.Tensor:
     """[n, 3, H, W] -> uint8 [n, H, W, 3] like ``((x + 1) * 127.5 | x * 255)`` followed by ``.astype(np.uint8)``."""
     n, c, H, W = x.shape
@@ -149,6 +164,7 @@ def frames_to_u8(x: torch.Tensor, back_norm: bool) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def video_to_frames_u8(videos: torch.Tensor, rescale: bool = False) -> torch.Tensor:
     """Output side: the uint8 conversion of ``save_videos_grid`` (animatediff/utils/util.py:55-72)
     on the GPU for a single video: videos [1, c=3, t, h, w] float32 in (0, 1) (or (-1, 1) with ``rescale``) ->
@@ -177,6 +193,7 @@ def save_videos_grid(videos: torch.Tensor, path: str, rescale=False, n_rows=6, f
     imageio.mimsave(path, frames, fps=fps)
 
 
+@_on_tensor_device
 def remap_cubic_wrap(src_u8: torch.Tensor, mapx: torch.Tensor, mapy: torch.Tensor, keep: torch.Tensor | None = None,
                      paired: bool = False, want_u8: bool = True, f32_mode: int = 0):
     """Batched ``cv2.remap(INTER_CUBIC, BORDER_WRAP)``: src uint8 [n, H, W, 3]; maps float32 [m, h, w].

@@ -24,16 +24,20 @@ BF16 = torch.bfloat16
 
 
 # ------------------------------------------------------------------------------------------------------
-# packed-weight cache: derived tensors (fused QKV, tap-major conv weights, GEGLU tiles) are rebuilt only when
-# the source parameters change (load_state_dict / LoRA merge bump Tensor._version or replace storage).
+# packed-weight cache: derived tensors (fused QKV, tap-major conv weights, GEGLU tiles) are rebuilt when the source
+# parameters change: load_state_dict / copy_ / in-place ops bump Tensor._version, .to() replaces storage; edits through
+# ``.data`` (the reference's LoRA merge) do neither and are caught by refresh_packed_weights() once per clip.
 # ------------------------------------------------------------------------------------------------------
 def _sig(params):
     return tuple((p.data_ptr(), p._version, p.dtype, p.device) for p in params if p is not None)
 
 
+_EPOCH = [0]   # bumped by invalidate_packed_weights(): every cached packing older than this is rebuilt
+
+
 def cached(mod: nn.Module, key: str, params, build):
     store = mod.__dict__.setdefault("_i360_cache", {})
-    sig = _sig(params)
+    sig = (_EPOCH[0],) + _sig(params)
     hit = store.get(key)
     if hit is None or hit[0] != sig:
         with torch.no_grad():
@@ -41,6 +45,45 @@ def cached(mod: nn.Module, key: str, params, build):
         store[key] = (sig, val)
         return val
     return hit[1]
+
+
+def invalidate_packed_weights(module: nn.Module | None = None) -> None:
+    """Drop every derived weight packing (fused QKV, tap-major conv, GEGLU tiles, adapter tokens).
+
+    ``Tensor._version`` -- the automatic invalidation key -- is bumped by ``load_state_dict`` / ``copy_`` / in-place ops
+    on the parameter, but NOT by edits through ``.data`` such as the reference's LoRA merge
+    (``curr_layer.weight.data += ...``, inference_dual_p2e.py:193).  Call this after such an edit, or rely on
+    :func:`refresh_packed_weights`, which ``AnimationPipeline.__call__`` runs once per clip."""
+    _EPOCH[0] += 1
+    if module is not None:
+        for m in module.modules():
+            m.__dict__.pop("_i360_cache", None)
+            if hasattr(m, "_adapter_cache"):
+                m._adapter_cache.clear()
+
+
+def refresh_packed_weights(module: nn.Module) -> bool:
+    """Content check of all parameters of ``module`` against the fingerprint taken at the previous call (per-tensor
+    L2 and L1 norms: two multi-tensor launches + two small D2H copies per dtype/device group).  Any difference -- in
+    particular a ``.data`` edit that left ``_version`` untouched -- invalidates the packed weights.  Returns True if
+    the packings were dropped."""
+    groups = {}
+    for p in module.parameters():
+        if p.numel() and p.is_floating_point():
+            groups.setdefault((p.dtype, p.device), []).append(p.detach())
+    prints = []
+    with torch.no_grad():
+        for key in sorted(groups, key=str):
+            ts = groups[key]
+            prints.append(torch.stack(torch._foreach_norm(ts)).double().cpu())
+            prints.append(torch.stack(torch._foreach_norm(ts, 1)).double().cpu())
+    fp = torch.cat(prints) if prints else torch.zeros(0, dtype=torch.float64)
+    old = module.__dict__.get("_i360_fingerprint")
+    module.__dict__["_i360_fingerprint"] = fp
+    if old is not None and (old.shape != fp.shape or not torch.equal(old, fp)):
+        invalidate_packed_weights(module)
+        return True
+    return False
 
 
 def _b(t):
@@ -277,6 +320,10 @@ class VanillaTemporalModule(nn.Module):
                  attention_block_types=("Temporal_Self", "Temporal_Self"), temporal_position_encoding=False,
                  temporal_position_encoding_max_len=24, temporal_attention_dim_div=1, zero_initialize=True, **_):
         super().__init__()
+        if not temporal_position_encoding:
+            # the reference then builds VersatileAttention without pos_encoder (motion_module.py:320-325); the native
+            # temporal path always adds the sinusoidal table, so refuse instead of silently diverging
+            raise NotImplementedError("temporal_position_encoding=False is not on the Imagine360 path (configs/prompt-dual.yaml:27)")
         self.temporal_transformer = TemporalTransformer3DModel(
             in_channels, num_attention_heads, in_channels // num_attention_heads // temporal_attention_dim_div,
             num_transformer_block, len(attention_block_types), temporal_position_encoding_max_len)
@@ -365,6 +412,10 @@ class UNet3DConditionModel(nn.Module):
                  use_adapter_temporal_projection=False, compress_video_features=False, **extra):
         super().__init__()
         self.config = SimpleNamespace(**{k: v for k, v in locals().items() if k not in ("self", "extra", "__class__")}, **extra)
+        if not use_inflated_groupnorm:
+            # nn.GroupNorm on the 5-D tensor takes its statistics over ALL frames (resnet.py:172-177); the native
+            # GroupNorm kernels are per image (InflatedGroupNorm, resnet.py:9-17), which is what prompt-dual.yaml:18 selects
+            raise NotImplementedError("use_inflated_groupnorm=False is not on the Imagine360 path (configs/prompt-dual.yaml:18)")
         mm_kwargs = dict(motion_module_kwargs or {})
         c0 = block_out_channels[0]
         time_dim = c0 * 4

@@ -227,6 +227,10 @@ class AutoencoderKL(nn.Module):
 
     @torch.no_grad()
     def encode(self, x, return_dict=True):
+        with ops.on_device(x.device):
+            return self._encode(x, return_dict)
+
+    def _encode(self, x, return_dict=True):
         """vae.py:565-573 / Encoder.forward :128-144.  (The pipeline passes the chunk length as the 2nd positional,
         which lands in ``return_dict`` -- any truthy value keeps the output object form; SURVEY.md trap 10.)"""
         e, g = self.encoder, self.groups
@@ -251,6 +255,10 @@ class AutoencoderKL(nn.Module):
 
     @torch.no_grad()
     def decode(self, z, return_dict=True):
+        with ops.on_device(z.device):
+            return self._decode(z, return_dict)
+
+    def _decode(self, z, return_dict=True):
         """vae.py:575-610 / Decoder.forward :208-224"""
         d, g = self.decoder, self.groups
         y = self._conv1x1(_to_nhwc(z), self.post_quant_conv)

@@ -26,11 +26,32 @@ def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def on_device(device):
+    """Context manager making ``device`` the current CUDA device (a no-op for CPU devices, so host-only code paths
+    and their tests run without a GPU)."""
+    import contextlib
+    device = torch.device(device)
+    return torch.cuda.device(device) if device.type == "cuda" else contextlib.nullcontext()
+
+
+def _chk_dev(t):
+    """Kernels are launched on the CURRENT device's current stream: a tensor living elsewhere would be an illegal
+    address (or a silent peer access).  The host mirror enters ``torch.cuda.device(tensor.device)`` at its entry
+    points (MultiViewBaseModel.forward, AnimationPipeline, AutoencoderKL); direct callers must do the same."""
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"imagine360_b200: tensor on {t.device} but the current CUDA device is "
+                           f"cuda:{torch.cuda.current_device()}; wrap the call in torch.cuda.device(tensor.device)")
+
+
 def _chk_bf16(*ts):
+    first = True
     for t in ts:
         if t is not None:
             if t.dtype != BF16 or not t.is_cuda:
                 raise TypeError(f"expected a CUDA bf16 tensor, got {t.dtype} on {t.device}")
+            if first:
+                _chk_dev(t)
+                first = False
 
 
 ACT_NONE, ACT_GEGLU, ACT_GELU, ACT_SILU = 0, 1, 2, 3
@@ -330,6 +351,7 @@ def avgpool_frames4(x: torch.Tensor) -> torch.Tensor:
 def grid_sample(img: torch.Tensor, grid: torch.Tensor, nearest: bool = False) -> torch.Tensor:
     """img [N, C, Hi, Wi] fp32, grid [N, Ho, Wo, 2] fp32 normalised (x, y), align_corners=True, zeros padding."""
     assert img.dtype == torch.float32 and grid.dtype == torch.float32 and img.is_cuda and grid.is_cuda
+    _chk_dev(img)
     img, grid = img.contiguous(), grid.contiguous()
     N, C, Hi, Wi = img.shape
     Ho, Wo = grid.shape[1:3]

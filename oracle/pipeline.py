@@ -31,19 +31,20 @@ def init_noise(pano_noise, cameras, pers_hw, dtype):
 
 
 def denoise_loop(sd, pano_latent, pers_latent, pano_mask, pers_masks, pano_masked, pers_masked, cond, cameras,
-                 num_steps, guidance=7.5, cfg=None, seed_python=None, mask_dtype=None, noise_fn=None):
+                 num_steps, guidance=7.5, cfg=None, seed_python=None, mask_dtype=None, noise_fn=None, grid_dtype=None,
+                 pe_dtype=None):
     """The `for t in timesteps` loop (:734-809).  ``cond`` holds the step-invariant conditioning:
     text_pano [2,77,D], text_pers [2m,77,D], feats_pano [2,f,4096,C], feats_pers [2,m,f,4096,C], fps (int),
     rel_pos [f,6], pitch [f].  Python's ``random`` supplies the 7 antipodal draws per step in the order
     enc0, enc1, enc2, mid, dec0, dec1, dec2; torch's global RNG supplies the two IP-token noise draws per step
-    (pano first), unless ``noise_fn(shape)`` is given."""
+    (pano first), unless ``noise_fn(shape)`` is given.  ``grid_dtype`` / ``pe_dtype``: see mvgen.warp_attn."""
     sched = DDIM()
     ts = sched.set_timesteps(num_steps)
     if seed_python is not None:
         random.seed(seed_python)
     m = pers_latent.shape[1]
     dtype = pano_latent.dtype
-    fps_pano = torch.tensor([cond["fps"]] * 2)
+    fps_pano = torch.tensor([cond["fps"]] * 2, device=pano_latent.device)
     fps_pers = fps_pano[:, None].repeat(1, m)
     rel_pos = cond["rel_pos"][None].repeat(2, 1, 1)
     pitch = cond["pitch"][None].repeat(2, 1)
@@ -57,9 +58,9 @@ def denoise_loop(sd, pano_latent, pers_latent, pano_mask, pers_masks, pano_maske
         n_pano = randn((2, ntok, dctx))
         n_pers = randn((2 * m, ntok, dctx))
         pred_pers, pred_pano = mv_forward(
-            sd, torch.cat([xin_pers] * 2), torch.cat([xin_pano] * 2), t.reshape(1), cond["text_pers"], cond["text_pano"],
+            sd, torch.cat([xin_pers] * 2), torch.cat([xin_pano] * 2), t.reshape(1).to(pano_latent.device), cond["text_pers"], cond["text_pano"],
             cameras, fps_pano, fps_pers, cond["feats_pano"], cond["feats_pers"], rel_pos, pitch, draws, n_pano, n_pers,
-            cfg=cfg, mask_dtype=mask_dtype)
+            cfg=cfg, mask_dtype=mask_dtype, grid_dtype=grid_dtype, pe_dtype=pe_dtype)
         pano_latent = sched.step(cfg_combine(pred_pano, guidance), int(t), pano_latent)
         pers_latent = sched.step(cfg_combine(pred_pers, guidance), int(t), pers_latent)
     return pano_latent, pers_latent
