@@ -78,8 +78,8 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 template <int HD, bool BIAS, bool MASKED>
 __device__ __forceinline__ void softmax_tile(uint32_t tS_mine, uint32_t tO_mine, const uint8_t* sB, uint8_t* sP,
                                              int row, int limit, float scale_log2, float& m_used, float& l_run,
-                                             int cbeg, bool first, uint64_t* s_empty, uint64_t* pv_done,
-                                             uint32_t pv_parity) {
+                                             int cbeg, bool have_acc, bool wait_prev, uint64_t* s_empty,
+                                             uint64_t* pv_done, uint32_t pv_parity) {
   const float LOG2E = 1.4426950408889634f;
   const uint32_t rsw = static_cast<uint32_t>(row & 7);
   uint32_t v[64];
@@ -90,9 +90,13 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS_mine, uint32_t tO_mine,
   mbar_arrive(s_empty);                            // S_j is in registers: the MMA warp may overwrite it
   float mx = -INFINITY;
   if (!BIAS && !MASKED) {
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // four independent chains (FMNMX3 latency)
 #pragma unroll
-    for (int e = 0; e < 64; e += 2) mx = fmax3(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-    mx *= scale_log2;                              // scale > 0: max commutes with the scaling
+    for (int e = 0; e < 64; e += 8) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) mx4[c] = fmax3(mx4[c], __uint_as_float(v[e + 2 * c]), __uint_as_float(v[e + 2 * c + 1]));
+    }
+    mx = fmax3(mx4[0], mx4[1], fmaxf(mx4[2], mx4[3])) * scale_log2;   // scale > 0: max commutes with the scaling
   } else {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -113,8 +117,8 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS_mine, uint32_t tO_mine,
   const bool need = m_new > m_used + 8.0f;         // also true for the first finite maximum (m_used = -inf)
   if (__any_sync(0xffffffffu, need)) {
     const float alpha = (m_new == m_used) ? 1.0f : fast_exp2(m_used - m_new);
-    if (!first) {
-      mbar_wait(pv_done, pv_parity);               // P_{j-1} V_{j-1} has landed in the accumulator
+    if (have_acc) {
+      mbar_wait(pv_done, pv_parity);               // every earlier P V (this head's included) has landed in the accumulator
       tc_fence_after();
       const float2 al2 = make_float2(alpha, alpha);
 #pragma unroll 1
@@ -154,7 +158,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS_mine, uint32_t tO_mine,
     pk[e >> 1] = pack_bf16x2(pe.x, pe.y);
   }
   l_run += sum2.x + sum2.y;
-  if (!first) mbar_wait(pv_done, pv_parity);       // the tensor core has finished reading P_{j-1} from smem
+  if (wait_prev) mbar_wait(pv_done, pv_parity);    // the tensor core has finished reading the previous P from smem
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     const int cc = cbeg + g * 8;
@@ -301,8 +305,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float m_used = -INFINITY, l_run = 0.f;
     const uint32_t tS_mine = tS + lane_sel + half * 64, tO_mine = tO + lane_sel + half * HD;
 
+    int jn = 0, jq = 0;                          // j % n1, j / n1 kept incrementally (a divide per tile costs ~45 issue slots)
     for (int j = 0; j < p.kv_tiles; ++j) {
-      const int kv_i1 = (j % p.kv.n1) * p.kv.box1, kv_i3 = (j / p.kv.n1) * p.kv.box3;
+      const int kv_i1 = jn * p.kv.box1, kv_i3 = jq * p.kv.box3;
+      if (++jn == p.kv.n1) { jn = 0; ++jq; }
       // columns [0, limit) of this tile hold real keys (tile = 128 tokens of one view, or box3 whole views)
       int limit;
       if (p.kv.box3 == 1) limit = (kv_i3 < p.kv.ext3) ? min(128, p.kv.d1 - kv_i1) : 0;
