@@ -65,6 +65,27 @@ class SphericalPE(nn.Module):
         self.register_buffer("freq_bands", base ** torch.linspace(0, n_freqs - 1, n_freqs))
 
 
+class BiasSlot:
+    """One WarpAttn call site of a CUDA-graphed step (host/pipeline.py::StepGraph).  A graph bakes pointers, while the
+    reference picks the normal or the antipodal mask per call and per step (random.random() < 0.4, utils.py:15-21): the
+    graph reads ``static`` and the chosen variant is copied into it before each replay (only when the choice changed)."""
+
+    def __init__(self):
+        self.antipodal = False          # variant requested while the slot is still being recorded (eager warm-up)
+        self.variants = {}              # {False / True: (bias_equi_q, bias_pers_q)} -- the geometry module's cached tensors
+        self.static = None              # (bias_equi_q, bias_pers_q) buffers the graph reads
+        self.current = None
+
+    def freeze(self):
+        self.static = tuple(torch.empty_like(t) for t in self.variants[False])
+
+    def select(self, antipodal: bool):
+        if self.current != antipodal:
+            for dst, src in zip(self.static, self.variants[antipodal]):
+                dst.copy_(src)
+            self.current = antipodal
+
+
 class WarpAttn(nn.Module):
     """src/modules/attn_perspano.py:10-99"""
 
@@ -84,7 +105,15 @@ class WarpAttn(nn.Module):
         _, ph, pw, _ = pers.shape
         _, eh, ew, _ = equi.shape
         hw, en = ph * pw, eh * ew
-        bias_e, bias_p = G.warp_biases(ph, pw, eh, ew, cameras, pers.device, antipodal)
+        if isinstance(antipodal, BiasSlot):
+            slot = antipodal
+            if slot.static is None:
+                slot.variants[slot.antipodal] = G.warp_biases(ph, pw, eh, ew, cameras, pers.device, slot.antipodal)
+                bias_e, bias_p = slot.variants[slot.antipodal]
+            else:
+                bias_e, bias_p = slot.static
+        else:
+            bias_e, bias_p = G.warp_biases(ph, pw, eh, ew, cameras, pers.device, antipodal)
         pe_p, pe_e = G.spherical_pe_tables(self.pe.freq_bands, ph, pw, eh, ew, cameras, pers.device)
         pt, et = Fw.tokens(pers), Fw.tokens(equi)
         g1, b1 = tr.norm1.weight, tr.norm1.bias
@@ -239,19 +268,21 @@ class MultiViewBaseModel(nn.Module):
         hit = self._adapter_cache.get("k")
         if hit is not None and hit[0] == key:
             return hit[1]
+        val = self._adapter_compute(feats_pano, feats_pers, rel_pos, pitch)
+        self._adapter_cache["k"] = (key, val, keyed)      # keyed: keeps the storages alive (see above)
+        return val
+
+    def _adapter_compute(self, feats_pano, feats_pers, rel_pos, pitch):
         b, m = feats_pers.shape[:2]
         ip_pano = ip_tokens_clean(self.pano_unet, feats_pano)
         # the reference feeds the SAME features to every view (pipeline...dual.py:716-717): run distinct clips once
-        fp = feats_pers.reshape(b * m, *feats_pers.shape[2:])
         if feats_pers.stride(1) == 0 or (m > 1 and torch.equal(feats_pers[:, 0], feats_pers[:, -1])
                                          and all(torch.equal(feats_pers[:, 0], feats_pers[:, v]) for v in range(1, m))):
             ip_pers = ip_tokens_clean(self.unet, feats_pers[:, 0].contiguous()).repeat_interleave(m, dim=0)
         else:
-            ip_pers = ip_tokens_clean(self.unet, fp)
+            ip_pers = ip_tokens_clean(self.unet, feats_pers.reshape(b * m, *feats_pers.shape[2:]))
         rp = relpos_tokens(self.pano_unet, rel_pos, pitch, ip_pano.shape[1]) if self.pano_unet.use_relative_postions == "WithAdapter" else None
-        val = (ip_pano.contiguous(), ip_pers.contiguous(), rp)
-        self._adapter_cache["k"] = (key, val, keyed)      # keyed: keeps the storages alive (see above)
-        return val
+        return ip_pano.contiguous(), ip_pers.contiguous(), rp
 
     @torch.no_grad()
     def forward(self, latents, pano_latent, timestep, prompt_embd, pano_prompt_embd, cameras, use_fps_condition,
@@ -268,7 +299,7 @@ class MultiViewBaseModel(nn.Module):
     def _forward(self, latents, pano_latent, timestep, prompt_embd, pano_prompt_embd, cameras, use_fps_condition,
                  use_ip_plus_cross_attention, fps_tensor_pano, fps_tensor_pers, reference_images_clip_feat_pano,
                  reference_images_clip_feat_pers, relative_position_tensor, pitchs_tensor, antipodal_draws=None,
-                 ip_noise=None):
+                 ip_noise=None, adapter_tokens=None):
         """One dual-branch denoise step (MVGenModel.py:59-481).  ``antipodal_draws`` / ``ip_noise`` let tests inject the
         outcomes of the reference's ``random.random() < 0.4`` (src/utils/utils.py:15) and ``torch.randn_like``
         (MVGenModel.py:12) draws; by default they are drawn here in the reference's order."""
@@ -287,8 +318,11 @@ class MultiViewBaseModel(nn.Module):
         x = Fw.conv_in(pu, latents.reshape(b * m, *latents.shape[2:]), False)
         y = Fw.conv_in(qu, pano_latent, True)
         # 1.2 IP tokens: clean tokens cached, fresh noise every step (pano first: MVGenModel.py:186-187)
-        ip_pano, ip_pers, rp = self._adapter(reference_images_clip_feat_pano, reference_images_clip_feat_pers,
-                                             relative_position_tensor, pitchs_tensor)
+        if adapter_tokens is not None:           # CUDA-graphed step: the clean tokens come from the adapter graph's buffers
+            ip_pano, ip_pers, rp = adapter_tokens
+        else:
+            ip_pano, ip_pers, rp = self._adapter(reference_images_clip_feat_pano, reference_images_clip_feat_pers,
+                                                 relative_position_tensor, pitchs_tensor)
         if ip_noise is None:
             ip_noise = (torch.randn_like(ip_pano), torch.randn_like(ip_pers))
         ip_pano = ops.axpby(ip_pano, ip_noise[0].to(BF16).contiguous(), 1.0, 0.1)

@@ -7,6 +7,7 @@ Same constructor and ``__call__`` signature / ``video_batch`` contract as the re
 """
 from __future__ import annotations
 
+import os
 import random
 import sys
 from dataclasses import dataclass
@@ -38,6 +39,137 @@ class Conditioning:
     rel_pos: torch.Tensor        # [F, 6]
     pitch: torch.Tensor          # [F]
     fps: int = 8
+
+
+class StepGraph:
+    """The dual-branch forward of a denoising step as two CUDA graphs: ``g_adapter`` (SAM features ->
+    clean IP tokens of both branches + relative-position tokens; replayed when the clip's conditioning changes) and
+    ``g_step`` (one ``MultiViewBaseModel._forward`` on static inputs; replayed every step).  A step is ~1 450 kernel
+    launches; replaying them removes the host's launch pace from the loop (at the 16x256x512 single-branch size the eager
+    step is host bound).  What varies per step enters through static device buffers: the latents (updated in place by the
+    fused CFG + DDIM kernel), the timestep, and the WarpAttn bias of each of the 7 call sites (``BiasSlot``), chosen by the
+    same ``random.random() < 0.4`` draws, in the same order, as the eager path; the IP-token noise is drawn inside the
+    graph from torch's CUDA generator (graph-safe philox), pano first, like ``MVGenModel.py:186-187``."""
+
+    def __init__(self, pipe, pano_latent, pers_latent, cond, cameras):
+        from .mvgen import BiasSlot
+        mv = pipe.mv_base_model
+        dev = pano_latent.device
+        _, m, _, f, ph, pw = pers_latent.shape
+        _, _, _, eh, ew = pano_latent.shape
+        self.m = m
+
+        def buf(*shape, dtype=BF16):
+            return torch.zeros(shape, dtype=dtype, device=dev)
+
+        self.lat_pano, self.lat_pers = buf(1, 4, f, eh, ew), buf(1, m, 4, f, ph, pw)
+        self.stat_pano, self.stat_pers = buf(1, 5, f, eh, ew), buf(1, m, 5, f, ph, pw)
+        self.text_pano, self.text_pers = buf(*cond.text_pano.shape), buf(*cond.text_pers.shape)
+        self.feats_pano = buf(*cond.feats_pano.shape)
+        self.feats_pers1 = buf(cond.feats_pers.shape[0], 1, *cond.feats_pers.shape[2:])
+        self.rel, self.pitch = buf(2, f, 6, dtype=torch.float32), buf(2, f, dtype=torch.float32)
+        self.fps_pano = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.fps_pers = torch.zeros(2, m, dtype=torch.int64, device=dev)
+        self.t = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.cams = dict(zip(("FoV", "theta", "phi"), (list(c[:m]) for c in G.camera_lists(
+            {k: (v.reshape(-1) if isinstance(v, torch.Tensor) else v) for k, v in cameras.items() if k in ("FoV", "theta", "phi")}))))
+        self.slots = [BiasSlot() for _ in range(7)]
+        self._src = {}                      # name -> (source tensor, version) last copied into the static buffers
+        self._adapter_dirty = True
+        self._load_cond(cond)
+        feats_pers = self.feats_pers1.expand(-1, m, -1, -1, -1)
+        ntok, dctx = mv.unet.num_tokens, cond.text_pano.shape[-1]
+        zero_noise = (buf(2, ntok, dctx), buf(2 * m, ntok, dctx))
+
+        def forward(draws, **kw):
+            xin_pano = torch.cat([self.lat_pano, self.stat_pano], dim=1)
+            xin_pers = torch.cat([self.lat_pers, self.stat_pers], dim=2)
+            return mv._forward(latents=torch.cat([xin_pers] * 2), pano_latent=torch.cat([xin_pano] * 2), timestep=self.t,
+                               prompt_embd=self.text_pers, pano_prompt_embd=self.text_pano, cameras=self.cams,
+                               use_fps_condition=True, use_ip_plus_cross_attention=True, fps_tensor_pano=self.fps_pano,
+                               fps_tensor_pers=self.fps_pers, reference_images_clip_feat_pano=self.feats_pano,
+                               reference_images_clip_feat_pers=feats_pers, relative_position_tensor=self.rel,
+                               pitchs_tensor=self.pitch, antipodal_draws=draws, **kw)
+
+        # eager warm-up, once per shape: fills every cache the capture relies on (weight packings, both bias variants of all
+        # 7 call sites, PE tables, kernel attributes); zero noise is injected so torch's RNG stream is left untouched
+        for anti in (False, True):
+            for s_ in self.slots:
+                s_.antipodal = anti
+            tokens = mv._adapter_compute(self.feats_pano, feats_pers, self.rel, self.pitch)
+            forward(list(self.slots), ip_noise=zero_noise, adapter_tokens=tokens)
+        for s_ in self.slots:
+            s_.freeze()
+        del tokens
+        torch.cuda.synchronize(dev)
+        torch.cuda.empty_cache()            # the eager warm-up's blocks go back before the graphs reserve their own pool
+        self.g_adapter, self.g_step = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_adapter):
+            self.tokens = mv._adapter_compute(self.feats_pano, feats_pers, self.rel, self.pitch)
+        with torch.cuda.graph(self.g_step):
+            self.pred_pers, self.pred_pano = forward(list(self.slots), adapter_tokens=self.tokens)
+
+    @staticmethod
+    def key_of(pipe, pano_latent, pers_latent, cond, cameras):
+        cams = G.camera_lists({k: (v.reshape(-1) if isinstance(v, torch.Tensor) else v) for k, v in cameras.items()
+                               if k in ("FoV", "theta", "phi")})
+        return (id(pipe.mv_base_model), str(pano_latent.device), tuple(pano_latent.shape), tuple(pers_latent.shape),
+                tuple(cond.text_pano.shape), tuple(cond.text_pers.shape), tuple(cond.feats_pano.shape), tuple(cond.feats_pers.shape),
+                tuple(c[:pers_latent.shape[1]] for c in cams))
+
+    @staticmethod
+    def _sig(t):
+        return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype)
+
+    def _copy_if_changed(self, name, dst, src):
+        last = self._src.get(name)
+        if last is None or last[1] != self._sig(src):
+            dst.copy_(src.to(dst.dtype) if src.dtype != dst.dtype else src)
+            self._src[name] = (src, self._sig(src))   # holding src pins its storage: (address, version) then means contents
+            return True
+        return False
+
+    def _load_cond(self, cond):
+        self._copy_if_changed("text_pano", self.text_pano, cond.text_pano)
+        self._copy_if_changed("text_pers", self.text_pers, cond.text_pers)
+        dirty = self._copy_if_changed("feats_pano", self.feats_pano, cond.feats_pano)
+        fp = cond.feats_pers
+        if fp.shape[1] > 1 and fp.stride(1) != 0:
+            raise NotImplementedError("per-view SAM features: the graphed step expects the reference's shared features "
+                                      "(pipeline...dual.py:716-717); set I360_CUDA_GRAPH=0")
+        dirty |= self._copy_if_changed("feats_pers", self.feats_pers1, fp[:, :1])
+        last = self._src.get("rel")
+        if last is None or last[1] != self._sig(cond.rel_pos) or self._src["pitch"][1] != self._sig(cond.pitch):
+            self.rel.copy_(cond.rel_pos.to(self.rel.device, torch.float32)[None].expand(2, -1, -1))
+            self.pitch.copy_(cond.pitch.to(self.rel.device, torch.float32)[None].expand(2, -1))
+            self._src["rel"], self._src["pitch"] = (cond.rel_pos, self._sig(cond.rel_pos)), (cond.pitch, self._sig(cond.pitch))
+            dirty = True
+        if self._src.get("fps") != cond.fps:
+            self.fps_pano.fill_(int(cond.fps))
+            self.fps_pers.fill_(int(cond.fps))
+            self._src["fps"] = cond.fps
+        self._adapter_dirty |= dirty
+
+    def load(self, cond, pano_latent, pers_latent, pano_mask, pers_masks, pano_masked, pers_masked):
+        self._load_cond(cond)
+        if self._adapter_dirty:
+            self.g_adapter.replay()
+            self._adapter_dirty = False
+        self.lat_pano.copy_(pano_latent)
+        self.lat_pers.copy_(pers_latent)
+        self.stat_pano[:, :1].copy_(pano_mask)
+        self.stat_pano[:, 1:].copy_(pano_masked)
+        self.stat_pers[:, :, :1].copy_(pers_masks)
+        self.stat_pers[:, :, 1:].copy_(pers_masked)
+
+    def step(self, t: int, draws, coeffs, guidance):
+        self.t.fill_(int(t))
+        for slot, d in zip(self.slots, draws):
+            slot.select(bool(d))
+        self.g_step.replay()
+        sa, sb, sap, sbp = coeffs
+        ops.cfg_ddim_step(self.lat_pano, self.pred_pano[0:1], self.pred_pano[1:2], guidance, sa, sb, sap, sbp, out=self.lat_pano)
+        ops.cfg_ddim_step(self.lat_pers, self.pred_pers[0:1], self.pred_pers[1:2], guidance, sa, sb, sap, sbp, out=self.lat_pers)
 
 
 class ResizeLongestSide:
@@ -181,6 +313,23 @@ class AnimationPipeline:
         dev = pano_latent.device
         m = pers_latent.shape[1]
         self.scheduler.set_timesteps(num_inference_steps, device=dev)
+        i0, i1 = step_range if step_range is not None else (0, num_inference_steps)
+        if inject is None and dev.type == "cuda" and os.environ.get("I360_CUDA_GRAPH", "1") != "0":
+            key = StepGraph.key_of(self, pano_latent, pers_latent, cond, cameras)
+            sg = self.__dict__.get("_step_graph")
+            if sg is None or sg[0] != key:
+                self.__dict__.pop("_step_graph", None)          # one graph (= one activation pool) alive at a time
+                del sg
+                sg = (key, StepGraph(self, pano_latent, pers_latent, cond, cameras))
+                self.__dict__["_step_graph"] = sg
+            sg = sg[1]
+            sg.load(cond, pano_latent, pers_latent, pano_mask, pers_masks, pano_masked, pers_masked)
+            for i, t in list(enumerate(self.scheduler.timesteps_host))[i0:i1]:
+                draws = [random.random() < 0.4 for _ in range(7)]           # utils.py:15, same order as the eager path
+                sg.step(t, draws, self.scheduler.coefficients(t), guidance_scale)
+                if on_step is not None:
+                    on_step(i, t)
+            return sg.lat_pano.clone(), sg.lat_pers.clone()
         # CFG-doubled per-clip tensors live on the Conditioning object: they are the same objects for every step (and
         # every denoise() call) of a clip, which is what lets the model's adapter cache recognise the clip
         derived = cond.__dict__.get("_derived")
@@ -195,7 +344,6 @@ class AnimationPipeline:
         static_pano = torch.cat([pano_mask.to(BF16), pano_masked.to(BF16)], dim=1)
         static_pers = torch.cat([pers_masks.to(BF16), pers_masked.to(BF16)], dim=2)
         pano_latent, pers_latent = pano_latent.to(BF16).contiguous(), pers_latent.to(BF16).contiguous()
-        i0, i1 = step_range if step_range is not None else (0, num_inference_steps)
         for i, t in list(enumerate(self.scheduler.timesteps_host))[i0:i1]:
             xin_pano = torch.cat([pano_latent, static_pano], dim=1)
             xin_pers = torch.cat([pers_latent, static_pers], dim=2)

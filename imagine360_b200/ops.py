@@ -326,11 +326,14 @@ def axpby(x: torch.Tensor, y: torch.Tensor | None, a: float, b: float) -> torch.
     return out
 
 
-def cfg_ddim_step(latent, pred_uncond, pred_cond, guidance: float, sa: float, sb: float, sap: float, sbp: float):
-    _chk_bf16(latent, pred_uncond, pred_cond)
+def cfg_ddim_step(latent, pred_uncond, pred_cond, guidance: float, sa: float, sb: float, sap: float, sbp: float, out=None):
+    """CFG combine + DDIM v-prediction update in one pass; ``out`` may alias ``latent`` (element-wise kernel)."""
+    _chk_bf16(latent, pred_uncond, pred_cond, out)
     assert latent.is_contiguous() and pred_uncond.is_contiguous() and pred_cond.is_contiguous()
     assert latent.shape == pred_uncond.shape == pred_cond.shape
-    out = torch.empty_like(latent)
+    if out is None:
+        out = torch.empty_like(latent)
+    assert out.shape == latent.shape and out.is_contiguous()
     check(lib().i360_cfg_ddim_step_bf16(_p(latent), _p(pred_uncond), _p(pred_cond), _p(out), c_float(guidance), c_float(sa),
                                         c_float(sb), c_float(sap), c_float(sbp), c_longlong(latent.numel()), _stream()),
           "i360_cfg_ddim_step_bf16")

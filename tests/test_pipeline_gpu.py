@@ -117,3 +117,48 @@ def test_denoise_loop_two_steps_vs_oracle():
     e1, e2 = rel_err(a, pl), rel_err(b, vl)
     print("denoise 2 steps rel err", e1, e2)
     assert e1 < 6e-2 and e2 < 6e-2
+
+
+def test_cuda_graph_step_equals_eager_step(monkeypatch):
+    """The graphed loop (StepGraph: adapter graph + step graph, bias slots, in-place DDIM) reproduces the eager loop
+    bit for bit: same kernels, same torch-RNG stream (IP noise, pano first), same Python ``random`` draws."""
+    import random
+    from imagine360_b200.host.config import SCHEDULER_KWARGS
+    from imagine360_b200.host.ddim import DDIMScheduler
+    from imagine360_b200.host.mvgen import MultiViewBaseModel
+    from imagine360_b200.host.pipeline import AnimationPipeline, Conditioning
+    g = load("mvgen.pt")
+    mv = MultiViewBaseModel(tiny_unet(), tiny_unet())
+    sd_n, _ = q(synth_state(g["shapes"], g["seed"]))
+    load_native(mv, sd_n)
+    f, m = 16, 2
+
+    def mk(shape, seed, scale=1.0):
+        return qt(synth_tensor(shape, seed) * scale)[0]
+
+    pano, pers = mk((1, 4, f, 32, 64), 20), mk((1, m, 4, f, 16, 16), 21)
+    pmask = torch.ones(1, 1, f, 32, 64).cuda()
+    pmask[..., 8:24, 16:48] = 0
+    vmask = torch.ones(1, m, 1, f, 16, 16).cuda()
+    pm, vm = mk((1, 4, f, 32, 64), 22, 0.18), mk((1, m, 4, f, 16, 16), 23, 0.18)
+    rel = torch.tensor([1.0, 1.0, 63.0, 63.0, 128.0, 256.0])[None].repeat(f, 1).cuda()
+    pitch = torch.linspace(-5, 5, f).cuda()
+    pipe = AnimationPipeline(None, None, None, mv.unet, mv.pano_unet, mv, DDIMScheduler(**SCHEDULER_KWARGS))
+
+    def run(clip_seed):
+        cond = Conditioning(mk((2, 5, 32), 24), mk((2 * m, 5, 32), 25), mk((2, f, 4096, 8), clip_seed),
+                            mk((2, 1, f, 4096, 8), clip_seed + 1).expand(-1, m, -1, -1, -1), rel, pitch, 8)
+        torch.manual_seed(5)
+        random.seed(6)
+        a, b = pipe.denoise(pano, pers, pmask, vmask, pm, vm, cond, g["cams"], 50, 7.5, step_range=(0, 2))
+        a, b = pipe.denoise(a, b, pmask, vmask, pm, vm, cond, g["cams"], 50, 7.5, step_range=(2, 4))     # resumes on the same graph
+        return a, b
+
+    monkeypatch.setenv("I360_CUDA_GRAPH", "0")
+    e1, e2 = run(26), run(36)
+    monkeypatch.setenv("I360_CUDA_GRAPH", "1")
+    g1, g2 = run(26), run(36)               # second clip: same graph, conditioning reloaded, adapter graph replayed
+    assert "_step_graph" in pipe.__dict__
+    for (ea, eb), (ga, gb) in ((e1, g1), (e2, g2)):
+        assert torch.equal(ea, ga) and torch.equal(eb, gb)
+    assert not torch.equal(e1[0], e2[0])
