@@ -155,6 +155,9 @@ def run_native(args, size, rank, world, device):
         ev[i][1].record()
     torch.cuda.synchronize()
     launches = (_lib.LAUNCHES - launches0) // max(1, args.steps)
+    sg = pipe.__dict__.get("_step_graph")
+    if sg is not None:                      # graphed step: the kernels are replayed by the graph, not issued through ctypes
+        launches += sg[1].kernels_per_replay
     clocks = sampler.stop()
     if world > 1:
         torch.distributed.barrier()
@@ -165,6 +168,8 @@ def run_native(args, size, rank, world, device):
     ms = float(t.item())
     # first step of a NEW clip in a warm process: the per-clip caches (adapter tokens of both branches) are rebuilt
     pipe.mv_base_model._adapter_cache.clear()
+    if pipe.__dict__.get("_step_graph") is not None:      # graphed loop: conditioning re-copied, adapter graph replayed
+        pipe.__dict__["_step_graph"][1]._src.clear()
     clip_first_ms = timed_once(args.warmup + args.steps)
     t = torch.tensor([clip_first_ms], device=device)
     if world > 1:
@@ -265,8 +270,18 @@ def run_native(args, size, rank, world, device):
         one_step(5)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+    res["cuda_graph"] = sg is not None
     if rank == 0:
-        res["roofline"], res["breakdown"] = kernel_roofline(pipe, inp, size, one_step)
+        prev = os.environ.get("I360_CUDA_GRAPH")
+        os.environ["I360_CUDA_GRAPH"] = "0"      # per-launch CUDA events need the eager launch sequence
+        try:
+            one_step(6)
+            res["roofline"], res["breakdown"] = kernel_roofline(pipe, inp, size, one_step)
+        finally:
+            if prev is None:
+                os.environ.pop("I360_CUDA_GRAPH", None)
+            else:
+                os.environ["I360_CUDA_GRAPH"] = prev
         res["pipe"] = pipe
     return res
 
@@ -427,20 +442,40 @@ def side_config_c2(pipe, device, steps=5):
         pred = unet_single_forward(unet, torch.cat([x] * 2), torch.tensor([ts[i % 25]], device=device), ctx, fps.to(torch.bfloat16))
         sa, sb, sap, sbp = sched.coefficients(ts[i % 25])
         lat = ops.cfg_ddim_step(lat, pred[0:1].contiguous(), pred[1:2].contiguous(), 7.5, sa, sb, sap, sbp)
-    for i in range(2):
-        one(i)
+    def timed(fn):
+        for i in range(2):
+            fn(i)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            fn(2 + i)
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / steps
+
+    ms_eager = timed(one)
+    # the same step as a CUDA graph (~700 launches of 10-40 us kernels: the eager loop is bound by the host's launch pace)
+    t_dev = torch.zeros(1, dtype=torch.int64, device=device)
+    graph = torch.cuda.CUDAGraph()
     torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for i in range(steps):
-        one(2 + i)
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / steps
+    with torch.cuda.graph(graph):
+        x = torch.cat([lat, static], dim=1)
+        pred_g = unet_single_forward(unet, torch.cat([x] * 2), t_dev, ctx, fps.to(torch.bfloat16))
+    lat_g = lat
+
+    def one_graphed(i):
+        t_dev.fill_(ts[i % 25])
+        graph.replay()
+        sa, sb, sap, sbp = sched.coefficients(ts[i % 25])
+        ops.cfg_ddim_step(lat_g, pred_g[0:1], pred_g[1:2], 7.5, sa, sb, sap, sbp, out=lat_g)
+
+    ms = timed(one_graphed)
     sched.set_timesteps(STEPS_PER_CLIP, device=device)
     return {"workload": "single-branch panorama UNet3DConditionModel.forward, 16x256x512, CFG 2, 25-step DDIM clip "
                         "(BASELINE.json configs[1]; the unet.py:632 graph, SURVEY.md 8(a) note on C2)",
-            "ms_per_step": ms, "steps": steps, "warmup": 2, "steps_per_clip": 25, "frames_per_s": 16 / (25 * ms * 1e-3),
+            "ms_per_step": ms, "ms_per_step_eager": ms_eager, "cuda_graph": True, "steps": steps, "warmup": 2,
+            "steps_per_clip": 25, "frames_per_s": 16 / (25 * ms * 1e-3),
             "step_tflops": C2_SINGLE_FLOPS / (ms * 1e-3) / 1e12, "outputs_finite": bool(torch.isfinite(lat.float()).all())}
 
 
@@ -720,7 +755,7 @@ def main():
            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                    "ms_per_step": r["ms_e2e"]},
            "roofline": r.get("roofline"), "step_tflops": (size["step_flops"] or 0) / (r["ms"] * 1e-3) / 1e12,
-           "host_ms_per_step": r["host_ms"],
+           "host_ms_per_step": r["host_ms"], "cuda_graph": r.get("cuda_graph"),
            "first_step_ms": {"process_cold": r["first_step_ms"], "new_clip_warm_process": r["clip_first_ms"],
                              "note": "process_cold builds weight packings, 14 mask/PE tables, TMA descriptors and the adapter "
                                      "tokens; new_clip rebuilds the per-clip adapter tokens only"}}

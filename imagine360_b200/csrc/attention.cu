@@ -173,16 +173,23 @@ __device__ __forceinline__ void tile_coords(const AttnOperand& op, int bi, int t
   c3 = (bi / op.A) * op.mul + (tile / op.n1) * op.box3;
 }
 
-template <int HD, bool BIAS>
+// G = heads handled by one CTA.  WarpAttn's dense bias tile (32 KB per 128 x 128 logits, the same for every head and batch
+// item) is what its kernel waits for: with one head per CTA every (head, batch item) re-streams the whole bias from L2
+// (13.4 GB per call at the first level against 0.4 GB of K + V).  With G = 2 the CTA keeps the bias tile in smem for two
+// heads -- Q_g, K_g, V_g flow through the same rings as "virtual tiles" i = j * G + g -- which halves that traffic; the
+// two extra accumulators fit because head_dim 32 leaves half of the 256 TMEM columns unused (S 128 + 4 x 32).
+template <int HD, bool BIAS, int G>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmB,
                  const AttnParams p) {
   using C = AttnCfg<HD>;
+  static_assert(G == 1 || G == 2, "heads per CTA");
+  static_assert(128 + G * 2 * HD <= C::kTmemCols, "accumulators of all heads must fit next to S");
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + C::kQBytes;             // 2 stages
+  uint8_t* sQ = smem;                        // G query tiles (one per head)
+  uint8_t* sK = sQ + G * C::kQBytes;         // 2 stages
   uint8_t* sV = sK + 2 * C::kKVBytes;        // 2 stages
   uint8_t* sP = sV + 2 * C::kKVBytes;
   uint8_t* sB = sP + C::kPBytes;             // bias tile (BIAS only)
@@ -201,7 +208,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, bi = blockIdx.z;
+  const int qt = blockIdx.x, head0 = blockIdx.y * G, bi = blockIdx.z;
+  const int n_virtual = p.kv_tiles * G;         // (kv tile, head) pairs, head fastest
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -220,33 +228,39 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;      // O_half h at tO + h * HD
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;      // O of (head g, column half h) at tO + (g * 2 + h) * HD
 
   int qc1, qc2, qc3;
   tile_coords(p.q, bi, qt, qc1, qc2, qc3);
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, C::kQBytes);
-      tma_load_4d(sQ, &tmQ, q_full, p.q.col0 + head * HD, qc1, qc2, qc3);
+      mbar_expect_tx(q_full, G * C::kQBytes);
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        tma_load_4d(sQ + g * C::kQBytes, &tmQ, q_full, p.q.col0 + (head0 + g) * HD, qc1, qc2, qc3);
       const int q_base = qt * 128;   // the bias arrives tile-padded: [q_tiles*128, kv_tiles*128]
       for (int j = 0; j < p.kv_tiles; ++j) {
-        const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
         int c1, c2, c3;
         tile_coords(p.kv, bi, j, c1, c2, c3);
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], C::kKVBytes);
-        tma_load_4d(sK + st * C::kKVBytes, &tmK, &k_full[st], p.kv.col0 + head * HD, c1, c2, c3);
-        if (BIAS) {
-          const int kv_base = j * 128;
-          mbar_wait(b_empty, (j & 1) ^ 1);
-          mbar_expect_tx(b_full, C::kBiasBytes);
-          tma_load_2d(sB, &tmB, b_full, kv_base, q_base);
-          tma_load_2d(sB + C::kBiasBytes / 2, &tmB, b_full, kv_base + 64, q_base);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int i = j * G + g;
+          const int st = i & 1; const uint32_t ph = (i >> 1) & 1;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_expect_tx(&k_full[st], C::kKVBytes);
+          tma_load_4d(sK + st * C::kKVBytes, &tmK, &k_full[st], p.kv.col0 + (head0 + g) * HD, c1, c2, c3);
+          if (BIAS && g == 0) {          // one bias tile serves the G heads of this kv tile
+            const int kv_base = j * 128;
+            mbar_wait(b_empty, (j & 1) ^ 1);
+            mbar_expect_tx(b_full, C::kBiasBytes);
+            tma_load_2d(sB, &tmB, b_full, kv_base, q_base);
+            tma_load_2d(sB + C::kBiasBytes / 2, &tmB, b_full, kv_base + 64, q_base);
+          }
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_expect_tx(&v_full[st], C::kKVBytes);
+          tma_load_4d(sV + st * C::kKVBytes, &tmV, &v_full[st], p.v_col0 + (head0 + g) * HD, c1, c2, c3);
         }
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], C::kKVBytes);
-        tma_load_4d(sV + st * C::kKVBytes, &tmV, &v_full[st], p.v_col0 + head * HD, c1, c2, c3);
       }
     }
   } else if (warp == 1) {
@@ -254,38 +268,41 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);   // B (=V) is MN-major
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      auto issue_s = [&](int j) {                   // S_j = Q K_j^T
-        const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+      auto issue_s = [&](int i) {                   // S_i = Q_g K_{j,g}^T for the virtual tile i = j * G + g
+        const int st = i & 1; const uint32_t ph = (i >> 1) & 1;
         mbar_wait(&k_full[st], ph);
         tc_fence_after();
         const uint32_t aK = smem_u32(sK + st * C::kKVBytes);
+        const uint32_t aQg = aQ + (i & (G - 1)) * C::kQBytes;
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks)
-          umma_bf16_ss(tS, make_smem_desc(aQ + ks * 32, C::kSBO, 16, C::kSwz),
+          umma_bf16_ss(tS, make_smem_desc(aQg + ks * 32, C::kSBO, 16, C::kSwz),
                        make_smem_desc(aK + ks * 32, C::kSBO, 16, C::kSwz), idesc_s, ks != 0);
         umma_commit(&k_empty[st]);
         umma_commit(s_full);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
-      for (int j = 0; j < p.kv_tiles; ++j) {
-        const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
-        if (j + 1 < p.kv_tiles) {                   // runs on the tensor core under the softmax of tile j
-          mbar_wait(s_empty, j & 1);
-          issue_s(j + 1);
+      for (int i = 0; i < n_virtual; ++i) {
+        const int st = i & 1; const uint32_t ph = (i >> 1) & 1;
+        const int g = i & (G - 1);
+        const bool have_acc = i >= G;               // kv tile j > 0: the head's accumulator holds earlier tiles
+        if (i + 1 < n_virtual) {                    // runs on the tensor core under the softmax of tile i
+          mbar_wait(s_empty, i & 1);
+          issue_s(i + 1);
         }
-        // ---- O_h += P_j[:, h*64 .. h*64+64) V_j[h*64 .. h*64+64, :] ----
+        // ---- O_{g,h} += P_i[:, h*64 .. h*64+64) V_i[h*64 .. h*64+64, :] ----
         mbar_wait(&v_full[st], ph);
         const uint32_t aV = smem_u32(sV + st * C::kKVBytes);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          mbar_wait(&p_full[h], j & 1);
+          mbar_wait(&p_full[h], i & 1);
           tc_fence_after();
 #pragma unroll
           for (int kk = h * 4; kk < h * 4 + 4; ++kk)
-            umma_bf16_ss(tO + h * HD, make_smem_desc(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 1024, 16, SWZ_128B),
+            umma_bf16_ss(tO + (g * 2 + h) * HD, make_smem_desc(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 1024, 16, SWZ_128B),
                          make_smem_desc(aV + kk * 16 * C::kRowBytes, C::kSBO, 16, C::kSwz), idesc_o,
-                         (j > 0) || (kk != h * 4));
+                         have_acc || (kk != h * 4));
           umma_commit(&pv_done[h]);
         }
         umma_commit(&v_empty[st]);
@@ -302,8 +319,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int q_tok = (qt % p.q.n1) * p.q.box1 + row % p.q.box1;
     const int q_view = (qt / p.q.n1) * p.q.box3 + row / p.q.box1;
     const bool q_valid = (q_tok < p.q.d1) && (q_view < p.q.ext3);
-    float m_used = -INFINITY, l_run = 0.f;
-    const uint32_t tS_mine = tS + lane_sel + half * 64, tO_mine = tO + lane_sel + half * HD;
+    float m_used[G], l_run[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { m_used[g] = -INFINITY; l_run[g] = 0.f; }
+    const uint32_t tS_mine = tS + lane_sel + half * 64;
 
     int jn = 0, jq = 0;                          // j % n1, j / n1 kept incrementally (a divide per tile costs ~45 issue slots)
     for (int j = 0; j < p.kv_tiles; ++j) {
@@ -313,55 +332,64 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       int limit;
       if (p.kv.box3 == 1) limit = (kv_i3 < p.kv.ext3) ? min(128, p.kv.d1 - kv_i1) : 0;
       else limit = min(128, (p.kv.ext3 - kv_i3) * p.kv.box1);
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      if (BIAS) mbar_wait(b_full, j & 1);
-      const uint32_t pvp = (j - 1) & 1;
-      if (limit >= 128) softmax_tile<HD, BIAS, false>(tS_mine, tO_mine, sB, sP, row, limit, p.scale_log2, m_used, l_run, half * 64, j == 0, s_empty, &pv_done[half], pvp);
-      else              softmax_tile<HD, BIAS, true>(tS_mine, tO_mine, sB, sP, row, limit, p.scale_log2, m_used, l_run, half * 64, j == 0, s_empty, &pv_done[half], pvp);
-      fence_proxy_async_smem();       // P visible to the tensor core (async proxy)
-      tc_fence_before();              // ... and the rescaled accumulator (tcgen05.st) ordered before the arrive
-      mbar_arrive(&p_full[half]);
-      if (BIAS) mbar_arrive(b_empty);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int i = j * G + g;
+        const uint32_t tO_mine = tO + lane_sel + (g * 2 + half) * HD;
+        mbar_wait(s_full, i & 1);
+        tc_fence_after();
+        if (BIAS && g == 0) mbar_wait(b_full, j & 1);
+        const uint32_t pvp = (i - 1) & 1;
+        if (limit >= 128) softmax_tile<HD, BIAS, false>(tS_mine, tO_mine, sB, sP, row, limit, p.scale_log2, m_used[g], l_run[g], half * 64, j > 0, i > 0, s_empty, &pv_done[half], pvp);
+        else              softmax_tile<HD, BIAS, true>(tS_mine, tO_mine, sB, sP, row, limit, p.scale_log2, m_used[g], l_run[g], half * 64, j > 0, i > 0, s_empty, &pv_done[half], pvp);
+        fence_proxy_async_smem();       // P visible to the tensor core (async proxy)
+        tc_fence_before();              // ... and the rescaled accumulator (tcgen05.st) ordered before the arrive
+        mbar_arrive(&p_full[half]);
+        if (BIAS && g == G - 1) mbar_arrive(b_empty);
+      }
     }
     // ---- epilogue: merge the two column halves of my row, write my half of the head-dim columns ----
-    const uint32_t lastp = (p.kv_tiles - 1) & 1;
+    const uint32_t lastp = (n_virtual - 1) & 1;
     mbar_wait(&pv_done[0], lastp);
     mbar_wait(&pv_done[1], lastp);
     tc_fence_after();
     float2* xml = reinterpret_cast<float2*>(sP);       // the P tile is dead after the last P.V MMA
-    xml[half * 128 + row] = make_float2(m_used, l_run);
+#pragma unroll
+    for (int g = 0; g < G; ++g) xml[(g * 2 + half) * 128 + row] = make_float2(m_used[g], l_run[g]);
     named_bar_sync(1, 256);
-    const float2 oth = xml[(half ^ 1) * 128 + row];
-    const float m_all = fmaxf(m_used, oth.x);
-    const float w_me = (m_used == -INFINITY) ? 0.f : fast_exp2(m_used - m_all);
-    const float w_ot = (oth.x == -INFINITY) ? 0.f : fast_exp2(oth.x - m_all);
-    const float inv = 1.0f / (l_run * w_me + oth.y * w_ot);
-    const float w_lo = (half == 0 ? w_me : w_ot) * inv, w_hi = (half == 0 ? w_ot : w_me) * inv;
-    bf16* dst = p.o + p.o_col0 + head * HD + half * HH + static_cast<long long>(q_tok) * p.os1 +
-                static_cast<long long>(qc2) * p.os2 +
-                static_cast<long long>((bi / p.q.A) * p.q.mul + q_view) * p.os3;
 #pragma unroll
-    for (int c = 0; c < HH; c += 16) {
-      uint32_t lo[16], hi[16];
-      tmem_ld_x16(tO + lane_sel + half * HH + c, lo);
-      tmem_ld_x16(tO + lane_sel + HD + half * HH + c, hi);
-      tmem_ld_wait();
-      if (q_valid) {
+    for (int g = 0; g < G; ++g) {
+      const float2 oth = xml[(g * 2 + (half ^ 1)) * 128 + row];
+      const float m_all = fmaxf(m_used[g], oth.x);
+      const float w_me = (m_used[g] == -INFINITY) ? 0.f : fast_exp2(m_used[g] - m_all);
+      const float w_ot = (oth.x == -INFINITY) ? 0.f : fast_exp2(oth.x - m_all);
+      const float inv = 1.0f / (l_run[g] * w_me + oth.y * w_ot);
+      const float w_lo = (half == 0 ? w_me : w_ot) * inv, w_hi = (half == 0 ? w_ot : w_me) * inv;
+      bf16* dst = p.o + p.o_col0 + (head0 + g) * HD + half * HH + static_cast<long long>(q_tok) * p.os1 +
+                  static_cast<long long>(qc2) * p.os2 +
+                  static_cast<long long>((bi / p.q.A) * p.q.mul + q_view) * p.os3;
 #pragma unroll
-        for (int g = 0; g < 16; g += 8) {
-          float o[8];
+      for (int c = 0; c < HH; c += 16) {
+        uint32_t lo[16], hi[16];
+        tmem_ld_x16(tO + lane_sel + (g * 2) * HD + half * HH + c, lo);
+        tmem_ld_x16(tO + lane_sel + (g * 2 + 1) * HD + half * HH + c, hi);
+        tmem_ld_wait();
+        if (q_valid) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(lo[g + e]) * w_lo + __uint_as_float(hi[g + e]) * w_hi;
-          if (p.accumulate) {
-            const uint4 old = *reinterpret_cast<const uint4*>(dst + c + g);
-            float prev[8];
-            unpack8(old, prev);
+          for (int e8 = 0; e8 < 16; e8 += 8) {
+            float o[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = prev[e] + __bfloat162float(__float2bfloat16(o[e]));
+            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(lo[e8 + e]) * w_lo + __uint_as_float(hi[e8 + e]) * w_hi;
+            if (p.accumulate) {
+              const uint4 old = *reinterpret_cast<const uint4*>(dst + c + e8);
+              float prev[8];
+              unpack8(old, prev);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = prev[e] + __bfloat162float(__float2bfloat16(o[e]));
+            }
+            *reinterpret_cast<uint4*>(dst + c + e8) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
           }
-          *reinterpret_cast<uint4*>(dst + c + g) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                              pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
         }
       }
     }
@@ -371,18 +399,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, C::kTmemCols); }
 }
 
-template <int HD, bool BIAS>
+template <int HD, bool BIAS, int G>
 static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const CUtensorMap& b,
                        const AttnParams& p, int heads, int batch, cudaStream_t st) {
   using C = AttnCfg<HD>;
-  const int smem = C::kQBytes + 4 * C::kKVBytes + C::kPBytes + (BIAS ? C::kBiasBytes : 0) + 256;   // barriers + TMEM slot
+  const int smem = G * C::kQBytes + 4 * C::kKVBytes + C::kPBytes + (BIAS ? C::kBiasBytes : 0) + 256;   // barriers + TMEM slot
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attention_kernel<HD, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(attention_kernel<HD, BIAS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return I360_ERR_CUDA;
     attr_set = true;
   }
-  attention_kernel<HD, BIAS><<<dim3(p.q_tiles, heads, batch), kAttnThreads, smem, st>>>(q, k, v, b, p);
+  attention_kernel<HD, BIAS, G><<<dim3(p.q_tiles, heads / G, batch), kAttnThreads, smem, st>>>(q, k, v, b, p);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -456,9 +484,11 @@ extern "C" int i360_attention_bf16(const I360TokenView* q, const I360TokenView* 
     uint64_t d[2] = {(uint64_t)bias_cols, (uint64_t)bias_rows}; uint64_t s[1] = {(uint64_t)bias_cols * 2};
     uint32_t b[2] = {64, 128};
     r = get_tmap_bf16(&tb, bias, 2, d, s, b, 3); if (r) return r;
-    if (head_dim == 64) return launch_attn<64, true>(tq, tk, tv, tb, p, heads, batch, st);
-    return launch_attn<32, true>(tq, tk, tv, tb, p, heads, batch, st);
+    if (head_dim == 64) return launch_attn<64, true, 1>(tq, tk, tv, tb, p, heads, batch, st);
+    static const bool pair = getenv("I360_WARP_HEADS_PER_CTA") == nullptr || atoi(getenv("I360_WARP_HEADS_PER_CTA")) != 1;
+    if (pair && (heads % 2) == 0) return launch_attn<32, true, 2>(tq, tk, tv, tb, p, heads, batch, st);   // WarpAttn
+    return launch_attn<32, true, 1>(tq, tk, tv, tb, p, heads, batch, st);
   }
-  if (head_dim == 64) return launch_attn<64, false>(tq, tk, tv, tb, p, heads, batch, st);
-  return launch_attn<32, false>(tq, tk, tv, tb, p, heads, batch, st);
+  if (head_dim == 64) return launch_attn<64, false, 1>(tq, tk, tv, tb, p, heads, batch, st);
+  return launch_attn<32, false, 1>(tq, tk, tv, tb, p, heads, batch, st);
 }

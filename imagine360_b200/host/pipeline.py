@@ -106,8 +106,11 @@ class StepGraph:
         self.g_adapter, self.g_step = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_adapter):
             self.tokens = mv._adapter_compute(self.feats_pano, feats_pers, self.rel, self.pitch)
+        from .. import _lib
+        n0 = _lib.LAUNCHES
         with torch.cuda.graph(self.g_step):
             self.pred_pers, self.pred_pano = forward(list(self.slots), adapter_tokens=self.tokens)
+        self.kernels_per_replay = _lib.LAUNCHES - n0        # C-ABI launches recorded into the step graph
 
     @staticmethod
     def key_of(pipe, pano_latent, pers_latent, cond, cameras):
