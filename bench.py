@@ -260,6 +260,10 @@ def run_native(args, size, rank, world, device):
         res["decode"] = {"error": repr(ex)}
     if rank == 0 and world == 1 and not args.no_comparator and size["step_flops"]:
         try:
+            # the comparator gets the GPU to itself: the native arm's step graph (and its activation pool) is dropped first
+            pipe.__dict__.pop("_step_graph", None)
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
             res["comparator"] = torch_cuda_comparator(pipe, inp, size)
         except Exception as ex:
             res["comparator"] = {"error": repr(ex)}

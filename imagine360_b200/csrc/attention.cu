@@ -98,20 +98,30 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS_mine, uint32_t tO_mine,
     }
     mx = fmax3(mx4[0], mx4[1], fmaxf(mx4[2], mx4[3])) * scale_log2;   // scale > 0: max commutes with the scaling
   } else {
+    // packed arithmetic (FMUL2 / FFMA2 on logit pairs, FMNMX3 on the pair): WarpAttn's kernel is bound by the issue
+    // slots of this loop -- head_dim 32 halves the tensor work per logit -- so every scalar op here costs step time
+    const float2 sc2 = make_float2(scale_log2, scale_log2), l2e = make_float2(LOG2E, LOG2E);
+    float mx2[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const int cc = cbeg + g * 8;
-      float bv[8];
-      if (BIAS) unpack8(*reinterpret_cast<const uint4*>(sB + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ rsw) << 4)), bv);
+      uint4 bb = make_uint4(0u, 0u, 0u, 0u);
+      if (BIAS) bb = *reinterpret_cast<const uint4*>(sB + (cc >> 6) * 16384 + row * 128 + ((((cc & 63) >> 3) ^ rsw) << 4));
+      const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float sv = __uint_as_float(v[g * 8 + e]) * scale_log2;
-        if (BIAS) sv = fmaf(bv[e], LOG2E, sv);
-        if (MASKED && (cc + e >= limit)) sv = -INFINITY;
-        v[g * 8 + e] = __float_as_uint(sv);       // keep the finished logit (log2 units)
-        mx = fmaxf(mx, sv);
+      for (int e = 0; e < 4; ++e) {
+        float2 sv = fmul2(make_float2(__uint_as_float(v[g * 8 + 2 * e]), __uint_as_float(v[g * 8 + 2 * e + 1])), sc2);
+        if (BIAS) sv = ffma2(unpack_bf16x2(bw[e]), l2e, sv);
+        if (MASKED) {
+          if (cc + 2 * e >= limit) sv.x = -INFINITY;
+          if (cc + 2 * e + 1 >= limit) sv.y = -INFINITY;
+        }
+        v[g * 8 + 2 * e] = __float_as_uint(sv.x);       // keep the finished logits (log2 units)
+        v[g * 8 + 2 * e + 1] = __float_as_uint(sv.y);
+        mx2[e & 1] = fmax3(mx2[e & 1], sv.x, sv.y);
       }
     }
+    mx = fmaxf(mx2[0], mx2[1]);
   }
   const float m_new = fmaxf(m_used, mx);
   const bool need = m_new > m_used + 8.0f;         // also true for the first finite maximum (m_used = -inf)
