@@ -47,6 +47,9 @@ struct AttnParams {
 #ifndef I360_POLY_MASK
 #define I360_POLY_MASK 0x22   // which of every 8 logit pairs evaluate 2^t on the FMA pipe instead of the MUFU (bit i = pair i)
 #endif
+#ifndef I360_POLY_MASK2
+#define I360_POLY_MASK2 0x22  // same, for attention2_kernel
+#endif
 constexpr int kAttnThreads = 320;   // warp0 TMA, warp1 MMA, warps 2..9 softmax (2 threads per query row)
 
 template <int HD>
@@ -425,6 +428,282 @@ static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtenso
   return I360_OK;
 }
 
+
+// ================================================================================================
+// attention2_kernel: head_dim 64, no bias, whole tiles (Nq % 256 == 0, Nk % 128 == 0) -- the spatial self-attention of
+// the 16x512x1024 step (pano 8192 / 2048 / 512 tokens, views of 1024 / 256).  Differences from attention_kernel:
+//   * ONE CTA per SM works on TWO 128-row query tiles against one K/V stream (each K/V tile is loaded once for 256
+//     query rows instead of once per 128), 576 threads: warp0 TMA, warp1 MMA, warps 2..17 = 2 tiles x 2 column halves
+//     x 4 lane quarters of softmax threads (two threads per query row, as before);
+//   * P never touches shared memory: a softmax thread overwrites the first 32 of ITS OWN 64 S columns in TMEM with
+//     its 64 bf16 probabilities (tcgen05.st) and P.V is issued with the A operand in TMEM (tcgen05.mma ".ts" form) --
+//     no 32 KB P tile, no st.shared + address arithmetic, no fence.proxy.async (a MEMBAR.ALL.CTA) per tile, and the P
+//     buffer cannot stall the next tile's softmax;
+//   * the two tiles ping-pong on the tensor pipe: the issue order is PV_0(j), S_0(j+1), PV_1(j), S_1(j+1); the pipe
+//     executes in order, so S_t(j+1) cannot overwrite P_t(j) before P_t(j).V has consumed it and no "S released"
+//     barrier is needed; while one tile's softmax runs, the other tile's two MMAs execute.
+// TMEM (all 512 columns): S_t / P_t at t*128, O_{t,h} at 256 + (t*2+h)*64.
+constexpr int kAttn2Threads = 576;
+constexpr int kAttn2Stages = 4;
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+         "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+         "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kAttn2Threads, 1)
+attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  constexpr int HD = 64;
+  using C = AttnCfg<HD>;
+  constexpr int NS = kAttn2Stages;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;                              // 2 query tiles
+  uint8_t* sK = sQ + 2 * C::kQBytes;               // NS stages
+  uint8_t* sV = sK + NS * C::kKVBytes;             // NS stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NS * C::kKVBytes);
+  uint64_t* q_full = bars;                         // 1
+  uint64_t* k_full = bars + 1;                     // NS
+  uint64_t* k_empty = k_full + NS;                 // NS
+  uint64_t* v_full = k_empty + NS;                 // NS
+  uint64_t* v_empty = v_full + NS;                 // NS
+  uint64_t* s_full = v_empty + NS;                 // [2 tiles]       MMA -> softmax: S_t(j) in TMEM
+  uint64_t* p_full = s_full + 2;                   // [2 tiles][2]    softmax -> MMA: P_{t,h}(j) in TMEM, O_{t,h} rescaled (128 arrivals)
+  uint64_t* pv_done = p_full + 4;                  // [2 tiles][2]    MMA -> softmax: O_{t,h} += P V retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 4);
+  float2* xml = reinterpret_cast<float2*>(tmem_slot + 2);      // [2 tiles][2 halves][128 rows] (m, l) exchange, 4 KB
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qp = blockIdx.x, head = blockIdx.y, bi = blockIdx.z;
+  const int T = p.kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < NS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int t = 0; t < 2; ++t) mbar_init(&s_full[t], 1);
+    for (int x = 0; x < 4; ++x) { mbar_init(&p_full[x], 128); mbar_init(&pv_done[x], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * C::kQBytes);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        int c1, c2, c3;
+        tile_coords(p.q, bi, 2 * qp + t, c1, c2, c3);
+        tma_load_4d(sQ + t * C::kQBytes, &tmQ, q_full, p.q.col0 + head * HD, c1, c2, c3);
+      }
+      int st = 0; uint32_t ph = 0;
+      for (int j = 0; j < T; ++j) {
+        int c1, c2, c3;
+        tile_coords(p.kv, bi, j, c1, c2, c3);
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], C::kKVBytes);
+        tma_load_4d(sK + st * C::kKVBytes, &tmK, &k_full[st], p.kv.col0 + head * HD, c1, c2, c3);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], C::kKVBytes);
+        tma_load_4d(sV + st * C::kKVBytes, &tmV, &v_full[st], p.v_col0 + head * HD, c1, c2, c3);
+        if (++st == NS) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);   // B (= V) is MN-major; A (= P) comes from TMEM
+      const uint32_t aQ = smem_u32(sQ);
+      auto issue_s = [&](int t, uint32_t aK) {           // S_t = Q_t K^T  -> TMEM columns t*128 ..
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_bf16_ss(tmem_base + t * 128, make_smem_desc(aQ + t * C::kQBytes + ks * 32, C::kSBO, 16, C::kSwz),
+                       make_smem_desc(aK + ks * 32, C::kSBO, 16, C::kSwz), idesc_s, ks != 0);
+        umma_commit(&s_full[t]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_s(0, smem_u32(sK));
+      issue_s(1, smem_u32(sK));
+      umma_commit(&k_empty[0]);
+      int st = 0; uint32_t ph = 0;                        // stage / phase of kv tile j
+      for (int j = 0; j < T; ++j) {
+        int stn = st + 1; uint32_t phn = ph;
+        if (stn == NS) { stn = 0; phn ^= 1; }
+        const bool more = j + 1 < T;
+        mbar_wait(&v_full[st], ph);
+        if (more) mbar_wait(&k_full[stn], phn);
+        const uint32_t aV = smem_u32(sV + st * C::kKVBytes);
+        const uint32_t aKn = smem_u32(sK + stn * C::kKVBytes);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {                   // O_{t,h} += P_{t,h}(j) V_j[h*64 .. h*64+64, :]
+            mbar_wait(&p_full[t * 2 + h], j & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_ts(tmem_base + 256 + (t * 2 + h) * HD, tmem_base + t * 128 + h * 64 + kk * 8,
+                           make_smem_desc(aV + (h * 4 + kk) * 16 * C::kRowBytes, C::kSBO, 16, C::kSwz), idesc_o,
+                           (j > 0) || (kk != 0));
+            umma_commit(&pv_done[t * 2 + h]);
+          }
+          if (more) issue_s(t, aKn);                      // in-order pipe: runs after P_t(j) has been consumed
+        }
+        umma_commit(&v_empty[st]);
+        if (more) umma_commit(&k_empty[stn]);
+        st = stn; ph = phn;
+      }
+    }
+  } else {
+    // ================================ softmax / epilogue ================================
+    const int idx = warp - 2;
+    const int t = idx >> 3;                        // query tile 0 / 1
+    const int half = (idx >> 2) & 1;               // key columns half*64 .. half*64+63 of every tile
+    const int ew = warp & 3;                       // TMEM lane quarter of this warp
+    const int row = ew * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
+    constexpr int HH = HD / 2;
+    const int qt = 2 * qp + t;
+    const int q_tok = (qt % p.q.n1) * p.q.box1 + row;
+    int qc1, qc2, qc3;
+    tile_coords(p.q, bi, qt, qc1, qc2, qc3);
+    const uint32_t tS_mine = tmem_base + lane_sel + t * 128 + half * 64;
+    const uint32_t tO_mine = tmem_base + lane_sel + 256 + (t * 2 + half) * HD;
+    uint64_t* my_p_full = &p_full[t * 2 + half];
+    uint64_t* my_pv_done = &pv_done[t * 2 + half];
+    float m_used = -INFINITY, l_run = 0.f;
+    const float scale_log2 = p.scale_log2;
+    const float2 sc2 = make_float2(scale_log2, scale_log2);
+
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t v[64];
+      tmem_ld_x32(tS_mine, v);
+      tmem_ld_x32(tS_mine + 32, v + 32);
+      tmem_ld_wait();
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int e = 0; e < 64; e += 8) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mx4[c] = fmax3(mx4[c], __uint_as_float(v[e + 2 * c]), __uint_as_float(v[e + 2 * c + 1]));
+      }
+      const float mx = fmax3(mx4[0], mx4[1], fmaxf(mx4[2], mx4[3])) * scale_log2;
+      const float m_new = fmaxf(m_used, mx);
+      const bool need = m_new > m_used + 8.0f;       // lazy rescale (see softmax_tile)
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = (m_new == m_used) ? 1.0f : fast_exp2(m_used - m_new);
+        if (j > 0) {
+          mbar_wait(my_pv_done, (j - 1) & 1);        // P(j-1) V(j-1) has landed in the accumulator
+          tc_fence_after();
+          const float2 al2 = make_float2(alpha, alpha);
+#pragma unroll 1
+          for (int c = 0; c < HD; c += 16) {
+            uint32_t o[16];
+            tmem_ld_x16(tO_mine + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              const float2 r = fmul2(make_float2(__uint_as_float(o[e]), __uint_as_float(o[e + 1])), al2);
+              o[e] = __float_as_uint(r.x); o[e + 1] = __float_as_uint(r.y);
+            }
+            tmem_st_x16(tO_mine + c, o);
+          }
+        }
+        l_run *= alpha;
+        m_used = m_new;
+      }
+      const float2 nm2 = make_float2(-m_used, -m_used);
+      float2 sum2 = make_float2(0.f, 0.f);
+      uint32_t pk[32];
+#pragma unroll
+      for (int e = 0; e < 64; e += 2) {
+        const float2 tt = ffma2(make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), sc2, nm2);
+        const bool poly = (I360_POLY_MASK2 >> ((e >> 1) & 7)) & 1;
+        const float2 pe = poly ? exp2_poly2(tt) : make_float2(fast_exp2(tt.x), fast_exp2(tt.y));
+        sum2 = fadd2(sum2, pe);
+        pk[e >> 1] = pack_bf16x2(pe.x, pe.y);
+      }
+      l_run += sum2.x + sum2.y;
+      tmem_st_x32(tS_mine, pk);                      // P over the first half of my own S columns
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(my_p_full);
+    }
+    // ---- epilogue: merge the two column halves of my row, write my half of the head-dim columns ----
+    const uint32_t lastp = (T - 1) & 1;
+    mbar_wait(&pv_done[t * 2], lastp);
+    mbar_wait(&pv_done[t * 2 + 1], lastp);
+    tc_fence_after();
+    xml[(t * 2 + half) * 128 + row] = make_float2(m_used, l_run);
+    named_bar_sync(1 + t, 256);
+    const float2 oth = xml[(t * 2 + (half ^ 1)) * 128 + row];
+    const float m_all = fmaxf(m_used, oth.x);
+    const float w_me = fast_exp2(m_used - m_all), w_ot = fast_exp2(oth.x - m_all);
+    const float inv = 1.0f / (l_run * w_me + oth.y * w_ot);
+    const float w_lo = (half == 0 ? w_me : w_ot) * inv, w_hi = (half == 0 ? w_ot : w_me) * inv;
+    bf16* dst = p.o + p.o_col0 + head * HD + half * HH + static_cast<long long>(q_tok) * p.os1 +
+                static_cast<long long>(qc2) * p.os2 + static_cast<long long>(qc3) * p.os3;
+    const uint32_t tO_t = tmem_base + lane_sel + 256 + (t * 2) * HD;
+#pragma unroll
+    for (int c = 0; c < HH; c += 16) {
+      uint32_t lo[16], hi[16];
+      tmem_ld_x16(tO_t + half * HH + c, lo);
+      tmem_ld_x16(tO_t + HD + half * HH + c, hi);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e8 = 0; e8 < 16; e8 += 8) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(lo[e8 + e]) * w_lo + __uint_as_float(hi[e8 + e]) * w_hi;
+        *reinterpret_cast<uint4*>(dst + c + e8) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                             pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+static int launch_attn2(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p, int heads,
+                        int batch, cudaStream_t st) {
+  using C = AttnCfg<64>;
+  const int smem = 2 * C::kQBytes + 2 * kAttn2Stages * C::kKVBytes + 512 + 4096;   // barriers + TMEM slot + (m, l) exchange
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return I360_ERR_CUDA;
+    attr_set = true;
+  }
+  attention2_kernel<<<dim3(p.q_tiles / 2, heads, batch), kAttn2Threads, smem, st>>>(q, k, v, p);
+  I360_CUDA_CHECK_LAUNCH();
+  return I360_OK;
+}
+
 }  // namespace i360
 
 using namespace i360;
@@ -499,6 +778,13 @@ extern "C" int i360_attention_bf16(const I360TokenView* q, const I360TokenView* 
     if (pair && (heads % 2) == 0) return launch_attn<32, true, 2>(tq, tk, tv, tb, p, heads, batch, st);   // WarpAttn
     return launch_attn<32, true, 1>(tq, tk, tv, tb, p, heads, batch, st);
   }
-  if (head_dim == 64) return launch_attn<64, false, 1>(tq, tk, tv, tb, p, heads, batch, st);
+  if (head_dim == 64) {
+    // whole-tile self-attention shapes: two query tiles per CTA, P kept in TMEM (attention2_kernel)
+    static const bool v2 = getenv("I360_ATTN_V2") == nullptr || atoi(getenv("I360_ATTN_V2")) != 0;
+    if (v2 && !accumulate && p.q.box3 == 1 && p.kv.box3 == 1 && p.q.ext3 == 1 && p.kv.ext3 == 1 && (p.q.d1 % 256) == 0 &&
+        (p.kv.d1 % 128) == 0)
+      return launch_attn2(tq, tk, tv, p, heads, batch, st);
+    return launch_attn<64, false, 1>(tq, tk, tv, tb, p, heads, batch, st);
+  }
   return launch_attn<32, false, 1>(tq, tk, tv, tb, p, heads, batch, st);
 }

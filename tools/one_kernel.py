@@ -38,6 +38,12 @@ if kind == "temporal":
     C = heads * hd
     qkv = torch.randn(B * Fr * D, 3 * C, device="cuda").bfloat16(); out = torch.empty(B * Fr * D, C, device="cuda", dtype=torch.bfloat16)
     fn = lambda: ops.temporal_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], out, B, Fr, D, heads, hd)
+if kind == "warp":
+    b, m, hw, EN, heads = a; hd = 32; C = heads * hd
+    pers_kv = torch.randn(b * m * hw, 2 * C, device="cuda").bfloat16(); equi = torch.randn(b * EN, C, device="cuda").bfloat16()
+    bias = torch.rand(EN, m * hw, device="cuda").bfloat16() * 2 - 1; out = torch.empty_like(equi)
+    fn = lambda: ops.attention(ops.seq_view(equi, b, EN), ops.multiview_view(pers_kv, 1, m, b, hw, 0), ops.multiview_view(pers_kv, 1, m, b, hw, C),
+                               ops.seq_view(out, b, EN), heads, hd, b, bias=bias)
 if kind == "ln":
     M, C = a
     x = torch.randn(M, C, device="cuda").bfloat16(); g = torch.ones(C, device="cuda").bfloat16(); b = torch.zeros(C, device="cuda").bfloat16()
