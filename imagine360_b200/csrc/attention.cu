@@ -439,10 +439,15 @@ static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtenso
 //     its 64 bf16 probabilities (tcgen05.st) and P.V is issued with the A operand in TMEM (tcgen05.mma ".ts" form) --
 //     no 32 KB P tile, no st.shared + address arithmetic, no fence.proxy.async (a MEMBAR.ALL.CTA) per tile, and the P
 //     buffer cannot stall the next tile's softmax;
-//   * the two tiles ping-pong on the tensor pipe: the issue order is PV_0(j), S_0(j+1), PV_1(j), S_1(j+1); the pipe
-//     executes in order, so S_t(j+1) cannot overwrite P_t(j) before P_t(j).V has consumed it and no "S released"
-//     barrier is needed; while one tile's softmax runs, the other tile's two MMAs execute.
+//   * (tile t, column half h) are FOUR independent pipelines S_x -> softmax -> P_x -> O_x += P_x V that share the tensor
+//     pipe round-robin: issue order PV_x(j), S_x(j+1) for x = 0..3; the pipe executes in order, so S_x(j+1) cannot
+//     overwrite P_x(j) before P_x(j).V has consumed it and no "S released" barrier is needed; while one pipeline waits
+//     for its two MMAs the other three are in their softmax (with only two pipelines -- whole tiles -- the softmax warps
+//     waited for S half of the time: profiles/r02_ncu_attention2_pano_l0_first.txt).
 // TMEM (all 512 columns): S_t / P_t at t*128, O_{t,h} at 256 + (t*2+h)*64.
+#ifndef I360_A2_DELAY_S
+#define I360_A2_DELAY_S 1
+#endif
 constexpr int kAttn2Threads = 576;
 constexpr int kAttn2Stages = 4;
 
@@ -467,6 +472,27 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
       : "memory");
 }
 
+#ifndef I360_A2_SPIN
+#define I360_A2_SPIN 0
+#endif
+// hand-offs on the critical path of attention2_kernel (softmax -> MMA -> softmax): optionally a pure test_wait spin
+// instead of the suspending try_wait (experiment knob)
+__device__ __forceinline__ void mbar_wait_fast(uint64_t* bar, uint32_t parity) {
+#if I360_A2_SPIN
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (++spins > I360_SPIN_LIMIT) __trap();
+  } while (!ok);
+#else
+  mbar_wait(bar, parity);
+#endif
+}
+
 __global__ void __launch_bounds__(kAttn2Threads, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -484,8 +510,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* k_empty = k_full + NS;                 // NS
   uint64_t* v_full = k_empty + NS;                 // NS
   uint64_t* v_empty = v_full + NS;                 // NS
-  uint64_t* s_full = v_empty + NS;                 // [2 tiles]       MMA -> softmax: S_t(j) in TMEM
-  uint64_t* p_full = s_full + 2;                   // [2 tiles][2]    softmax -> MMA: P_{t,h}(j) in TMEM, O_{t,h} rescaled (128 arrivals)
+  uint64_t* s_full = v_empty + NS;                 // [2 tiles][2]    MMA -> softmax: S_{t,h}(j) in TMEM
+  uint64_t* p_full = s_full + 4;                   // [2 tiles][2]    softmax -> MMA: P_{t,h}(j) in TMEM, O_{t,h} rescaled (128 arrivals)
   uint64_t* pv_done = p_full + 4;                  // [2 tiles][2]    MMA -> softmax: O_{t,h} += P V retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 4);
   float2* xml = reinterpret_cast<float2*>(tmem_slot + 2);      // [2 tiles][2 halves][128 rows] (m, l) exchange, 4 KB
@@ -498,8 +524,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < NS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    for (int t = 0; t < 2; ++t) mbar_init(&s_full[t], 1);
-    for (int x = 0; x < 4; ++x) { mbar_init(&p_full[x], 128); mbar_init(&pv_done[x], 1); }
+    for (int x = 0; x < 4; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 128); mbar_init(&pv_done[x], 1); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -532,21 +557,25 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);   // B (= V) is MN-major; A (= P) comes from TMEM
       const uint32_t aQ = smem_u32(sQ);
-      auto issue_s = [&](int t, uint32_t aK) {           // S_t = Q_t K^T  -> TMEM columns t*128 ..
+      // The two column halves of a tile are independent online softmaxes, so (tile t, half h) = x is a pipeline of its
+      // own: S_x = Q_t K[h*64 .. h*64+64)^T (N = 64) -> softmax -> P_x -> O_x += P_x V[h*64 .. ).  Four pipelines share
+      // the tensor pipe round-robin: while one waits for its two MMAs, the other three are in their softmax.
+      auto issue_s = [&](int x, uint32_t aK) {
+        const int t = x >> 1, h = x & 1;
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks)
-          umma_bf16_ss(tmem_base + t * 128, make_smem_desc(aQ + t * C::kQBytes + ks * 32, C::kSBO, 16, C::kSwz),
-                       make_smem_desc(aK + ks * 32, C::kSBO, 16, C::kSwz), idesc_s, ks != 0);
-        umma_commit(&s_full[t]);
+          umma_bf16_ss(tmem_base + t * 128 + h * 64, make_smem_desc(aQ + t * C::kQBytes + ks * 32, C::kSBO, 16, C::kSwz),
+                       make_smem_desc(aK + h * 64 * C::kRowBytes + ks * 32, C::kSBO, 16, C::kSwz), idesc_s, ks != 0);
+        umma_commit(&s_full[x]);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_s(0, smem_u32(sK));
-      issue_s(1, smem_u32(sK));
+#pragma unroll
+      for (int x = 0; x < 4; ++x) issue_s(x, smem_u32(sK));
       umma_commit(&k_empty[0]);
       int st = 0; uint32_t ph = 0;                        // stage / phase of kv tile j
       for (int j = 0; j < T; ++j) {
@@ -558,20 +587,27 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint32_t aV = smem_u32(sV + st * C::kKVBytes);
         const uint32_t aKn = smem_u32(sK + stn * C::kKVBytes);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
+        for (int x = 0; x < 4; ++x) {                     // O_x += P_x(j) V_j[h*64 .. h*64+64, :]
+          const int t = x >> 1, h = x & 1;
+          mbar_wait_fast(&p_full[x], j & 1);
+          tc_fence_after();
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {                   // O_{t,h} += P_{t,h}(j) V_j[h*64 .. h*64+64, :]
-            mbar_wait(&p_full[t * 2 + h], j & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_bf16_ts(tmem_base + 256 + (t * 2 + h) * HD, tmem_base + t * 128 + h * 64 + kk * 8,
-                           make_smem_desc(aV + (h * 4 + kk) * 16 * C::kRowBytes, C::kSBO, 16, C::kSwz), idesc_o,
-                           (j > 0) || (kk != 0));
-            umma_commit(&pv_done[t * 2 + h]);
-          }
-          if (more) issue_s(t, aKn);                      // in-order pipe: runs after P_t(j) has been consumed
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ts(tmem_base + 256 + x * HD, tmem_base + t * 128 + h * 64 + kk * 8,
+                         make_smem_desc(aV + (h * 4 + kk) * 16 * C::kRowBytes, C::kSBO, 16, C::kSwz), idesc_o,
+                         (j > 0) || (kk != 0));
+          umma_commit(&pv_done[x]);
+          // S_x(j+1) overwrites the TMEM columns P_x(j).V reads: issued back to back the pipe drains between the two
+          // (measured: ~700 idle clocks per pair).  One independent P.V is slotted in between.
+#if I360_A2_DELAY_S
+          if (more && x >= 1) issue_s(x - 1, aKn);
+#else
+          if (more) issue_s(x, aKn);                      // in-order pipe: runs after P_x(j) has been consumed
+#endif
         }
+#if I360_A2_DELAY_S
+        if (more) issue_s(3, aKn);
+#endif
         umma_commit(&v_empty[st]);
         if (more) umma_commit(&k_empty[stn]);
         st = stn; ph = phn;
@@ -599,7 +635,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const float2 sc2 = make_float2(scale_log2, scale_log2);
 
     for (int j = 0; j < T; ++j) {
-      mbar_wait(&s_full[t], j & 1);
+      mbar_wait_fast(&s_full[t * 2 + half], j & 1);
       tc_fence_after();
       uint32_t v[64];
       tmem_ld_x32(tS_mine, v);
@@ -779,8 +815,11 @@ extern "C" int i360_attention_bf16(const I360TokenView* q, const I360TokenView* 
     return launch_attn<32, true, 1>(tq, tk, tv, tb, p, heads, batch, st);
   }
   if (head_dim == 64) {
-    // whole-tile self-attention shapes: two query tiles per CTA, P kept in TMEM (attention2_kernel)
-    static const bool v2 = getenv("I360_ATTN_V2") == nullptr || atoi(getenv("I360_ATTN_V2")) != 0;
+    // whole-tile self-attention shapes: two query tiles per CTA, P kept in TMEM (attention2_kernel).  EXPERIMENT, off by
+    // default: correct (same test results as attention_kernel) and 28 % fewer instructions per tile, but slower on the
+    // B200 -- 3.89 / 4.41 ms (two / four pipelines) against 3.50 ms for the 32 x 8192-token panorama level: its softmax
+    // warps wait for S 50-66 % of the time (profiles/r02_ncu_attention2_*.txt).  I360_ATTN_V2=1 selects it.
+    static const bool v2 = getenv("I360_ATTN_V2") != nullptr && atoi(getenv("I360_ATTN_V2")) != 0;
     if (v2 && !accumulate && p.q.box3 == 1 && p.kv.box3 == 1 && p.q.ext3 == 1 && p.kv.ext3 == 1 && (p.q.d1 % 256) == 0 &&
         (p.kv.d1 % 128) == 0)
       return launch_attn2(tq, tk, tv, p, heads, batch, st);

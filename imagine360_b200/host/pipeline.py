@@ -380,6 +380,57 @@ class AnimationPipeline:
         video = self.decode_latents(G.pad_pano(pano_latent, 4))
         return G.unpad_pano(video, 4 * self.vae_scale_factor)
 
+    @torch.no_grad()
+    def decode_video_streamed(self, pano_latent, frames_per_call: int = 4, on_frames=None):
+        """Output side of the path: ``decode_video`` in chunks of ``frames_per_call`` frames with the
+        device -> host copies of chunk k (fp32 video for the reference's return value, uint8 NHWC frames for the mp4
+        writer) running on a copy stream UNDER the decode of chunk k+1, and finished uint8 chunks handed to
+        ``on_frames(first_frame, frames_u8[n, H, W, 3])`` on the host while the GPU keeps decoding (an encoder thread can
+        consume them).  -> (video fp32 [1, 3, f, H, W] in [0, 1], frames uint8 [f, H, W, 3]), both in pinned host memory;
+        values are those of ``decode_video(...).cpu()`` and of ``save_videos_grid``'s ``(x * 255).astype(uint8)``
+        (animatediff/utils/util.py:55-72) exactly."""
+        from .preprocess import frames_to_u8
+        dev = pano_latent.device
+        with ops.on_device(dev):
+            z = G.pad_pano(pano_latent, 4)
+            b, c, f, h, w = z.shape
+            if b != 1:
+                raise NotImplementedError("one clip per call (the reference is batch 1, pipeline...dual.py:598)")
+            zf = (z / 0.18215).permute(0, 2, 1, 3, 4).reshape(f, c, h, w).to(self.vae.dtype)
+            crop, sf = 4 * self.vae_scale_factor, self.vae_scale_factor
+            H, W = h * sf, w * sf - 2 * crop
+            video = torch.empty((1, 3, f, H, W), dtype=torch.float32).pin_memory()
+            frames = torch.empty((f, H, W, 3), dtype=torch.uint8).pin_memory()
+            main, side = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
+            pending = []
+
+            def drain(block_all):
+                while pending and (block_all or len(pending) > 1 or pending[0][2].query()):
+                    i0, n0, done = pending.pop(0)
+                    done.synchronize()
+                    if on_frames is not None:
+                        on_frames(i0, frames[i0:i0 + n0])
+
+            for i in range(0, f, frames_per_call):
+                n = min(frames_per_call, f - i)
+                out = self.vae.decode(zf[i:i + n]).sample
+                vid = (out / 2 + 0.5).clamp(0, 1).float()[..., crop:crop + W].contiguous()      # [n, 3, H, W]
+                u8 = frames_to_u8(vid, back_norm=False)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    frames[i:i + n].copy_(u8, non_blocking=True)
+                    video[0, :, i:i + n].copy_(vid.permute(1, 0, 2, 3), non_blocking=True)
+                    u8.record_stream(side)
+                    vid.record_stream(side)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                pending.append((i, n, done))
+                drain(False)
+            drain(True)
+        return video, frames
+
     # ------------------------------------------------------------------------------------------------
     def _encode_prompt(self, prompt, device, negative_prompt):
         """:227-299 through the caller-supplied CLIP tokenizer / text encoder -> cat([uncond, cond]) [2 * len(prompt), 77, D]."""
@@ -461,7 +512,9 @@ class AnimationPipeline:
                             vb["relative_position"].to(device).reshape(f, 6), vb["pitchs"].to(device).reshape(f), vb["fps"])
         pano_latent, _ = self.denoise(pano_latent, pers_latent, pano_mask_l, pers_masks_l, pano_masked, pers_masked, cond, cameras,
                                       num_inference_steps, guidance_scale_text)
-        return self.decode_video(pano_latent).cpu()
+        video, frames_u8 = self.decode_video_streamed(pano_latent)
+        video._i360_frames_u8 = frames_u8      # the drop-in save_videos_grid writes these instead of re-converting fp32
+        return video
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -184,7 +184,11 @@ def video_to_frames_u8(videos: torch.Tensor, rescale: bool = False) -> torch.Ten
 def save_videos_grid(videos: torch.Tensor, path: str, rescale=False, n_rows=6, fps=8, n_frames=None):
     """Reference signature; frames are converted on the GPU, one D2H copy of uint8 instead of float32, then imageio."""
     import os
-    frames = video_to_frames_u8(videos, rescale)
+    pre = getattr(videos, "_i360_frames_u8", None)       # AnimationPipeline output: frames already converted on the GPU
+    if pre is not None and not rescale and tuple(pre.shape) == (videos.shape[2], videos.shape[3], videos.shape[4], 3):
+        frames = pre
+    else:
+        frames = video_to_frames_u8(videos, rescale)
     if n_frames is not None:
         frames = frames[:n_frames]
     frames = list(frames.cpu().numpy())

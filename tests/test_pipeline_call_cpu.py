@@ -135,7 +135,7 @@ def test_call_accepts_the_scripts_kwargs_and_reaches_denoise(monkeypatch):
     monkeypatch.setattr(pipe, "prepare_masked_latents_pano", lambda f_, px, mask: (torch.zeros(1, 4, f, H // 8, W // 8), torch.zeros(1, 1, f, H // 8, W // 8)))
     monkeypatch.setattr(pipe, "prepare_masked_latents_pers", lambda f_, px, mask: (torch.zeros(1, m, 4, f, ps // 8, ps // 8), torch.zeros(1, m, 1, f, ps // 8, ps // 8)))
     monkeypatch.setattr(pipe, "denoise", fake_denoise)
-    monkeypatch.setattr(pipe, "decode_video", lambda lat: torch.zeros(1, 3, f, H, W))
+    monkeypatch.setattr(pipe, "decode_video_streamed", lambda lat: (torch.zeros(1, 3, f, H, W), torch.zeros(f, H, W, 3, dtype=torch.uint8)))
     g = torch.Generator().manual_seed(1)
     vb = {                                                        # inference_dual_p2e.py:548-564
         "videoid": "x.mp4", "fps": 8,
@@ -150,7 +150,7 @@ def test_call_accepts_the_scripts_kwargs_and_reaches_denoise(monkeypatch):
     out = pipe("a prompt", latents_dtype=BF, video_batch=vb, num_inference_steps=50, use_outpaint=True,
                generator=torch.Generator().manual_seed(0), use_ip_plus_cross_attention=True, ip_plus_condition="video",
                use_fps_condition=True, negative_prompt="bad").videos      # :584-595
-    assert out.shape == (1, 3, f, H, W)
+    assert out.shape == (1, 3, f, H, W) and out._i360_frames_u8.shape == (f, H, W, 3)
     assert seen["init_noise"] == (1, f, H // 8, W // 8, ps // 8, ps // 8)
     d = seen["denoise"]
     c = d["cond"]

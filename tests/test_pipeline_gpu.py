@@ -162,3 +162,24 @@ def test_cuda_graph_step_equals_eager_step(monkeypatch):
     for (ea, eb), (ga, gb) in ((e1, g1), (e2, g2)):
         assert torch.equal(ea, ga) and torch.equal(eb, gb)
     assert not torch.equal(e1[0], e2[0])
+
+
+def test_decode_video_streamed_equals_decode_video():
+    """Output side (SURVEY.md 8(f) row 3): chunked decode with the D2H copies of chunk k under the decode of chunk k+1;
+    fp32 video identical to decode_video(...).cpu(), uint8 frames identical to save_videos_grid's conversion, chunks
+    delivered to the host callback in order."""
+    import numpy as np
+    from imagine360_b200.host.pipeline import AnimationPipeline
+    from imagine360_b200.host.vae import AutoencoderKL
+    g = load("vae.pt")
+    vae = AutoencoderKL(**VAE_KW)
+    load_native(vae, q(synth_state(g["shapes"], g["seed"]))[0])
+    pipe = AnimationPipeline(vae, None, None, None, None, None, None)
+    lat = qt(synth_tensor((1, 4, 10, 8, 16), 77, 0.2))[0]
+    want = pipe.decode_video(lat).cpu()
+    seen = []
+    video, frames = pipe.decode_video_streamed(lat, frames_per_call=4, on_frames=lambda i, fr: seen.append((i, fr.clone())))
+    assert video.shape == want.shape == (1, 3, 10, 64, 128) and torch.equal(video, want)
+    ref_u8 = (want[0].permute(1, 2, 3, 0) * 255).numpy().astype(np.uint8)          # util.py:61-67 for one video
+    assert np.array_equal(frames.numpy(), ref_u8)
+    assert [i for i, _ in seen] == [0, 4, 8] and all(torch.equal(fr, frames[i:i + len(fr)]) for i, fr in seen)

@@ -22,9 +22,12 @@ def timeit(fn, iters=10, warm=3):
     return ts[len(ts) // 2]
 
 
-tag = f"v2={os.environ.get('I360_ATTN_V2', '1')} warpG={os.environ.get('I360_WARP_HEADS_PER_CTA', '2')}"
+tag = f"v2={os.environ.get('I360_ATTN_V2', '1')} lib={os.path.basename(os.environ.get('I360_LIB_PATH', 'default'))}"
 if "warp" not in sys.argv:
-    for imgs, N, heads in [(32, 8192, 5), (640, 1024, 5), (32, 2048, 10), (640, 256, 10), (32, 512, 20), (48, 18432, 5)]:
+    shapes = [(32, 8192, 5), (640, 1024, 5), (32, 2048, 10), (640, 256, 10), (32, 512, 20), (48, 18432, 5)]
+    if "quick" in sys.argv:
+        shapes = shapes[:2]
+    for imgs, N, heads in shapes:
         hd = 64
         C = heads * hd
         qkv = torch.randn(imgs * N, 3 * C, device="cuda").bfloat16()
