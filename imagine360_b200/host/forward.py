@@ -7,6 +7,9 @@ motion_module.py:166-181,:348,:427).
 """
 from __future__ import annotations
 
+import functools
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -17,6 +20,29 @@ from .unet3d import BF16, cached, conv_w, fused_w, geglu_w, lin_w, pad8
 # ------------------------------------------------------------------------------------------------------
 # layout glue for the 4/9-channel latents at the model boundary (tiny tensors; torch is plumbing here)
 # ------------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------------
+# NVTX ranges per block (SURVEY.md section 5: the reference has no tracing at all).  I360_NVTX=1 names every ResnetBlock3D /
+# Transformer3DModel / temporal module / WarpAttn / sampler of a step in nsys / ncu timelines; off = zero cost.
+# ------------------------------------------------------------------------------------------------------
+_NVTX = os.environ.get("I360_NVTX", "0") not in ("", "0")
+
+
+def traced(name):
+    def deco(fn):
+        if not _NVTX:
+            return fn
+
+        @functools.wraps(fn)
+        def wrapped(*a, **k):
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return wrapped
+    return deco
+
+
 def latents_to_nhwc(x, circular_pad: int = 0):
     """[b, c, f, h, w] -> [(b f), h, w(+2p), pad8(c)] bf16, optionally circularly padded on w (pad_pano)."""
     b, c, f, h, w = x.shape
@@ -80,6 +106,7 @@ def all_temb_projections(unet, silu_emb):
 # ------------------------------------------------------------------------------------------------------
 # ResnetBlock3D (resnet.py:221-254), optionally on the pano circular halo (MVGenModel.py:276-281)
 # ------------------------------------------------------------------------------------------------------
+@traced("resnet_block")
 def resnet_block(x, r, temb, frames: int, groups: int, skip=None, halo: int = 0):
     """x [N,H,W,C1] (+ skip [N,H,W,C2] = the torch.cat of the up path) -> [N,H,W,Cout].
     halo > 0: pad_pano(halo) -> block -> unpad_pano(halo): the GroupNorm statistics are taken over the padded tensor
@@ -97,6 +124,7 @@ def resnet_block(x, r, temb, frames: int, groups: int, skip=None, halo: int = 0)
     return ops.conv3x3(h, w2, bias=b2, resid=x, crop=halo, out_scale=1.0 / r.output_scale_factor)
 
 
+@traced("downsample")
 def downsample(x, d, circular: bool):
     """Downsample3D (resnet.py:132-140); circular: pad_pano(2) -> conv -> unpad_pano(1) (MVGenModel.py:305-314)."""
     n, h, w, c = x.shape
@@ -105,6 +133,7 @@ def downsample(x, d, circular: bool):
     return y.view(n, h // 2, w // 2, -1)
 
 
+@traced("upsample")
 def upsample(x, u, circular: bool):
     """Upsample3D (resnet.py:86-114); circular: pad_pano(1) -> x2 -> conv -> unpad_pano(2) (MVGenModel.py:449-456)."""
     wp, b = conv_w(u.conv)
@@ -126,6 +155,7 @@ class Context:
         self.n_ctx = text.shape[0]
 
 
+@traced("spatial_transformer")
 def spatial_transformer(x, t3d, ctx: Context, frames: int):
     n, h, w, c = x.shape
     heads, hd = t3d.heads, t3d.dim_head
@@ -171,6 +201,7 @@ def spatial_transformer(x, t3d, ctx: Context, frames: int):
     return ops.gemm(t, wo, bias=bo, resid=tokens(x)).view(n, h, w, c)
 
 
+@traced("feed_forward")
 def feed_forward(t, ff, norm):
     nrm = ops.layernorm(t, norm.weight, norm.bias, norm.eps)
     wg, bg = geglu_w(ff)
@@ -188,6 +219,7 @@ def _pe_table(att, frames, dtype_like):
     return cached(att, f"pe{frames}", [pe], lambda: pe[0, :frames].to(dtype_like).float().contiguous())
 
 
+@traced("temporal_module")
 def temporal_module(x, mm, frames: int):
     tt = mm.temporal_transformer
     n, h, w, c = x.shape
@@ -212,6 +244,7 @@ def temporal_module(x, mm, frames: int):
 # ------------------------------------------------------------------------------------------------------
 # conv_in / conv_out
 # ------------------------------------------------------------------------------------------------------
+@traced("conv_in")
 def conv_in(unet, latents, circular: bool):
     """[b, 9, f, h, w] -> [(b f), h, w, C0]; pano: pad_pano(1) -> conv -> unpad_pano(1) (MVGenModel.py:136-143)."""
     x = latents_to_nhwc(latents, 1 if circular else 0)
@@ -219,6 +252,7 @@ def conv_in(unet, latents, circular: bool):
     return ops.conv3x3(x, wp, bias=b, crop=1 if circular else 0)
 
 
+@traced("conv_out")
 def conv_out(unet, x, batch: int, circular: bool):
     """GroupNorm -> SiLU -> conv_out; pano: the norm runs BEFORE pad_pano(1) (MVGenModel.py:472-478)."""
     co = unet.conv_out.out_channels

@@ -96,6 +96,7 @@ class WarpAttn(nn.Module):
         self.pe = SphericalPE(dim // 4)
         self.dim = dim
 
+    @Fw.traced("WarpAttn")
     def forward_native(self, pers, equi, cameras, clips: int, views: int, frames: int, antipodal: bool):
         """pers [(clips*views*frames), ph, pw, C], equi [(clips*frames), eh, ew, C] (channels-last) -> same shapes."""
         tr = self.transformer
@@ -272,6 +273,7 @@ class MultiViewBaseModel(nn.Module):
         self._adapter_cache["k"] = (key, val, keyed)      # keyed: keeps the storages alive (see above)
         return val
 
+    @Fw.traced("adapter")
     def _adapter_compute(self, feats_pano, feats_pers, rel_pos, pitch):
         b, m = feats_pers.shape[:2]
         ip_pano = ip_tokens_clean(self.pano_unet, feats_pano)

@@ -203,8 +203,10 @@ def seq_view(t: torch.Tensor, n_seq: int, n_tok: int, col0: int = 0, share_div: 
     bi // share_div (share_div = frames when K/V are shared by all frames of a clip)."""
     assert t.dim() == 2 and t.stride(1) == 1
     ld = t.stride(0)
-    return TokenView(t.data_ptr(), t.shape[1], col0, n_tok, n_seq, 1, ld, ld * n_tok, ld * n_tok * n_seq, 0, share_div,
-                     0, 1)
+    v = TokenView(t.data_ptr(), t.shape[1], col0, n_tok, n_seq, 1, ld, ld * n_tok, ld * n_tok * n_seq, 0, share_div,
+                  0, 1)
+    v.src = ("seq", t, n_seq, n_tok, col0, share_div)       # python-side description (imagine360_b200.debug reads it)
+    return v
 
 
 def multiview_view(t: torch.Tensor, n_clip: int, n_view: int, n_frame: int, n_tok: int, col0: int = 0) -> TokenView:
@@ -212,8 +214,10 @@ def multiview_view(t: torch.Tensor, n_clip: int, n_view: int, n_frame: int, n_to
     the (view, token) axis of its frame (WarpAttn's '(b m) c f h w -> (b f) (m h w) c')."""
     assert t.dim() == 2 and t.stride(1) == 1
     ld = t.stride(0)
-    return TokenView(t.data_ptr(), t.shape[1], col0, n_tok, n_frame, n_clip * n_view, ld, ld * n_tok,
-                     ld * n_tok * n_frame, n_frame, 1, n_view, n_view)
+    v = TokenView(t.data_ptr(), t.shape[1], col0, n_tok, n_frame, n_clip * n_view, ld, ld * n_tok,
+                  ld * n_tok * n_frame, n_frame, 1, n_view, n_view)
+    v.src = ("multiview", t, n_clip, n_view, n_frame, n_tok, col0)
+    return v
 
 
 def _tile_rule(d1: int, ext3: int):
