@@ -97,8 +97,11 @@ def build_native(device, size):
     random_init_(mv.cpu() if False else mv)
     pipe = AnimationPipeline(None, None, None, pers, pano, mv, DDIMScheduler(**SCHEDULER_KWARGS))
     pipe.device = torch.device(device)
-    rank = int(os.environ.get("RANK", "0"))
-    inp = synthetic_inputs(frames=size["frames"], pano_hw=size["pano_hw"], views=size["views"], device=device, seed=996995 + rank)
+    from imagine360_b200.host.parallel import clips_for_rank, seeds_for_clip
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    clip = clips_for_rank(world, rank, world)[0]            # one clip per rank: clip i -> rank i mod world
+    inp = synthetic_inputs(frames=size["frames"], pano_hw=size["pano_hw"], views=size["views"], device=device,
+                           seed=seeds_for_clip(996995, clip))
     return pipe, inp
 
 
@@ -161,20 +164,13 @@ def run_native(args, size, rank, world, device):
     clocks = sampler.stop()
     if world > 1:
         torch.distributed.barrier()
-    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    t = torch.tensor([ms], device=device)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms = float(t.item())
+    from imagine360_b200.host.parallel import max_over_ranks
+    ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev) / args.steps, device)
     # first step of a NEW clip in a warm process: the per-clip caches (adapter tokens of both branches) are rebuilt
     pipe.mv_base_model._adapter_cache.clear()
     if pipe.__dict__.get("_step_graph") is not None:      # graphed loop: conditioning re-copied, adapter graph replayed
         pipe.__dict__["_step_graph"][1]._src.clear()
-    clip_first_ms = timed_once(args.warmup + args.steps)
-    t = torch.tensor([clip_first_ms], device=device)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    clip_first_ms = float(t.item())
+    clip_first_ms = max_over_ranks(timed_once(args.warmup + args.steps), device)
 
     # ---- e2e: same step through the public API with HOST buffers (pinned) -> H2D, step, D2H inside the timed region
     host = {}
@@ -240,10 +236,7 @@ def run_native(args, size, rank, world, device):
     torch.cuda.current_stream().wait_stream(copy_stream)      # the last D2H belongs to the timed region
     e.record()
     torch.cuda.synchronize()
-    t2 = torch.tensor([s.elapsed_time(e) / args.steps], device=device)
-    if world > 1:
-        torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
-    ms_e2e = float(t2.item())
+    ms_e2e = max_over_ranks(s.elapsed_time(e) / args.steps, device)
 
     res = dict(ms=ms, ms_e2e=ms_e2e, launches=launches, clocks=clocks, h2d=h2d, d2h=d2h, first_step_ms=first_step_ms,
                clip_first_ms=clip_first_ms, host_ms=host_s * 1e3 / args.steps)
@@ -251,10 +244,7 @@ def run_native(args, size, rank, world, device):
     # the D2H copy of the finished clip; timed on every rank, max over ranks
     try:
         dec = decode_stage(pipe, lat[0], device)
-        t3 = torch.tensor([dec["ms_per_clip"]], device=device)
-        if world > 1:
-            torch.distributed.all_reduce(t3, op=torch.distributed.ReduceOp.MAX)
-        dec["ms_per_clip"] = float(t3.item())
+        dec["ms_per_clip"] = max_over_ranks(dec["ms_per_clip"], device)
         res["decode"] = dec
     except Exception as ex:   # keep the headline line
         res["decode"] = {"error": repr(ex)}
@@ -293,20 +283,18 @@ def run_native(args, size, rank, world, device):
 def decode_stage(pipe, pano_latent, device, reps=2):
     """decode_video + uint8 conversion + D2H of one finished clip (pipeline...dual.py:811-815, util.py:55-72)."""
     from imagine360_b200.host.config import FULL_VAE_KWARGS
-    from imagine360_b200.host.preprocess import video_to_frames_u8
     from imagine360_b200.host.vae import AutoencoderKL
     if pipe.vae is None:
         torch.manual_seed(1)
         with torch.device(device):
             pipe.vae = AutoencoderKL(**FULL_VAE_KWARGS).to(torch.bfloat16)
     b, c, f, h, w = pano_latent.shape
-    out_host = torch.empty((f, h * 8, w * 8, 3), dtype=torch.uint8).pin_memory()
 
     def run():
-        video = pipe.decode_video(pano_latent)              # fp32 [1, 3, f, H, W] on the device
-        out_host.copy_(video_to_frames_u8(video), non_blocking=True)
+        # the product's output path: chunked decode, fp32 video + uint8 frames copied D2H under the next chunk's decode
+        return pipe.decode_video_streamed(pano_latent)
 
-    run()
+    video, frames = run()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
@@ -314,8 +302,10 @@ def decode_stage(pipe, pano_latent, device, reps=2):
         run()
     e.record()
     torch.cuda.synchronize()
-    return {"ms_per_clip": s.elapsed_time(e) / reps, "frames": f, "d2h_bytes_per_clip": out_host.numel(),
-            "stages": "pad_pano(4) -> AutoencoderKL.decode (4 frames per launch set) -> crop 32 px -> uint8 NHWC -> pinned host"}
+    return {"ms_per_clip": s.elapsed_time(e) / reps, "frames": f,
+            "d2h_bytes_per_clip": video.numel() * 4 + frames.numel(),
+            "stages": "pad_pano(4) -> AutoencoderKL.decode (4 frames per launch set) -> crop 32 px -> fp32 video + uint8 NHWC "
+                      "frames -> pinned host (copies overlapped with the next chunk's decode)"}
 
 
 def torch_cuda_comparator(pipe, inp, size, steps=3, warmup=1):
