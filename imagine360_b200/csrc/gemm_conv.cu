@@ -49,6 +49,10 @@ struct GemmConvParams {
   int act;            // 0 none, 1 GEGLU (tile = [values | gates]), 2 GELU(erf), 3 SiLU
   float out_scale;
   int n_out;          // logical output columns (GEGLU: N/2)
+  int rowvec_mod;     // > 0: rowvec row = (row / rowvec_div) % rowvec_mod  (temporal PE: frame of a (b, f, d) row)
+  // LayerNorm folded into the GEMM (LNF kernels): D = rstd_r * (A W'^T - mean_r * u) + c, W' = W * gamma (per column
+  // of K), u[n] = sum_k W'[n,k], c[n] = sum_k beta[k] W[n,k] + bias[n]; row statistics are taken from the A tiles in smem
+  const float* ln_u; const float* ln_c; float ln_eps;
 };
 
 constexpr int BM = 128;
@@ -58,7 +62,7 @@ constexpr int kThreads = 320;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue (tw
 // MT: M sub-tiles per CTA tile (1 or 2).  MT = 2 (GEMM mode, BN = 128 only) computes a 256 x 128 tile as two 128-row
 // accumulators that share the weight tile in smem: 683 instead of 569 FLOP per byte loaded from L2 for the N = 640 /
 // 1920 projections, which are bound by L2 -> SM traffic at the tensor-core pace; epilogue group g owns accumulator g.
-template <int BN, bool RING = false, int MT = 1> struct Cfg {
+template <int BN, bool RING = false, int MT = 1, bool LNF = false> struct Cfg {
   static constexpr int kABytes = MT * BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -74,11 +78,13 @@ template <int BN, bool RING = false, int MT = 1> struct Cfg {
   // table in smem -- one copy per epilogue group, filled one tile ahead through registers -- instead of every
   // thread re-loading and unpacking the same bf16 values for every chunk.
   static constexpr bool kBiasTable = BN >= 160;
-  static constexpr int kTableBytes = kBiasTable ? 2 * BN * 4 : 0;       // [group][BN]
+  static_assert(!LNF || kBiasTable, "the LayerNorm-folding epilogue reads c and u from the smem tables");
+  static constexpr int kTableBytes = kBiasTable ? (LNF ? 4 : 2) * BN * 4 : 0;       // [group][BN] bias (LNF: c), then [group][BN] u
+  static constexpr int kStatBytes = LNF ? 2 * MT * BM * 8 : 0;                        // [acc stage][row] (rstd, -mean * rstd)
   // dynamic smem is declared __align__(1024) (checked at run time), so no alignment slack is reserved
-  static constexpr int kBudget = 227 * 1024 - kNumStg * kStgBytes - kTableBytes - 256;
+  static constexpr int kBudget = 227 * 1024 - kNumStg * kStgBytes - kTableBytes - kStatBytes - 256;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kNumStg * kStgBytes + kTableBytes + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNumStg * kStgBytes + kTableBytes + kStatBytes + 256 /*barriers*/;
   static constexpr int kAccCols = MT * BN;        // TMEM columns of one accumulator stage
   static constexpr int kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128
                                    : (2 * kAccCols <= 256) ? 256 : 512;
@@ -94,27 +100,35 @@ enum : int { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_RESID = 2, EPI_ROWVEC = 3, EPI_AC
 // Ring or not is a compile-time property, so the ring kernels carry no (predicated-off) direct-read instructions.
 template <int BN, int EPI> struct UseRing { static constexpr bool value = (EPI == EPI_RESID) && (BN <= 192); };
 
-template <int BN, int EPI, int MT = 1>
-__global__ void __launch_bounds__(kThreads, 1)
+// LNF: LayerNorm folded into the GEMM.  Four extra warps (10..13) read every A tile from smem next to the tensor core
+// (row sums and sums of squares; a row of the token matrix is exactly the K extent), publish (rstd, -mean * rstd) per
+// row and accumulator stage, and the epilogue applies  rstd * acc - mean * rstd * u[n] + c[n].  The normalised
+// activations are never written to or read from HBM: the LayerNorm pass (one read + one write of the token matrix per
+// norm, 192 launches and ~13 ms of the 16x512x1024 step) disappears.
+template <int BN, int EPI, int MT = 1, bool LNF = false>
+__global__ void __launch_bounds__(kThreads + (LNF ? 128 : 0), 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                  const GemmConvParams p) {
   constexpr bool kRing = UseRing<BN, EPI>::value;
-  using C = Cfg<BN, kRing, MT>;
+  using C = Cfg<BN, kRing, MT, LNF>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if ((base & 1023u) != 0) __trap();            // 128B-swizzled TMA / UMMA tiles need 1024-byte aligned stages
   uint8_t* smem = smem_raw;
   uint8_t* stg = smem + C::kStages * C::kStageBytes;            // 2 staging buffers (1024-aligned)
   float* sbias = reinterpret_cast<float*>(stg + C::kNumStg * C::kStgBytes);   // [2 groups][BN] (kBiasTable only)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + C::kNumStg * C::kStgBytes + C::kTableBytes);
+  float* su = sbias + 2 * BN;                                                  // [2 groups][BN] (LNF only)
+  float2* sstat = reinterpret_cast<float2*>(stg + C::kNumStg * C::kStgBytes + C::kTableBytes);   // [2][MT * BM] (LNF only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + C::kNumStg * C::kStgBytes + C::kTableBytes + C::kStatBytes);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + C::kStages;         // [kStages]
   uint64_t* tfull = bars + 2 * C::kStages;     // [2]
   uint64_t* tempty = bars + 2 * C::kStages + 2;// [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
   uint64_t* rbar = bars + 2 * C::kStages + 5;   // [2 groups][4]: residual chunk landed in staging buffer
+  uint64_t* sfull = rbar + 8;                   // [2] (LNF): row statistics of the tile in accumulator stage s published
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -123,8 +137,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmD);
     if (p.C2 > 0) tma_prefetch_desc(&tmA2);
     if (p.C3 > 0) tma_prefetch_desc(&tmA3);
-    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], LNF ? 5 : 1); }   // LNF: MMA + 4 stats warps
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); if (LNF) mbar_init(&sfull[s], 4); }
     if (kRing) { for (int s = 0; s < 8; ++s) mbar_init(&rbar[s], 1); tma_prefetch_desc(&tmR); }
     fence_barrier_init();
   }
@@ -201,6 +215,48 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
+  } else if (LNF && warp >= 10) {
+    // =============================== row statistics (warps 10..13, LNF) ===============================
+    // thread r owns row r (and r + 128 for MT = 2) of every A tile: 8 x 16-byte reads per k block in swizzle order
+    // (lane l of a quarter-warp reads chunk i ^ (r & 7): conflict-free), fp32 sum and sum of squares over the K extent.
+    const int r = (warp - 10) * 32 + lane;
+    const float inv_k = 1.0f / static_cast<float>(p.K);
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      float2 acc[MT][2];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) { acc[m][0] = make_float2(0.f, 0.f); acc[m][1] = make_float2(0.f, 0.f); }
+      for (int kb = 0; kb < p.k_iters; ++kb) {
+        mbar_wait(&full[stage], phase);
+        const uint8_t* sa = smem + stage * C::kStageBytes;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const uint8_t* rowp = sa + (m * BM + r) * (BK * 2);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 x = *reinterpret_cast<const uint4*>(rowp + ((static_cast<uint32_t>(i) ^ (r & 7)) << 4));
+            const float2 a = unpack_bf16x2(x.x), b = unpack_bf16x2(x.y), c = unpack_bf16x2(x.z), d = unpack_bf16x2(x.w);
+            acc[m][0] = fadd2(acc[m][0], fadd2(fadd2(a, b), fadd2(c, d)));
+            acc[m][1] = ffma2(a, a, ffma2(b, b, ffma2(c, c, ffma2(d, d, acc[m][1]))));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);      // this warp is done with the stage (the MMA commit is the 5th arrival)
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+      mbar_wait(&tempty[as], aphase ^ 1);               // the epilogue that read this statistics slot two tiles ago is done
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const float mean = (acc[m][0].x + acc[m][0].y) * inv_k;
+        const float var = fmaxf((acc[m][1].x + acc[m][1].y) * inv_k - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.ln_eps);
+        sstat[as * (MT * BM) + m * BM + r] = make_float2(rstd, -mean * rstd);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sfull[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
   } else {
     // =============================== epilogue (warps 2..9) ===============================
     // TMEM -> registers -> (bias / temb / activation / residual) -> bf16 -> swizzled smem -> TMA tensor store.
@@ -254,14 +310,22 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool has_bias = p.bias != nullptr;
     const int gtid = (warp & 3) * 32 + lane;             // thread index inside the epilogue group
     float nb0 = 0.f, nb1 = 0.f;                          // bias of columns gtid, gtid + 128 of the NEXT tile
+    float nu0 = 0.f, nu1 = 0.f;                          // LNF: u of the same columns
     auto load_bias = [&](int tt) {
       if (tt < total_tiles) {
         const int c0 = (tt % p.n_tiles) * BN + gtid;
-        nb0 = (has_bias && c0 < p.N) ? __bfloat162float(p.bias[c0]) : 0.f;
-        nb1 = (has_bias && gtid + 128 < BN && c0 + 128 < p.N) ? __bfloat162float(p.bias[c0 + 128]) : 0.f;
+        if (LNF) {
+          nb0 = (c0 < p.N) ? p.ln_c[c0] : 0.f;
+          nu0 = (c0 < p.N) ? p.ln_u[c0] : 0.f;
+          nb1 = (gtid + 128 < BN && c0 + 128 < p.N) ? p.ln_c[c0 + 128] : 0.f;
+          nu1 = (gtid + 128 < BN && c0 + 128 < p.N) ? p.ln_u[c0 + 128] : 0.f;
+        } else {
+          nb0 = (has_bias && c0 < p.N) ? __bfloat162float(p.bias[c0]) : 0.f;
+          nb1 = (has_bias && gtid + 128 < BN && c0 + 128 < p.N) ? __bfloat162float(p.bias[c0 + 128]) : 0.f;
+        }
       }
     };
-    if (C::kBiasTable && (has_bias || kGeglu)) load_bias(blockIdx.x);
+    if (C::kBiasTable && (has_bias || kGeglu || LNF)) load_bias(blockIdx.x);
     int as = 0; uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
@@ -282,13 +346,14 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         valid = r < p.M; orow = r; vec_idx = r;
       }
       if (!valid) { orow = 0; vec_idx = 0; }
-      const float* rv = (kRowvec && p.rowvec != nullptr)
-                            ? p.rowvec + static_cast<long long>(vec_idx / p.rowvec_div) * p.rowvec_ld : nullptr;
+      const int rv_row = p.rowvec_mod > 0 ? (vec_idx / p.rowvec_div) % p.rowvec_mod : vec_idx / p.rowvec_div;
+      const float* rv = (kRowvec && p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(rv_row) * p.rowvec_ld : nullptr;
       const bf16* rrow = (kResid && !ring_on && p.resid != nullptr && valid) ? p.resid + orow * p.ldr : nullptr;
       bf16* drow = p.D + orow * p.ldd;
 
       const float* tbias = sbias + grp * BN;
-      if (C::kBiasTable && (has_bias || kGeglu)) {
+      const float* tu = su + grp * BN;
+      if (C::kBiasTable && (has_bias || kGeglu || LNF)) {
         // this tile's values were fetched into registers during the previous tile.  Every thread of the group has
         // finished reading the previous tile's table once it passed that tile's last chunk barrier; the cropped
         // direct-store mode has no chunk barriers, hence the extra one.
@@ -296,11 +361,22 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float* tw = sbias + grp * BN;
         tw[gtid] = nb0;
         if (gtid + 128 < BN) tw[gtid + 128] = nb1;
+        if (LNF) {
+          float* uw = su + grp * BN;
+          uw[gtid] = nu0;
+          if (gtid + 128 < BN) uw[gtid + 128] = nu1;
+        }
         named_bar_sync(1 + grp, 128);
         load_bias(t + gridDim.x);                      // lands under this tile's chunks
       }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
+      float2 rstd2 = make_float2(1.f, 1.f), nmr2 = make_float2(0.f, 0.f);     // LNF: rstd and -mean * rstd of my row
+      if (LNF) {
+        mbar_wait(&sfull[as], aphase);
+        const float2 st = sstat[as * (MT * BM) + row_off + row];
+        rstd2 = make_float2(st.x, st.x); nmr2 = make_float2(st.y, st.y);
+      }
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * C::kAccCols + (MT == 2 ? grp * BN : 0);
       constexpr int n_chunks = kGeglu ? (BN / 2) / CH : BN / CH;
       const int oc0 = kGeglu ? n_blk * (BN / 2) : n_blk * BN;     // first OUTPUT column of this tile
@@ -342,10 +418,22 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { ba[j] = make_float2(0.f, 0.f); bg[j] = make_float2(0.f, 0.f); }
               }
+              if (LNF) {       // rstd * acc - mean * rstd * u + c for the value and the gate column
+                const float4 p0 = *reinterpret_cast<const float4*>(tu + ci * CH + g * 8);
+                const float4 p1 = *reinterpret_cast<const float4*>(tu + ci * CH + g * 8 + 4);
+                const float4 q0 = *reinterpret_cast<const float4*>(tu + BN / 2 + ci * CH + g * 8);
+                const float4 q1 = *reinterpret_cast<const float4*>(tu + BN / 2 + ci * CH + g * 8 + 4);
+                ba[0] = ffma2(make_float2(p0.x, p0.y), nmr2, ba[0]); ba[1] = ffma2(make_float2(p0.z, p0.w), nmr2, ba[1]);
+                ba[2] = ffma2(make_float2(p1.x, p1.y), nmr2, ba[2]); ba[3] = ffma2(make_float2(p1.z, p1.w), nmr2, ba[3]);
+                bg[0] = ffma2(make_float2(q0.x, q0.y), nmr2, bg[0]); bg[1] = ffma2(make_float2(q0.z, q0.w), nmr2, bg[1]);
+                bg[2] = ffma2(make_float2(q1.x, q1.y), nmr2, bg[2]); bg[3] = ffma2(make_float2(q1.z, q1.w), nmr2, bg[3]);
+              }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float2 val = fadd2(make_float2(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])), ba[j]);
-                const float2 gate = fadd2(make_float2(__uint_as_float(vg[g * 8 + 2 * j]), __uint_as_float(vg[g * 8 + 2 * j + 1])), bg[j]);
+                const float2 av = make_float2(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1]));
+                const float2 ag = make_float2(__uint_as_float(vg[g * 8 + 2 * j]), __uint_as_float(vg[g * 8 + 2 * j + 1]));
+                const float2 val = LNF ? ffma2(av, rstd2, ba[j]) : fadd2(av, ba[j]);
+                const float2 gate = LNF ? ffma2(ag, rstd2, bg[j]) : fadd2(ag, bg[j]);
                 f2[g * 4 + j] = fmul2(val, gelu_erf2(gate));
               }
             }
@@ -353,7 +441,15 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) f2[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-            if (has_bias) {
+            if (LNF) {                       // rstd * acc + (-mean * rstd) * u + c
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 b4 = *reinterpret_cast<const float4*>(tbias + ci * CH + q * 4);
+                const float4 u4 = *reinterpret_cast<const float4*>(tu + ci * CH + q * 4);
+                f2[2 * q] = ffma2(f2[2 * q], rstd2, ffma2(make_float2(u4.x, u4.y), nmr2, make_float2(b4.x, b4.y)));
+                f2[2 * q + 1] = ffma2(f2[2 * q + 1], rstd2, ffma2(make_float2(u4.z, u4.w), nmr2, make_float2(b4.z, b4.w)));
+              }
+            } else if (has_bias) {
               if (C::kBiasTable) {           // fp32 table in smem (zero past N): broadcast LDS.128, packed adds
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -465,14 +561,14 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-template <int BN, int EPI, int MT = 1>
+template <int BN, int EPI, int MT = 1, bool LNF = false>
 static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3,
                   const CUtensorMap& w, const CUtensorMap& d, const CUtensorMap& rmap, const GemmConvParams& p,
                   cudaStream_t st) {
-  using C = Cfg<BN, UseRing<BN, EPI>::value, MT>;
+  using C = Cfg<BN, UseRing<BN, EPI>::value, MT, LNF>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_conv_kernel<BN, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_conv_kernel<BN, EPI, MT, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              C::kSmemBytes) != cudaSuccess)
       return I360_ERR_CUDA;
     attr_set = true;
@@ -480,7 +576,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms()) grid = num_sms();
   if (grid <= 0) return I360_OK;
-  gemm_conv_kernel<BN, EPI, MT><<<grid, kThreads, C::kSmemBytes, st>>>(a, a2, a3, w, d, rmap, p);
+  gemm_conv_kernel<BN, EPI, MT, LNF><<<grid, kThreads + (LNF ? 128 : 0), C::kSmemBytes, st>>>(a, a2, a3, w, d, rmap, p);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -682,4 +778,64 @@ extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, co
     if (resid) { r = get_tmap_bf16(&tr, resid, 4, d, s, b, 2); if (r) return r; }
   }
   return dispatch(bn, ta, ta2, ta3, tw, td, tr, p, static_cast<cudaStream_t>(stream));
+}
+
+
+// LayerNorm folded into the projection that consumes it:  D = act( LN(A; gamma, beta, eps) W^T + bias (+ rowvec) ).
+// Wf: [N, K] = W * gamma (bf16);  u[n] = sum_k Wf[n,k] (fp32, from the bf16-rounded Wf);  c[n] = sum_k beta[k] W[n,k] + bias[n]
+// (fp32).  K must be the LayerNorm width (the whole row), a multiple of 64.  act: 0 none, 1 GEGLU (Wf / u / c packed with
+// i360_gemm_geglu_block like the un-folded weight).  rowvec (fp32 [rowvec_mod or M/div, N]) is added per row at
+// (row / rowvec_div) % rowvec_mod -- the temporal module's PE term (LN(x) + pe_f) W^T = LN(x) W^T + (pe W^T)[f].
+// Replaces nn.LayerNorm followed by nn.Linear (animatediff/models/attention.py:463-508, motion_module.py:247-259,:350).
+extern "C" int i360_gemm_ln_bf16(const void* A, long long lda, const void* Wf, long long ldw, void* D, long long ldd, int M,
+                                 int N, int K, const float* u, const float* c, float eps, const float* rowvec,
+                                 int rowvec_div, int rowvec_mod, int rowvec_ld, int act, void* stream) {
+  if (!A || !Wf || !D || !u || !c || M <= 0 || N <= 0 || K <= 0) return I360_ERR_ARG;
+  if ((K % 64) || (lda % 8) || (ldw % 8) || (ldd % 8) || (N % 8)) return I360_ERR_ARG;
+  if (act != 0 && act != 1) return I360_ERR_UNSUPPORTED;
+  if (act == 1 && ((N % 256) || rowvec)) return I360_ERR_UNSUPPORTED;
+  const int bn = pick_bn(N, act);
+  if (bn < 160) return I360_ERR_UNSUPPORTED;        // narrow outputs keep the separate LayerNorm pass (host decides)
+  GemmConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K; p.conv = 0;
+  p.m_tiles = (M + BM - 1) / BM; p.n_tiles = (N + bn - 1) / bn; p.k_iters = K / BK;
+  p.D = static_cast<bf16*>(D); p.ldd = ldd;
+  p.rowvec = rowvec; p.rowvec_div = rowvec_div > 0 ? rowvec_div : 1; p.rowvec_ld = rowvec_ld; p.rowvec_mod = rowvec_mod;
+  p.act = act; p.out_scale = 1.0f; p.n_out = (act == 1) ? N / 2 : N;
+  p.ln_u = u; p.ln_c = c; p.ln_eps = eps;
+  CUtensorMap ta, tw, td;
+  uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}; uint64_t sA[1] = {(uint64_t)lda * 2};
+  uint32_t bA[2] = {BK, (uint32_t)BM};
+  uint64_t dW[2] = {(uint64_t)K, (uint64_t)N}; uint64_t sW[1] = {(uint64_t)ldw * 2};
+  uint32_t bW[2] = {BK, (uint32_t)bn};
+  int r = get_tmap_bf16(&ta, A, 2, dA, sA, bA, 3); if (r) return r;
+  r = get_tmap_bf16(&tw, Wf, 2, dW, sW, bW, 3); if (r) return r;
+  uint64_t dD[2] = {(uint64_t)p.n_out, (uint64_t)M}; uint64_t sD[1] = {(uint64_t)ldd * 2};
+  uint32_t bD[2] = {32, BM};
+  r = get_tmap_bf16(&td, D, 2, dD, sD, bD, 2); if (r) return r;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (act == 1) return launch<256, EPI_GEGLU, 1, true>(ta, ta, ta, tw, td, td, p, st);
+  if (rowvec) {
+    switch (bn) {
+      case 160: return launch<160, EPI_ROWVEC, 1, true>(ta, ta, ta, tw, td, td, p, st);
+      case 192: return launch<192, EPI_ROWVEC, 1, true>(ta, ta, ta, tw, td, td, p, st);
+      case 256: return launch<256, EPI_ROWVEC, 1, true>(ta, ta, ta, tw, td, td, p, st);
+    }
+  } else {
+    switch (bn) {
+      case 160: return launch<160, EPI_PLAIN, 1, true>(ta, ta, ta, tw, td, td, p, st);
+      case 192: return launch<192, EPI_PLAIN, 1, true>(ta, ta, ta, tw, td, td, p, st);
+      case 256: return launch<256, EPI_PLAIN, 1, true>(ta, ta, ta, tw, td, td, p, st);
+    }
+  }
+  return I360_ERR_UNSUPPORTED;
+}
+
+// tile width i360_gemm_ln_bf16 would use for N output columns (0: not supported, keep LayerNorm + GEMM)
+extern "C" int i360_gemm_ln_supported(int N, int K, int act) {
+  if ((K % 64) || (N % 8)) return 0;
+  if (act == 1) return (N % 256 == 0) ? 256 : 0;
+  const int bn = pick_bn(N, 0);
+  return bn >= 160 ? bn : 0;
 }

@@ -65,6 +65,41 @@ def tokens(x):
 
 
 # ------------------------------------------------------------------------------------------------------
+# LayerNorm -> Linear as ONE kernel (ops.gemm_ln): the fold (W * gamma, row sums, W beta + b) is a cached weight packing
+# ------------------------------------------------------------------------------------------------------
+LN_FOLD = os.environ.get("I360_LN_FOLD", "1") not in ("", "0")
+
+
+def ln_linear(t, norm, owner, key, mods, bias_mod=None, act=ops.ACT_NONE, pe=None, pe_div=1, pe_mod=0):
+    """act(LayerNorm(t) @ cat(W of mods)^T + bias (+ pe @ W^T per row group)).  ``pe`` fp32 [pe_mod, C] is the table
+    the temporal module adds AFTER the norm (motion_module.py:350)."""
+    ws = [m.weight for m in mods]
+    n_total, k = sum(w.shape[0] for w in ws), ws[0].shape[1]
+    geglu = act == ops.ACT_GEGLU
+    if LN_FOLD and ops.gemm_ln_supported(n_total, k, act):
+        params = ws + [norm.weight, norm.bias] + ([bias_mod.bias] if bias_mod is not None and bias_mod.bias is not None else [])
+
+        def build():
+            w = torch.cat([x.to(BF16) for x in ws], 0)
+            b = bias_mod.bias.to(BF16) if bias_mod is not None and bias_mod.bias is not None else None
+            return ops.fold_layernorm(w, b, norm.weight.to(BF16), norm.bias.to(BF16), geglu)
+
+        wf, u, c = cached(owner, "lnfold_" + key, params, build)
+        rv = None
+        if pe is not None:
+            rv = cached(owner, f"lnpe_{key}_{pe.shape[0]}", ws + [pe],
+                        lambda: (pe.float() @ torch.cat([x.to(BF16) for x in ws], 0).float().t()).contiguous())
+        return ops.gemm_ln(t, wf, u, c, norm.eps, rowvec=rv, rowvec_div=pe_div, rowvec_mod=pe_mod if pe is not None else 0, act=act)
+    nrm = ops.layernorm(t, norm.weight, norm.bias, norm.eps, post_add=pe, post_div=pe_div, post_mod=pe_mod if pe is not None else 1)
+    if geglu:
+        wg, bg = geglu_w(owner)
+        return ops.gemm(nrm, wg, bias=bg, act=ops.ACT_GEGLU)
+    w = fused_w(owner, key, mods) if len(mods) > 1 else lin_w(mods[0])[0]
+    b = lin_w(bias_mod)[1] if bias_mod is not None else None
+    return ops.gemm(nrm, w, bias=b)
+
+
+# ------------------------------------------------------------------------------------------------------
 # time embedding (unet.py:718-744; MVGenModel.py:104-133)
 # ------------------------------------------------------------------------------------------------------
 def _mlp(t_emb, te):
@@ -166,8 +201,7 @@ def spatial_transformer(x, t3d, ctx: Context, frames: int):
     for blk in t3d.transformer_blocks:
         # --- attn1: fused QKV projection, flash attention reading q/k/v as column slices ---
         a1 = blk.attn1
-        nrm = ops.layernorm(t, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
-        qkv = ops.gemm(nrm, fused_w(a1, "qkv", [a1.to_q, a1.to_k, a1.to_v]))
+        qkv = ln_linear(t, blk.norm1, a1, "qkv", [a1.to_q, a1.to_k, a1.to_v])
         o = torch.empty_like(t)
         ops.attention(ops.seq_view(qkv, n, npix, 0), ops.seq_view(qkv, n, npix, c), ops.seq_view(qkv, n, npix, 2 * c),
                       ops.seq_view(o, n, npix), heads, hd, n)
@@ -175,8 +209,7 @@ def spatial_transformer(x, t3d, ctx: Context, frames: int):
         t = ops.gemm(o, wo, bias=bo, resid=t)
         # --- attn2: text + image-prompt cross attention, outputs summed before to_out (attention.py:148) ---
         a2 = blk.attn2
-        nrm = ops.layernorm(t, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
-        q = ops.gemm(nrm, lin_w(a2.to_q)[0])
+        q = ln_linear(t, blk.norm2, a2, "q", [a2.to_q])
         nt, ni = ctx.text.shape[1], ctx.ip.shape[1]
         kv_t = ops.gemm(ctx.text.view(-1, ctx.text.shape[-1]), fused_w(a2, "kv", [a2.to_k, a2.to_v]))
         ip = ctx.ip[..., : a2.image_cross_attention_dim] if a2.image_cross_attention_dim != a2.cross_attention_dim else ctx.ip
@@ -203,9 +236,7 @@ def spatial_transformer(x, t3d, ctx: Context, frames: int):
 
 @traced("feed_forward")
 def feed_forward(t, ff, norm):
-    nrm = ops.layernorm(t, norm.weight, norm.bias, norm.eps)
-    wg, bg = geglu_w(ff)
-    g = ops.gemm(nrm, wg, bias=bg, act=ops.ACT_GEGLU)
+    g = ln_linear(t, norm, ff, "geglu", [ff.net[0].proj], bias_mod=ff.net[0].proj, act=ops.ACT_GEGLU)
     w2, b2 = lin_w(ff.net[2])
     return ops.gemm(g, w2, bias=b2, resid=t)
 
@@ -229,9 +260,8 @@ def temporal_module(x, mm, frames: int):
     t = ops.gemm(tokens(hn), wi, bias=bi)
     for blk in tt.transformer_blocks:
         for att, norm in zip(blk.attention_blocks, blk.norms):
-            nrm = ops.layernorm(t, norm.weight, norm.bias, norm.eps, post_add=_pe_table(att, frames, BF16), post_div=d,
-                                post_mod=frames)
-            qkv = ops.gemm(nrm, fused_w(att, "qkv", [att.to_q, att.to_k, att.to_v]))
+            qkv = ln_linear(t, norm, att, "qkv", [att.to_q, att.to_k, att.to_v], pe=_pe_table(att, frames, BF16), pe_div=d,
+                            pe_mod=frames)
             o = torch.empty_like(t)
             ops.temporal_attention(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], o, n // frames, frames, d, tt.heads, tt.dim_head)
             wo, bo = lin_w(att.to_out[0])

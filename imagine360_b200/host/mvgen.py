@@ -143,10 +143,9 @@ class WarpAttn(nn.Module):
 
 
 def _warp_ff(t, tr):
-    nrm = ops.layernorm(t, tr.norm2.weight, tr.norm2.bias, tr.norm2.eps)
-    wg, bg = geglu_w(tr.ff)
+    g = Fw.ln_linear(t, tr.norm2, tr.ff, "geglu", [tr.ff.net[0].proj], bias_mod=tr.ff.net[0].proj, act=ops.ACT_GEGLU)
     w2, b2 = lin_w(tr.ff.net[2])
-    return ops.gemm(ops.gemm(nrm, wg, bias=bg, act=ops.ACT_GEGLU), w2, bias=b2, resid=t)
+    return ops.gemm(g, w2, bias=b2, resid=t)
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -104,6 +104,52 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, resid=None, rowvec=None, r
     return out
 
 
+def gemm_ln_supported(N: int, K: int, act: int = ACT_NONE) -> bool:
+    return int(lib().i360_gemm_ln_supported(c_int(N), c_int(K), c_int(act))) != 0
+
+
+def fold_layernorm(weight: torch.Tensor, bias, gamma: torch.Tensor, beta: torch.Tensor, geglu: bool = False):
+    """(W [N, K], bias [N] | None, LayerNorm gamma / beta [K]) -> (Wf bf16 [N, K], u fp32 [N], c fp32 [N]) for
+    :func:`gemm_ln`:  LN(x) W^T + b = rstd * (x Wf^T - mean * u) + c  with Wf = W * gamma, u = rowsum(Wf) taken from the
+    bf16-ROUNDED Wf (so that the mean term cancels exactly what the tensor core accumulated), c = W beta + b."""
+    w32 = weight.float()
+    wf = (w32 * gamma.float()[None, :]).to(BF16)
+    u = wf.float().sum(dim=1)
+    c = w32 @ beta.float()
+    if bias is not None:
+        c = c + bias.float()
+    if geglu:
+        n_total = weight.shape[0]
+        half, inner = geglu_block(n_total) // 2, n_total // 2
+        idx = torch.cat([torch.cat([torch.arange(t * half, (t + 1) * half), inner + torch.arange(t * half, (t + 1) * half)])
+                         for t in range(inner // half)]).to(weight.device)
+        wf, u, c = wf.index_select(0, idx), u.index_select(0, idx), c.index_select(0, idx)
+    return wf.contiguous(), u.contiguous(), c.contiguous()
+
+
+def gemm_ln(a: torch.Tensor, wf: torch.Tensor, u: torch.Tensor, c: torch.Tensor, eps: float = 1e-5, rowvec=None,
+            rowvec_div: int = 1, rowvec_mod: int = 0, act: int = ACT_NONE, out: torch.Tensor | None = None) -> torch.Tensor:
+    """out[M, N] = act(LayerNorm(a)[M, K] @ W^T + bias (+ rowvec[(r // rowvec_div) % rowvec_mod])) with the LayerNorm folded
+    into the GEMM (see :func:`fold_layernorm`); ``a`` is the UN-normalised token matrix."""
+    _chk_bf16(a, wf, out)
+    assert a.dim() == 2 and wf.dim() == 2 and a.shape[1] == wf.shape[1] and a.stride(1) == 1 and wf.stride(1) == 1
+    assert u.dtype == torch.float32 and c.dtype == torch.float32 and u.is_contiguous() and c.is_contiguous()
+    M, K = a.shape
+    N = wf.shape[0]
+    n_out = N // 2 if act == ACT_GEGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=BF16, device=a.device)
+    assert out.shape == (M, n_out) and out.stride(1) == 1
+    if rowvec is not None:
+        assert rowvec.dtype == torch.float32 and rowvec.stride(-1) == 1 and rowvec.shape[-1] == N
+    rc = lib().i360_gemm_ln_bf16(_p(a), c_longlong(a.stride(0)), _p(wf), c_longlong(wf.stride(0)), _p(out),
+                                 c_longlong(out.stride(0)), c_int(M), c_int(N), c_int(K), _p(u), _p(c), c_float(eps),
+                                 _p(rowvec), c_int(rowvec_div), c_int(rowvec_mod),
+                                 c_int(rowvec.stride(0) if rowvec is not None else 0), c_int(act), _stream())
+    check(rc, "i360_gemm_ln_bf16")
+    return out
+
+
 def pack_conv3x3(weight: torch.Tensor, *shortcuts: torch.Tensor) -> torch.Tensor:
     """[Cout, Cin, 3, 3] (+ optional 1x1 shortcut weights [Cout, Ci, 1, 1]) -> [Cout, 9*Cin + sum Ci]
     with the 3x3 part ordered (kh, kw, cin) to match the tap loop of the kernel."""

@@ -110,3 +110,41 @@ def test_conv3x3_fused_shortcut_temb_crop():
     ref = ref + temb.repeat_interleave(F_, 0)[:, :, None, None]
     ref = ref.permute(0, 2, 3, 1) + resid.float()
     _close(out, ref, "fused conv")
+
+
+@pytest.mark.parametrize("M,N,K,act,pe", [(1000, 960, 320, 0, False), (777, 320, 320, 0, False), (513, 2560, 320, 1, False),
+                                          (300, 3840, 1280, 0, True), (4100, 1920, 640, 0, True), (129, 1280, 1280, 0, False),
+                                          (2000, 5120, 640, 1, False), (64, 960, 320, 0, True)])
+def test_gemm_with_folded_layernorm(M, N, K, act, pe):
+    """i360_gemm_ln_bf16: LayerNorm folded into the consuming projection (row statistics from the A tiles in smem, applied
+    in the epilogue) against fp32 torch LayerNorm -> Linear (-> GEGLU), incl. the temporal-PE row vector."""
+    from imagine360_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = (torch.randn(M, K, device="cuda", generator=g) * 1.7 + 0.6 * torch.randn(M, 1, device="cuda", generator=g)).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g).bfloat16() if act else None
+    gamma = (1 + 0.2 * torch.randn(K, device="cuda", generator=g)).bfloat16()
+    beta = (0.2 * torch.randn(K, device="cuda", generator=g)).bfloat16()
+    assert ops.gemm_ln_supported(N, K, act)
+    wf, u, c = ops.fold_layernorm(w, b, gamma, beta, geglu=bool(act))
+    Fr, D = 4, 5
+    table = torch.randn(Fr, K, device="cuda", generator=g).bfloat16().float() if pe else None
+    rv = (table @ w.float().t()).contiguous() if pe else None
+    out = ops.gemm_ln(x, wf, u, c, 1e-5, rowvec=rv, rowvec_div=D, rowvec_mod=Fr if pe else 0, act=act)
+    y = F.layer_norm(x.float(), (K,), gamma.float(), beta.float(), 1e-5)
+    if pe:
+        y = y + table[(torch.arange(M, device="cuda") // D) % Fr]
+    ref = y @ w.float().t()
+    if act:
+        ref = ref + b.float()
+        val, gate = ref.chunk(2, dim=-1)
+        ref = val * F.gelu(gate)
+    _close(out, ref, f"gemm_ln {M}x{N}x{K} act{act}")
+    # and within a bf16 round-off of the two-kernel path it replaces (which rounds the normalised activations to bf16)
+    nrm = ops.layernorm(x, gamma, beta, 1e-5, post_add=table, post_div=D, post_mod=Fr if pe else 1)
+    if act:
+        wp, bp = ops.pack_geglu(w, b)
+        two = ops.gemm(nrm, wp, bias=bp, act=ops.ACT_GEGLU)
+    else:
+        two = ops.gemm(nrm, w)
+    _close(out, two, "folded vs LayerNorm + GEMM", rtol=1.0 / 64, atol_scale=1e-2)
