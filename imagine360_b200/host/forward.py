@@ -65,9 +65,13 @@ def tokens(x):
 
 
 # ------------------------------------------------------------------------------------------------------
-# LayerNorm -> Linear as ONE kernel (ops.gemm_ln): the fold (W * gamma, row sums, W beta + b) is a cached weight packing
+# LayerNorm -> Linear as ONE kernel (ops.gemm_ln): the fold (W * gamma, row sums, W beta + b) is a cached weight packing.
+# EXPERIMENT, off by default (I360_LN_FOLD=1 enables it): it removes 192 of the 220 LayerNorm launches of a 16x512x1024
+# step (13.5 ms of HBM passes), but the four statistics warps it adds to the GEMM CTA need ~2.2 issue slots per A-tile
+# element, recomputed by every N tile of a row block, and take them from the epilogue warps that bound the K = 320 / 640
+# projections: measured on one B200, same box, 317.9 ms per step with the fold against 308.7 ms without.
 # ------------------------------------------------------------------------------------------------------
-LN_FOLD = os.environ.get("I360_LN_FOLD", "1") not in ("", "0")
+LN_FOLD = os.environ.get("I360_LN_FOLD", "0") not in ("", "0")
 
 
 def ln_linear(t, norm, owner, key, mods, bias_mod=None, act=ops.ACT_NONE, pe=None, pe_div=1, pe_mod=0):
