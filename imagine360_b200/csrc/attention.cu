@@ -42,6 +42,7 @@ struct AttnParams {
   bf16* o; long long os1, os2, os3; int o_col0;
   int accumulate;             // out = bf16(out + bf16(O))   (IP-adapter branch sum, attention.py:148)
   int has_bias; int bias_rows, bias_cols;
+  int bias_item_rows;         // 0: one bias for every (batch item, head); else rows of the bias per (batch item, head) block
 };
 
 #ifndef I360_POLY_MASK
@@ -252,7 +253,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
       for (int g = 0; g < G; ++g)
         tma_load_4d(sQ + g * C::kQBytes, &tmQ, q_full, p.q.col0 + (head0 + g) * HD, qc1, qc2, qc3);
-      const int q_base = qt * 128;   // the bias arrives tile-padded: [q_tiles*128, kv_tiles*128]
+      // the bias arrives tile-padded: [q_tiles*128, kv_tiles*128]; per-item biases (SAM's decomposed relative position
+      // term, one block of bias_item_rows rows per (batch item, head)) are stacked along the row axis
+      const int q_base = qt * 128 + (bi * static_cast<int>(gridDim.y) * G + head0) * p.bias_item_rows;
       for (int j = 0; j < p.kv_tiles; ++j) {
         int c1, c2, c3;
         tile_coords(p.kv, bi, j, c1, c2, c3);
@@ -778,9 +781,9 @@ static void fill_operand(AttnOperand* o, const I360TokenView& v) {
 // row r of query tile qt, column j*128 + c the key held by row c of key tile j (see fill_operand: a tile is 128
 // consecutive tokens of one view, or 128/d1 whole views when d1 divides 128).  For sequences whose views are
 // multiples of 128 tokens (every level of the 512x1024 / 256x512 configurations) this IS the dense [Nq, Nk] matrix.
-extern "C" int i360_attention_bf16(const I360TokenView* q, const I360TokenView* k, const I360TokenView* v,
-                                   const I360TokenView* o, int heads, int head_dim, int batch, float scale,
-                                   const void* bias, int bias_rows, int bias_cols, int accumulate, void* stream) {
+static int attention_impl(const I360TokenView* q, const I360TokenView* k, const I360TokenView* v,
+                          const I360TokenView* o, int heads, int head_dim, int batch, float scale,
+                          const void* bias, int bias_rows, int bias_cols, int bias_item_rows, int accumulate, void* stream) {
   if (!q || !k || !v || !o || !q->ptr || !k->ptr || !v->ptr || !o->ptr) return I360_ERR_ARG;
   if (head_dim != 32 && head_dim != 64) return I360_ERR_UNSUPPORTED;
   if (heads <= 0 || batch <= 0) return I360_ERR_ARG;
@@ -798,6 +801,8 @@ extern "C" int i360_attention_bf16(const I360TokenView* q, const I360TokenView* 
   p.o = static_cast<bf16*>(const_cast<void*>(o->ptr)); p.os1 = o->s1; p.os2 = o->s2; p.os3 = o->s3; p.o_col0 = o->col0;
   p.accumulate = accumulate;
   p.has_bias = bias != nullptr; p.bias_rows = bias_rows; p.bias_cols = bias_cols;
+  p.bias_item_rows = bias ? bias_item_rows : 0;
+  if (p.bias_item_rows && (head_dim != 64 || p.q.box3 != 1 || p.kv.box3 != 1)) return I360_ERR_UNSUPPORTED;
   CUtensorMap tq, tk, tv, tb;
   int r = make_view_map(&tq, *q, head_dim, p.q.box1, p.q.box3); if (r) return r;
   r = make_view_map(&tk, *k, head_dim, p.kv.box1, p.kv.box3); if (r) return r;
@@ -826,4 +831,24 @@ extern "C" int i360_attention_bf16(const I360TokenView* q, const I360TokenView* 
     return launch_attn<64, false, 1>(tq, tk, tv, tb, p, heads, batch, st);
   }
   return launch_attn<32, false, 1>(tq, tk, tv, tb, p, heads, batch, st);
+}
+
+extern "C" int i360_attention_bf16(const I360TokenView* q, const I360TokenView* k, const I360TokenView* v,
+                                   const I360TokenView* o, int heads, int head_dim, int batch, float scale,
+                                   const void* bias, int bias_rows, int bias_cols, int accumulate, void* stream) {
+  return attention_impl(q, k, v, o, heads, head_dim, batch, scale, bias, bias_rows, bias_cols, 0, accumulate, stream);
+}
+
+// Same kernel with one bias block per (batch item, head): bias is [batch * heads * bias_item_rows, bias_cols] bf16, block
+// (bi * heads + h) holding the [Nq, Nk] logits bias of that head (rows past Nq of the last query tile run into the next
+// block and are never used).  Plain sequences and head_dim 64 only.  Replaces the `attn + rel_h + rel_w` -> softmax ->
+// `attn @ v` sequence of segment_anything's ImageEncoderViT Attention.forward (modeling/image_encoder.py, release 1.0).
+extern "C" int i360_attention_item_bias_bf16(const I360TokenView* q, const I360TokenView* k, const I360TokenView* v,
+                                             const I360TokenView* o, int heads, int head_dim, int batch, float scale,
+                                             const void* bias, int bias_item_rows, int bias_cols, void* stream) {
+  if (!bias || bias_item_rows <= 0) return I360_ERR_ARG;
+  const long long rows = static_cast<long long>(batch) * heads * bias_item_rows;
+  if (rows > 0x7fffffffLL) return I360_ERR_ARG;
+  return attention_impl(q, k, v, o, heads, head_dim, batch, scale, bias, static_cast<int>(rows), bias_cols, bias_item_rows, 0,
+                        stream);
 }

@@ -19,6 +19,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from . import geometry as G
+from .encoders import SamImageEncoderNative, _DeviceSwitch, wrap_text_encoder
 from .unet3d import refresh_packed_weights
 
 BF16 = torch.bfloat16
@@ -206,6 +207,10 @@ class SamPredictor:
         self.model = sam_model
         self.transform = ResizeLongestSide(sam_model.image_encoder.img_size)
         self.features = None
+        # a segment_anything ImageEncoderViT is evaluated on the sm_100a kernels when its input is
+        # on a GPU (host/encoders.py); any other encoder module is simply called
+        enc = sam_model.image_encoder
+        self.native_encoder = SamImageEncoderNative(enc) if SamImageEncoderNative.supports(enc) else None
 
     def _preprocess(self, x):
         if callable(getattr(self.model, "preprocess", None)):
@@ -219,7 +224,11 @@ class SamPredictor:
         size = self.model.image_encoder.img_size
         assert transformed_image.dim() == 4 and transformed_image.shape[1] == 3 and max(transformed_image.shape[2:]) == size, \
             f"set_torch_image input must be BCHW with long side {size}."
-        self.features = self.model.image_encoder(self._preprocess(transformed_image))
+        x = self._preprocess(transformed_image)
+        if self.native_encoder is not None and x.is_cuda:
+            self.features = self.native_encoder(x)
+        else:
+            self.features = self.model.image_encoder(x)
 
     def get_image_embedding(self):
         if self.features is None:
@@ -228,17 +237,16 @@ class SamPredictor:
 
 
 def _make_sam_predictor(image_encoder):
-    try:                                  # the real package wins when it is installed (same three members)
-        from segment_anything import SamPredictor as _Real
-        return _Real(image_encoder)
-    except ImportError:
-        return SamPredictor(image_encoder)
+    """The pipeline's predictor (pipeline...dual.py:171-174).  Always this module's mirror of the three members the
+    reference touches: it routes a segment_anything ViT through the native encoder, which the package's own
+    ``SamPredictor.set_torch_image`` (a plain ``self.model.image_encoder(x)``) would not."""
+    return SamPredictor(image_encoder)
 
 
 class AnimationPipeline:
     def __init__(self, vae, text_encoder, tokenizer, pers_unet, pano_unet, mv_base_model, scheduler, image_encoder=None,
                  image_encoder_name="CLIP"):
-        self.vae, self.text_encoder, self.tokenizer = vae, text_encoder, tokenizer
+        self.vae, self.text_encoder, self.tokenizer = vae, wrap_text_encoder(text_encoder), tokenizer
         self.pers_unet, self.pano_unet, self.mv_base_model, self.scheduler = pers_unet, pano_unet, mv_base_model, scheduler
         self.image_encoder, self.image_encoder_name = image_encoder, image_encoder_name
         self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1) if vae is not None else 8
@@ -251,7 +259,7 @@ class AnimationPipeline:
     def to(self, device):
         self.device = torch.device(device)
         for m in (self.vae, self.text_encoder, self.mv_base_model, self.image_encoder):
-            if isinstance(m, torch.nn.Module):
+            if isinstance(m, torch.nn.Module) or isinstance(m, _DeviceSwitch):
                 m.to(device)
         return self
 

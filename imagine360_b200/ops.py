@@ -306,6 +306,32 @@ def attention(q: TokenView, k: TokenView, v: TokenView, o: TokenView, heads: int
     check(rc, "i360_attention_bf16")
 
 
+def attention_item_bias(q: TokenView, k: TokenView, v: TokenView, o: TokenView, heads: int, head_dim: int, batch: int,
+                        bias: torch.Tensor, scale: float | None = None) -> None:
+    """Attention with one [Nq, Nk_padded] bias block per (batch item, head): ``bias`` is [batch * heads, Nq, ldb] bf16."""
+    _chk_bf16(bias)
+    assert bias.dim() == 3 and bias.is_contiguous() and bias.shape[0] == batch * heads and bias.shape[1] == q.d1
+    rc = lib().i360_attention_item_bias_bf16(ctypes.byref(q), ctypes.byref(k), ctypes.byref(v), ctypes.byref(o), c_int(heads),
+                                             c_int(head_dim), c_int(batch),
+                                             c_float(scale if scale is not None else head_dim ** -0.5), _p(bias),
+                                             c_int(bias.shape[1]), c_int(bias.shape[2]), _stream())
+    check(rc, "i360_attention_item_bias_bf16")
+
+
+def relpos_bias(qkv: torch.Tensor, col0: int, items: int, heads: int, head_dim: int, S: int, rel_h: torch.Tensor,
+                rel_w: torch.Tensor) -> torch.Tensor:
+    """SAM's decomposed relative position bias for ``items`` sequences of S x S tokens -> [items * heads, S*S, ldb] bf16."""
+    _chk_bf16(qkv, rel_h, rel_w)
+    assert qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.shape[0] == items * S * S
+    assert rel_h.shape == (2 * S - 1, head_dim) and rel_w.shape == (2 * S - 1, head_dim) and rel_h.is_contiguous() and rel_w.is_contiguous()
+    ldb = -(-S * S // 8) * 8
+    bias = torch.empty((items * heads, S * S, ldb), dtype=BF16, device=qkv.device)
+    rc = lib().i360_relpos_bias_bf16(_p(qkv), c_longlong(qkv.stride(0)), c_int(col0), c_int(items), c_int(heads), c_int(head_dim),
+                                     c_int(S), _p(rel_h), _p(rel_w), _p(bias), c_int(ldb), _stream())
+    check(rc, "i360_relpos_bias_bf16")
+    return bias
+
+
 def cross_attention_text_ip_supported(head_dim: int, nt: int, ni: int) -> bool:
     ntp, nip = -(-nt // 16) * 16, -(-ni // 16) * 16
     return head_dim == 64 and ntp <= 96 and nip <= 96 and -(-ntp // 64) + -(-nip // 64) <= 3

@@ -104,6 +104,24 @@ int i360_attention_bf16(const I360TokenView* q, const I360TokenView* k, const I3
                         const I360TokenView* o, int heads, int head_dim, int batch, float scale, const void* bias,
                         int bias_rows, int bias_cols, int accumulate, void* stream);
 
+/* The same attention with one bias block per (batch item, head): bias is [batch * heads * bias_item_rows, bias_cols]
+ * bf16, block (bi * heads + h) = the [Nq, Nk] additive logits of that head.  Plain sequences, head_dim 64.
+ * Replaces `attn = (q * scale) @ k^T; attn = add_decomposed_rel_pos(attn, ...); softmax; attn @ v` of
+ * segment_anything's ImageEncoderViT (modeling/image_encoder.py Attention.forward, release 1.0; the package is a
+ * dependency of the reference: requirements.txt:11, inference_dual_p2e.py:369-370; its encoder is run by
+ * animatediff/pipelines/pipeline_animation_inference_dual.py:685-690,:708-713). */
+int i360_attention_item_bias_bf16(const I360TokenView* q, const I360TokenView* k, const I360TokenView* v,
+                                  const I360TokenView* o, int heads, int head_dim, int batch, float scale,
+                                  const void* bias, int bias_item_rows, int bias_cols, void* stream);
+
+/* SAM ViT decomposed relative position bias: bias[(item, head), q, k] = q . Rh[qh - kh + S - 1] + q . Rw[qw - kw + S - 1]
+ * for sequences of S x S tokens (a 14 x 14 window or the 64 x 64 grid), q the unscaled query of the head at columns
+ * col0 + head * hd of the [items * S*S, ldq] projection output; rel_h / rel_w: [2S - 1, hd] bf16; bias rows of ldb
+ * elements (ldb % 8 == 0, columns past S*S zeroed).  Replaces get_rel_pos + add_decomposed_rel_pos (two einsums and a
+ * broadcast add on the [B*heads, S^2, S^2] logits) of segment_anything modeling/image_encoder.py. */
+int i360_relpos_bias_bf16(const void* q, long long ldq, int col0, int items, int heads, int hd, int S,
+                          const void* rel_h, const void* rel_w, void* bias, int ldb, void* stream);
+
 /* Fused text + image-prompt cross-attention: O = softmax(Q Kt^T * scale) Vt + softmax(Q Ki^T * scale) Vi, summed in
  * fp32 and rounded once.  q, o: [rows, heads*64] (row strides in elements); rows = n_ctx * rows_per_ctx, the rows of
  * clip element e (all of its frames) are [e * rows_per_ctx, +rows_per_ctx) and attend to text tokens
