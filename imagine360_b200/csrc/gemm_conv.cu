@@ -10,6 +10,13 @@
 //               exactly conv2d's zero padding -> no im2col buffer is ever materialised.
 //               Up to two extra 1x1 sources are accumulated into the same tile (ResnetBlock's
 //               conv_shortcut over the un-normalised input / the skip-concat halves).
+//   HALO mode : CONV with a 16 x 8 pixel tile whose (16+2) x (8+2) halo is loaded ONCE per 64-channel block (one 4-D
+//               TMA box, 180 rows of 128 B); the nine taps are nine tcgen05.mma groups whose A descriptor starts
+//               (kh * 10 + kw) rows into that tile with SBO = 10 rows (1280 B): each 8-row core group of the operand
+//               is one 8-pixel image row of the tile, and the tensor core applies the 128-byte swizzle to the absolute
+//               shared-memory address (probed: tools/probe_halo_desc.cu), so shifted starts read exactly what TMA
+//               wrote.  Activation traffic from L2 drops from 9 x 16 KB to 22.5 KB per channel block; the weight
+//               tiles (one per tap and channel block) flow through their own ring.
 //
 // Warp roles (320 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer (one elected
 // lane), warps 2..9 = two epilogue groups (TMEM -> registers -> bias/temb/residual/GEGLU -> bf16 ->
@@ -35,6 +42,7 @@ struct GemmConvParams {
   int TW, TH, TB;     // pixel box, TW*TH*TB == 128
   int n_wt, n_ht, n_bt;
   int Cin, C2, C3;    // channels of the 3x3 source and of up to two extra 1x1 sources
+  int halo;           // CONV through the halo-tile kernels (TW = 8, TH = 16, TB = 1)
   int crop;           // output columns cropped on each side (pano halo)
   int xoff;           // column offset applied to the extra 1x1 sources (= -crop: they are stored un-padded)
   int Hout, Wout;
@@ -62,10 +70,19 @@ constexpr int kThreads = 320;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue (tw
 // MT: M sub-tiles per CTA tile (1 or 2).  MT = 2 (GEMM mode, BN = 128 only) computes a 256 x 128 tile as two 128-row
 // accumulators that share the weight tile in smem: 683 instead of 569 FLOP per byte loaded from L2 for the N = 640 /
 // 1920 projections, which are bound by L2 -> SM traffic at the tensor-core pace; epilogue group g owns accumulator g.
-template <int BN, bool RING = false, int MT = 1, bool LNF = false> struct Cfg {
+constexpr int kHaloTW = 8, kHaloTH = 16;                       // pixel tile of HALO mode (8-pixel rows = UMMA core groups)
+constexpr int kHaloW = kHaloTW + 2, kHaloH = kHaloTH + 2;      // loaded box
+constexpr int kHaloRows = kHaloW * kHaloH;                     // 180 rows of 128 bytes
+constexpr int kHaloTxBytes = kHaloRows * BK * 2;               // 23 040
+constexpr int kHaloBytes = 23 * 1024;                          // ... rounded up to the 1024-byte swizzle atom
+constexpr int kHaloStages = 2;                                 // a halo tile lives for 9 taps: double buffering suffices
+
+template <int BN, bool RING = false, int MT = 1, bool LNF = false, bool HALO = false> struct Cfg {
+  static_assert(!HALO || (MT == 1 && !LNF), "HALO is a CONV mode");
   static constexpr int kABytes = MT * BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = HALO ? kBBytes : kABytes + kBBytes;   // HALO: the ring holds weight tiles only
+  static constexpr int kHaloTotal = HALO ? kHaloStages * kHaloBytes : 0;
   // epilogue staging: output columns leave in 32-column chunks (64-byte rows, 64B swizzle) through 2 smem
   // buffers per epilogue group
   static constexpr int CH = 32;
@@ -82,9 +99,10 @@ template <int BN, bool RING = false, int MT = 1, bool LNF = false> struct Cfg {
   static constexpr int kTableBytes = kBiasTable ? (LNF ? 4 : 2) * BN * 4 : 0;       // [group][BN] bias (LNF: c), then [group][BN] u
   static constexpr int kStatBytes = LNF ? 2 * MT * BM * 8 : 0;                        // [acc stage][row] (rstd, -mean * rstd)
   // dynamic smem is declared __align__(1024) (checked at run time), so no alignment slack is reserved
-  static constexpr int kBudget = 227 * 1024 - kNumStg * kStgBytes - kTableBytes - kStatBytes - 256;
-  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kNumStg * kStgBytes + kTableBytes + kStatBytes + 256 /*barriers*/;
+  static constexpr int kBudget = 227 * 1024 - kNumStg * kStgBytes - kTableBytes - kStatBytes - 256 - kHaloTotal;
+  static constexpr int kMaxStages = HALO ? 6 : 8;
+  static constexpr int kStages = kBudget / kStageBytes > kMaxStages ? kMaxStages : kBudget / kStageBytes;
+  static constexpr int kSmemBytes = kHaloTotal + kStages * kStageBytes + kNumStg * kStgBytes + kTableBytes + kStatBytes + 256 /*barriers*/;
   static constexpr int kAccCols = MT * BN;        // TMEM columns of one accumulator stage
   static constexpr int kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128
                                    : (2 * kAccCols <= 256) ? 256 : 512;
@@ -105,18 +123,19 @@ template <int BN, int EPI> struct UseRing { static constexpr bool value = (EPI =
 // row and accumulator stage, and the epilogue applies  rstd * acc - mean * rstd * u[n] + c[n].  The normalised
 // activations are never written to or read from HBM: the LayerNorm pass (one read + one write of the token matrix per
 // norm, 192 launches and ~13 ms of the 16x512x1024 step) disappears.
-template <int BN, int EPI, int MT = 1, bool LNF = false>
+template <int BN, int EPI, int MT = 1, bool LNF = false, bool HALO = false>
 __global__ void __launch_bounds__(kThreads + (LNF ? 128 : 0), 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                  const GemmConvParams p) {
   constexpr bool kRing = UseRing<BN, EPI>::value;
-  using C = Cfg<BN, kRing, MT, LNF>;
+  using C = Cfg<BN, kRing, MT, LNF, HALO>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t base = smem_u32(smem_raw);
-  if ((base & 1023u) != 0) __trap();            // 128B-swizzled TMA / UMMA tiles need 1024-byte aligned stages
-  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();   // 128B-swizzled TMA / UMMA tiles need 1024-byte aligned stages
+  uint8_t* shalo = smem_raw;                          // HALO: kHaloStages activation tiles in front of the weight ring
+  uint8_t* smem = smem_raw + C::kHaloTotal;
+  const uint32_t base = smem_u32(smem);
   uint8_t* stg = smem + C::kStages * C::kStageBytes;            // 2 staging buffers (1024-aligned)
   float* sbias = reinterpret_cast<float*>(stg + C::kNumStg * C::kStgBytes);   // [2 groups][BN] (kBiasTable only)
   float* su = sbias + 2 * BN;                                                  // [2 groups][BN] (LNF only)
@@ -129,6 +148,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
   uint64_t* rbar = bars + 2 * C::kStages + 5;   // [2 groups][4]: residual chunk landed in staging buffer
   uint64_t* sfull = rbar + 8;                   // [2] (LNF): row statistics of the tile in accumulator stage s published
+  uint64_t* afull = rbar + 8;                   // [2] (HALO, never together with LNF): halo tile landed
+  uint64_t* aempty = rbar + 10;                 // [2] (HALO): the nine taps that read the halo tile have retired
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -140,6 +161,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], LNF ? 5 : 1); }   // LNF: MMA + 4 stats warps
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); if (LNF) mbar_init(&sfull[s], 4); }
     if (kRing) { for (int s = 0; s < 8; ++s) mbar_init(&rbar[s], 1); tma_prefetch_desc(&tmR); }
+    if (HALO) { for (int s = 0; s < kHaloStages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); } }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, C::kTmemCols); tmem_relinquish(); }
@@ -154,6 +176,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      int hstage = 0; uint32_t hphase = 0;      // HALO: activation ring
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
         const int n0 = n_blk * BN;
@@ -173,7 +196,28 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_load_2d(sb, &tmW, &full[stage], kcoord, n0);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         };
-        if (!p.conv) {
+        if (HALO) {
+          // activation tile (halo box, or a plain 128-pixel box for the fused 1x1 sources) into the A ring, then the
+          // weight tiles that multiply it into the B ring
+          auto issue_a = [&](const CUtensorMap* ma, int c0, int cw, int ch, int bytes) {
+            mbar_wait(&aempty[hstage], hphase ^ 1);
+            mbar_expect_tx(&afull[hstage], bytes);
+            tma_load_4d(shalo + hstage * kHaloBytes, ma, &afull[hstage], c0, cw, ch, b0);
+            if (++hstage == kHaloStages) { hstage = 0; hphase ^= 1; }
+          };
+          auto issue_b = [&](int kcoord) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], C::kBBytes);
+            tma_load_2d(smem + stage * C::kStageBytes, &tmW, &full[stage], kcoord, n0);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          };
+          for (int c0 = 0; c0 < p.Cin; c0 += BK) {
+            issue_a(&tmA, c0, w0 - 1, h0 - 1, kHaloTxBytes);
+            for (int tap = 0; tap < 9; ++tap) issue_b(tap * p.Cin + c0);
+          }
+          for (int c0 = 0; c0 < p.C2; c0 += BK) { issue_a(&tmA2, c0, w0 + p.xoff, h0, BM * BK * 2); issue_b(9 * p.Cin + c0); }
+          for (int c0 = 0; c0 < p.C3; c0 += BK) { issue_a(&tmA3, c0, w0 + p.xoff, h0, BM * BK * 2); issue_b(9 * p.Cin + p.C2 + c0); }
+        } else if (!p.conv) {
           for (int kb = 0; kb < p.k_iters; ++kb) issue(&tmA, kb * BK, 0, 0, kb * BK);
         } else {
           for (int tap = 0; tap < 9; ++tap) {
@@ -190,11 +234,39 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
       int stage = 0; uint32_t phase = 0;
+      int hstage = 0; uint32_t hphase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * C::kAccCols;
+        if (HALO) {
+          const int n_cin = (p.Cin + BK - 1) / BK, n_extra = (p.C2 + BK - 1) / BK + (p.C3 + BK - 1) / BK;
+          uint32_t acc = 0;
+          for (int cb = 0; cb < n_cin + n_extra; ++cb) {
+            mbar_wait(&afull[hstage], hphase);
+            const uint32_t sa = smem_u32(shalo) + hstage * kHaloBytes;
+            const bool halo = cb < n_cin;          // else: a plain 128-pixel tile of a fused 1x1 source
+            const int taps = halo ? 9 : 1;
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(&full[stage], phase);
+              tc_fence_after();
+              const uint32_t sb = base + stage * C::kStageBytes;
+              const uint32_t sa_tap = halo ? sa + ((tap / 3) * kHaloW + tap % 3) * (BK * 2) : sa;
+              const uint32_t sbo = halo ? kHaloW * BK * 2 : 1024;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16_ss(d_tmem, make_smem_desc(sa_tap + k * 32, sbo, 16, SWZ_128B),
+                             make_smem_desc(sb + k * 32, 1024, 16, SWZ_128B), idesc, acc);
+                acc = 1;
+              }
+              umma_commit(&empty[stage]);
+              if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&aempty[hstage]);          // every MMA that reads this activation tile has been issued before
+            if (++hstage == kHaloStages) { hstage = 0; hphase ^= 1; }
+          }
+        } else
         for (int kb = 0; kb < p.k_iters; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -561,14 +633,15 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-template <int BN, int EPI, int MT = 1, bool LNF = false>
+template <int BN, int EPI, int MT = 1, bool LNF = false, bool HALO = false>
 static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3,
                   const CUtensorMap& w, const CUtensorMap& d, const CUtensorMap& rmap, const GemmConvParams& p,
                   cudaStream_t st) {
-  using C = Cfg<BN, UseRing<BN, EPI>::value, MT, LNF>;
+  using C = Cfg<BN, UseRing<BN, EPI>::value, MT, LNF, HALO>;
+  static_assert(C::kStages >= 3, "weight / operand ring too shallow");
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_conv_kernel<BN, EPI, MT, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_conv_kernel<BN, EPI, MT, LNF, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              C::kSmemBytes) != cudaSuccess)
       return I360_ERR_CUDA;
     attr_set = true;
@@ -576,7 +649,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms()) grid = num_sms();
   if (grid <= 0) return I360_OK;
-  gemm_conv_kernel<BN, EPI, MT, LNF><<<grid, kThreads + (LNF ? 128 : 0), C::kSmemBytes, st>>>(a, a2, a3, w, d, rmap, p);
+  gemm_conv_kernel<BN, EPI, MT, LNF, HALO><<<grid, kThreads + (LNF ? 128 : 0), C::kSmemBytes, st>>>(a, a2, a3, w, d, rmap, p);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -629,6 +702,15 @@ static int pick_epi(const GemmConvParams& p) {
 template <int BN>
 static int dispatch_epi(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3, const CUtensorMap& w,
                         const CUtensorMap& d, const CUtensorMap& r, const GemmConvParams& p, cudaStream_t st) {
+  if (p.halo) {
+    switch (pick_epi(p)) {
+      case EPI_PLAIN: return launch<BN, EPI_PLAIN, 1, false, true>(a, a2, a3, w, d, r, p, st);
+      case EPI_RESID: return launch<BN, EPI_RESID, 1, false, true>(a, a2, a3, w, d, r, p, st);
+      case EPI_ROWVEC: return launch<BN, EPI_ROWVEC, 1, false, true>(a, a2, a3, w, d, r, p, st);
+      case EPI_RESID_DIRECT: return launch<BN, EPI_RESID_DIRECT, 1, false, true>(a, a2, a3, w, d, r, p, st);
+      default: return I360_ERR_UNSUPPORTED;      // the host only selects HALO for these four epilogues
+    }
+  }
   switch (pick_epi(p)) {
     case EPI_PLAIN: return launch<BN, EPI_PLAIN>(a, a2, a3, w, d, r, p, st);
     case EPI_GEGLU: return launch<BN, EPI_GEGLU>(a, a2, a3, w, d, r, p, st);
@@ -712,6 +794,63 @@ extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long 
   return dispatch(bn, ta, ta, ta, tw, td, tr, p, static_cast<cudaStream_t>(stream));
 }
 
+// HALO mode (fixed 16 x 8 pixel tiles) is used when its padded work is within 4 % of the best free-form pixel box, the
+// input has at least one full 64-channel block, the epilogue is one the halo kernels are instantiated for and there is no
+// fused 1x1 source: those k-steps need a fresh activation tile each, and the two-deep activation ring then exposes the TMA
+// latency (measured: conv2 + shortcut of the 16x512x1024 step 6 % slower).  Measured on one B200 (tools/microbench.py
+// conv): 960->320 at 640x32x32 +7 %, pano 320->320 +6 %, VAE 256->256 +12 %, 512->512 +11 %, 320->320 at 32x32 +-0 %,
+// 640->640 at 32x68 (6 % padded columns) -9 % -> excluded by the 4 % rule.  Inside the 16x512x1024 step (inputs warm in L2
+// after the GroupNorm pass) the 32x32 / 16x16 perspective convs gained nothing (75.9 ms of convs with, 75.1 ms without), the
+// VAE decode of 4 frames went 24.8 -> 23.4 ms: the rule therefore also asks for images of at least 64 x 64 pixels (the
+// VAE, panorama level 0).  I360_CONV_HALO=0 disables it (A/B runs).
+struct HaloPolicy { int on; double tol; int allow_extra; int min_hw; };
+static HaloPolicy& halo_policy() {
+  static HaloPolicy p = {getenv("I360_CONV_HALO") == nullptr || atoi(getenv("I360_CONV_HALO")) != 0,
+                         getenv("I360_CONV_HALO_TOL") ? atof(getenv("I360_CONV_HALO_TOL")) : 1.04,
+                         getenv("I360_CONV_HALO_EXTRA") != nullptr && atoi(getenv("I360_CONV_HALO_EXTRA")) != 0,
+                         getenv("I360_CONV_HALO_MIN_HW") ? atoi(getenv("I360_CONV_HALO_MIN_HW")) : 64};
+  return p;
+}
+static bool use_halo(int H, int W, int Cin, bool resid, bool rowvec, bool extra_sources, double waste_best) {
+  const HaloPolicy& hp = halo_policy();
+  const double waste_h = (double)((W + kHaloTW - 1) / kHaloTW * kHaloTW) * ((H + kHaloTH - 1) / kHaloTH * kHaloTH) / ((double)W * H);
+  return hp.on && !(resid && rowvec) && (hp.allow_extra || !extra_sources) && Cin >= 64 && H >= hp.min_hw && W >= hp.min_hw &&
+         waste_h <= hp.tol * waste_best;
+}
+
+// Selection rule of the halo kernels (see use_halo): on / padded-work tolerance / allow fused 1x1 sources / smallest image
+// side; a negative
+// argument keeps the current value.  For tests (which widen the rule to cover every halo kernel path) and A/B runs.
+extern "C" void i360_conv3x3_halo_policy(int on, double tol, int allow_extra, int min_hw) {
+  HaloPolicy& hp = halo_policy();
+  if (min_hw >= 0) hp.min_hw = min_hw;
+  if (on >= 0) hp.on = on;
+  if (tol >= 0) hp.tol = tol;
+  if (allow_extra >= 0) hp.allow_extra = allow_extra;
+}
+
+static void best_box(int B, int H, int W, int* TW, int* TH, int* TB, double* waste) {
+  int bestTW = 16, bestTH = 8, bestTB = 1; double bestw = 1e30;
+  for (int tw = 1; tw <= 128; tw *= 2)
+    for (int th = 1; tw * th <= 128; th *= 2) {
+      const int tb = 128 / (tw * th);
+      if (tw > 1 && tw / 2 >= W) continue;
+      if (th > 1 && th / 2 >= H) continue;
+      const double w = (double)((W + tw - 1) / tw * tw) * ((H + th - 1) / th * th) *
+                       ((B + tb - 1) / tb * tb) / ((double)W * H * B);
+      const double score = w - 1e-6 * tw;  // ties -> wider rows
+      if (score < bestw) { bestw = score; bestTW = tw; bestTH = th; bestTB = tb; }
+    }
+  *TW = bestTW; *TH = bestTH; *TB = bestTB; *waste = bestw;
+}
+
+// 1 when i360_conv3x3_bf16 would run this problem through the halo-tile kernels (tests / benchmarks ask)
+extern "C" int i360_conv3x3_uses_halo(int B, int H, int W, int Cin, int has_resid, int has_rowvec, int has_extra_sources) {
+  int tw, th, tb; double w;
+  best_box(B, H, W, &tw, &th, &tb, &w);
+  return use_halo(H, W, Cin, has_resid != 0, has_rowvec != 0, has_extra_sources != 0, w + 1e-6 * tw) ? 1 : 0;
+}
+
 // x: NHWC [B,H,W,Cin] (H,W include any materialised halo); Wt: [Cout, 9*Cin + C2 + C3] with the
 // 3x3 part ordered (kh, kw, cin). x2/x3: optional NHWC [B,H,W-2*crop,C2|C3] sources for a fused 1x1
 // (stored WITHOUT the halo, i.e. aligned with the output). Output NHWC [B, H, W-2*crop, Cout].
@@ -727,19 +866,12 @@ extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, co
   // K segments need no 64-alignment: channels past a source's extent are zero-filled by TMA, so whatever
   // weight columns a partial K block overlaps are multiplied by zeros.
   // choose the pixel box minimising padded work
-  int bestTW = 16, bestTH = 8, bestTB = 1; double bestw = 1e30;
-  for (int tw = 1; tw <= 128; tw *= 2)
-    for (int th = 1; tw * th <= 128; th *= 2) {
-      const int tb = 128 / (tw * th);
-      if (tw > 1 && tw / 2 >= W) continue;
-      if (th > 1 && th / 2 >= H) continue;
-      const double waste = (double)((W + tw - 1) / tw * tw) * ((H + th - 1) / th * th) *
-                           ((B + tb - 1) / tb * tb) / ((double)W * H * B);
-      const double score = waste - 1e-6 * tw;  // ties -> wider rows
-      if (score < bestw) { bestw = score; bestTW = tw; bestTH = th; bestTB = tb; }
-    }
+  int bestTW, bestTH, bestTB; double bestw;
+  best_box(B, H, W, &bestTW, &bestTH, &bestTB, &bestw);
   GemmConvParams p;
   memset(&p, 0, sizeof(p));
+  p.halo = use_halo(H, W, Cin, resid != nullptr, rowvec != nullptr, C2 + C3 > 0, bestw + 1e-6 * bestTW);
+  if (p.halo) { bestTW = kHaloTW; bestTH = kHaloTH; bestTB = 1; }
   p.conv = 1; p.B = B; p.H = H; p.W = W; p.TW = bestTW; p.TH = bestTH; p.TB = bestTB;
   p.n_wt = (W + p.TW - 1) / p.TW; p.n_ht = (H + p.TH - 1) / p.TH; p.n_bt = (B + p.TB - 1) / p.TB;
   p.Cin = Cin; p.C2 = C2; p.C3 = C3; p.crop = crop; p.xoff = -crop; p.Hout = H; p.Wout = W - 2 * crop;
@@ -760,7 +892,16 @@ extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, co
     uint32_t b[4] = {BK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
     return get_tmap_bf16(m, ptr, 4, d, s, b, 3);
   };
-  int r = act_map(&ta, x, Cin, W); if (r) return r;
+  int r;
+  if (p.halo) {
+    uint64_t d[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t s[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t b[4] = {BK, (uint32_t)kHaloW, (uint32_t)kHaloH, 1u};
+    r = get_tmap_bf16(&ta, x, 4, d, s, b, 3);
+  } else {
+    r = act_map(&ta, x, Cin, W);
+  }
+  if (r) return r;
   ta2 = ta; ta3 = ta;
   if (C2 > 0) { r = act_map(&ta2, x2, C2, W - 2 * crop); if (r) return r; }
   if (C3 > 0) { r = act_map(&ta3, x3, C3, W - 2 * crop); if (r) return r; }

@@ -187,6 +187,18 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias=None, x2=None, x3=None
     return out
 
 
+def conv3x3_uses_halo(B: int, H: int, W: int, Cin: int, resid: bool = False, rowvec: bool = False, extra: bool = False) -> bool:
+    return bool(lib().i360_conv3x3_uses_halo(c_int(B), c_int(H), c_int(W), c_int(Cin), c_int(int(resid)), c_int(int(rowvec)),
+                                             c_int(int(extra))))
+
+
+def conv3x3_halo_policy(on: int = -1, tol: float = -1.0, allow_extra: int = -1, min_hw: int = -1) -> None:
+    """Selection rule of the halo conv kernels (tests / A-B runs); negative = keep."""
+    f = lib().i360_conv3x3_halo_policy
+    f.restype = None
+    f(c_int(on), ctypes.c_double(tol), c_int(allow_extra), c_int(min_hw))
+
+
 # ------------------------------------------------------------------------------------------------
 # normalisation
 # ------------------------------------------------------------------------------------------------

@@ -67,6 +67,14 @@ int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, const void* x
                       const void* Wt, int Cout, void* D, int crop, const void* bias, const void* resid,
                       const float* rowvec, int rowvec_div, int rowvec_ld, float out_scale, void* stream);
 
+/* 1 when i360_conv3x3_bf16 runs this problem through its halo-tile variant (16 x 8 pixel tiles whose 18 x 10 halo is
+ * loaded once per 64-channel block and shared by the nine taps), 0 for the tap-by-tap variant.  Informational. */
+int i360_conv3x3_uses_halo(int B, int H, int W, int Cin, int has_resid, int has_rowvec, int has_extra_sources);
+/* Selection rule of the halo variant: enabled / padded-work tolerance against the best free-form pixel box (default
+ * 1.04) / allow fused 1x1 sources (default 0) / smallest image side (default 64); a negative argument keeps the current
+ * value.  Tests and A/B runs only. */
+void i360_conv3x3_halo_policy(int on, double tol, int allow_extra, int min_hw);
+
 /* GroupNorm statistics / application over a virtual tensor = concat(x1, x2) along C, circularly padded by `pad`
  * columns.  Replaces InflatedGroupNorm / nn.GroupNorm (+ SiLU) (animatediff/models/resnet.py:9-17,:224-225,:243)
  * together with torch.cat (MVGenModel.py:399) and pad_pano (src/utils/pano.py:75-92).  stats: [B, groups, 2] fp64. */

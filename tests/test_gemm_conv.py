@@ -112,6 +112,57 @@ def test_conv3x3_fused_shortcut_temb_crop():
     _close(out, ref, "fused conv")
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,mode", [
+    (2, 32, 32, 320, 320, "bias"), (2, 32, 32, 320, 320, "resid"), (4, 32, 32, 320, 320, "rowvec"), (1, 64, 136, 128, 128, "bias"),
+    (2, 32, 36, 192, 160, "resid"), (2, 16, 16, 640, 640, "bias"), (1, 64, 136, 128, 8, "bias"), (2, 64, 136, 320, 320, "crop"),
+    (2, 32, 72, 640, 320, "shortcut_crop"), (3, 48, 40, 72, 256, "bias"), (1, 128, 272, 256, 256, "resid"),
+])
+def test_conv3x3_halo_tiles(B, H, W, Cin, Cout, mode):
+    """The halo-tile variant (one 18 x 10 TMA box per 64-channel block shared by the nine taps, shifted UMMA descriptors):
+    every epilogue it is instantiated for, W / H tails, a partial last channel block, the cropped pano output."""
+    from imagine360_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + H + W + Cin + Cout)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    x = rn(B, H, W, Cin).bfloat16()
+    w = (rn(Cout, Cin, 3, 3) / (9 * Cin) ** 0.5).bfloat16()
+    bias = rn(Cout).bfloat16()
+    crop = 2 if "crop" in mode else 0
+    kw, ref = {}, F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias.float(), padding=1)
+    if crop:
+        ref = ref[..., crop:-crop]
+    wp = ops.pack_conv3x3(w)
+    if mode in ("resid", "crop"):
+        kw["resid"] = rn(B, H, W - 2 * crop, Cout).bfloat16()
+        ref = ref + kw["resid"].float().permute(0, 3, 1, 2)
+    if mode == "rowvec":
+        kw["rowvec"], kw["rowvec_div"] = rn(B // 2, Cout), 2
+        ref = ref + kw["rowvec"].repeat_interleave(2, 0)[:, :, None, None]
+    if mode == "shortcut_crop":
+        x2, x3 = rn(B, H, W - 2 * crop, 64).bfloat16(), rn(B, H, W - 2 * crop, 96).bfloat16()
+        ws = (rn(Cout, 160, 1, 1) / 160 ** 0.5).bfloat16()
+        wp = ops.pack_conv3x3(w, ws)
+        kw.update(x2=x2, x3=x3)
+        ref = ref + F.conv2d(torch.cat([x2, x3], -1).float().permute(0, 3, 1, 2), ws.float())
+    # W / H tails and the fused 1x1 sources are outside the production selection rule: widen it for this test so that
+    # those kernel paths stay covered
+    ops.conv3x3_halo_policy(1, 1.5, 1, 0)
+    try:
+        assert ops.conv3x3_uses_halo(B, H, W, Cin, "resid" in kw, "rowvec" in kw, "x2" in kw), "meant to take the halo kernels"
+        out = ops.conv3x3(x, wp, bias=bias, crop=crop, **kw)
+        out2 = ops.conv3x3(x, wp, bias=bias, crop=crop, **kw)
+    finally:
+        ops.conv3x3_halo_policy(1, 1.04, 0, 64)
+    _close(out, ref.permute(0, 2, 3, 1), f"halo conv {mode} {B}x{H}x{W} {Cin}->{Cout}")
+    assert torch.equal(out, out2)
+    # the tap-by-tap kernels on the same problem agree to accumulation-order noise
+    ops.conv3x3_halo_policy(0)
+    try:
+        out3 = ops.conv3x3(x, wp, bias=bias, crop=crop, **kw)
+    finally:
+        ops.conv3x3_halo_policy(1)
+    _close(out3, ref.permute(0, 2, 3, 1), f"tap conv {mode} {B}x{H}x{W} {Cin}->{Cout}")
+
+
 @pytest.mark.parametrize("M,N,K,act,pe", [(1000, 960, 320, 0, False), (777, 320, 320, 0, False), (513, 2560, 320, 1, False),
                                           (300, 3840, 1280, 0, True), (4100, 1920, 640, 0, True), (129, 1280, 1280, 0, False),
                                           (2000, 5120, 640, 1, False), (64, 960, 320, 0, True)])
