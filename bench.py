@@ -507,7 +507,7 @@ def kernel_roofline(pipe, inp, size, one_step):
     records = []
     orig_gemm, orig_conv = ops.gemm, ops.conv3x3
     L = ops.lib()
-    names = ["i360_gemm_bf16", "i360_conv3x3_bf16", "i360_attention_bf16", "i360_cross_attention_text_ip_bf16", "i360_temporal_attention_bf16", "i360_groupnorm_stats",
+    names = ["i360_gemm_bf16", "i360_gemm_rowstats_bf16", "i360_gemm_ln_bf16", "i360_conv3x3_bf16", "i360_attention_bf16", "i360_cross_attention_text_ip_bf16", "i360_temporal_attention_bf16", "i360_groupnorm_stats",
              "i360_groupnorm_apply", "i360_layernorm", "i360_upsample2x_nhwc", "i360_im2col3x3_s2_nhwc", "i360_axpby_bf16",
              "i360_cfg_ddim_step_bf16", "i360_avgpool_frames4_bf16", "i360_grid_sample_f32", "i360_softmax_rows_bf16"]
     timed = {}
@@ -528,14 +528,24 @@ def kernel_roofline(pipe, inp, size, one_step):
     shapes = []     # (kind, M, N, K, act, index into timed[name])
 
     def gemm(a, w, *args, **kw):
+        name = "i360_gemm_rowstats_bf16" if kw.get("rowstats") else "i360_gemm_bf16"
         flops["gemm"] += 2.0 * a.shape[0] * w.shape[0] * a.shape[1]
-        shapes.append(("gemm", a.shape[0], w.shape[0], a.shape[1], kw.get("act", 0), len(timed.get("i360_gemm_bf16", []))))
+        shapes.append(("gemm+stats" if kw.get("rowstats") else "gemm", a.shape[0], w.shape[0], a.shape[1], kw.get("act", 0),
+                       (name, len(timed.get(name, [])))))
         return orig_gemm(a, w, *args, **kw)
+
+    orig_gemm_ln = ops.gemm_ln
+
+    def gemm_ln(a, stats, wf, *args, **kw):       # LayerNorm folded into the projection: same 2*M*N*K
+        flops["gemm"] += 2.0 * a.shape[0] * wf.shape[0] * a.shape[1]
+        shapes.append(("ln+gemm", a.shape[0], wf.shape[0], a.shape[1], kw.get("act", 0),
+                       ("i360_gemm_ln_bf16", len(timed.get("i360_gemm_ln_bf16", [])))))
+        return orig_gemm_ln(a, stats, wf, *args, **kw)
 
     def conv(x, wp, *args, **kw):
         b, h, wd, _ = x.shape
         flops["conv"] += 2.0 * b * h * wd * wp.shape[0] * wp.shape[1]
-        shapes.append(("conv", b * h * wd, wp.shape[0], wp.shape[1], 0, len(timed.get("i360_conv3x3_bf16", []))))
+        shapes.append(("conv", b * h * wd, wp.shape[0], wp.shape[1], 0, ("i360_conv3x3_bf16", len(timed.get("i360_conv3x3_bf16", [])))))
         return orig_conv(x, wp, *args, **kw)
 
     orig_attn = ops.attention
@@ -543,7 +553,7 @@ def kernel_roofline(pipe, inp, size, one_step):
     def attn(q, k, v, o, heads, head_dim, batch, scale=None, bias=None, accumulate=False):
         nq, nk = q.d1 * max(1, q.ext3), k.d1 * max(1, k.ext3)
         shapes.append(("attn", f"batch={batch} heads={heads} hd={head_dim} Nq={nq} Nk={nk} bias={int(bias is not None)} acc={int(accumulate)}",
-                       4.0 * batch * heads * nq * nk * head_dim, 0, 0, len(timed.get("i360_attention_bf16", []))))
+                       4.0 * batch * heads * nq * nk * head_dim, 0, 0, ("i360_attention_bf16", len(timed.get("i360_attention_bf16", [])))))
         return orig_attn(q, k, v, o, heads, head_dim, batch, scale=scale, bias=bias, accumulate=accumulate)
 
     class LibProxy:
@@ -553,17 +563,17 @@ def kernel_roofline(pipe, inp, size, one_step):
 
     proxy = LibProxy()
     orig_lib = ops.lib
-    ops.lib, ops.gemm, ops.conv3x3, ops.attention = (lambda: proxy), gemm, conv, attn
-    import imagine360_b200.host.forward as Fw
+    ops.lib, ops.gemm, ops.conv3x3, ops.attention, ops.gemm_ln = (lambda: proxy), gemm, conv, attn, gemm_ln
     try:
         one_step(7)
         torch.cuda.synchronize()
     finally:
-        ops.lib, ops.gemm, ops.conv3x3, ops.attention = orig_lib, orig_gemm, orig_conv, orig_attn
+        ops.lib, ops.gemm, ops.conv3x3, ops.attention, ops.gemm_ln = orig_lib, orig_gemm, orig_conv, orig_attn, orig_gemm_ln
     per = {n: (len(v), sum(a.elapsed_time(b) for a, b in v)) for n, v in timed.items()}
     total = sum(ms for _, ms in per.values())
-    gc_ms = per.get("i360_gemm_bf16", (0, 0))[1] + per.get("i360_conv3x3_bf16", (0, 0))[1]
-    gc_n = per.get("i360_gemm_bf16", (0, 0))[0] + per.get("i360_conv3x3_bf16", (0, 0))[0]
+    engine = ("i360_gemm_bf16", "i360_gemm_rowstats_bf16", "i360_gemm_ln_bf16", "i360_conv3x3_bf16")   # one kernel template
+    gc_ms = sum(per.get(n, (0, 0))[1] for n in engine)
+    gc_n = sum(per.get(n, (0, 0))[0] for n in engine)
     pk = peaks()
     achieved = (flops["gemm"] + flops["conv"]) / (gc_ms * 1e-3) / 1e12 if gc_ms > 0 else 0.0
     roof = {"kernel": "gemm_conv_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)", "bound": "tensor", "achieved": round(achieved, 1),
@@ -586,11 +596,10 @@ def kernel_roofline(pipe, inp, size, one_step):
     breakdown = {n: {"launches": c, "ms": round(ms, 3)} for n, (c, ms) in sorted(per.items(), key=lambda kv: -kv[1][1])}
     agg = {}
     for kind, M, N, K, act, idx in shapes:
+        ev = timed[idx[0]][idx[1]]
         if kind == "attn":
-            ev = timed["i360_attention_bf16"][idx]
             key, f1 = f"attn {M}", N
         else:
-            ev = timed["i360_gemm_bf16" if kind == "gemm" else "i360_conv3x3_bf16"][idx]
             key, f1 = f"{kind} M={M} N={N} K={K} act={act}", 2.0 * M * N * K
         c, ms, fl = agg.get(key, (0, 0.0, 0.0))
         agg[key] = (c + 1, ms + ev[0].elapsed_time(ev[1]), fl + f1)

@@ -58,14 +58,22 @@ struct GemmConvParams {
   float out_scale;
   int n_out;          // logical output columns (GEGLU: N/2)
   int rowvec_mod;     // > 0: rowvec row = (row / rowvec_div) % rowvec_mod  (temporal PE: frame of a (b, f, d) row)
+  int rowvec_in_table; // LNF: every row of a tile maps to the same rowvec row (rowvec_div % 128 == 0): the vector is folded
+                      // into the tile's smem bias table instead of being re-read by every thread for every chunk
   // LayerNorm folded into the GEMM (LNF kernels): D = rstd_r * (A W'^T - mean_r * u) + c, W' = W * gamma (per column
-  // of K), u[n] = sum_k W'[n,k], c[n] = sum_k beta[k] W[n,k] + bias[n]; row statistics are taken from the A tiles in smem
+  // of K), u[n] = sum_k W'[n,k], c[n] = sum_k beta[k] W[n,k] + bias[n]; the row statistics come from the GEMM that
+  // PRODUCED A (its epilogue wrote partial sums per row, see rowstats)
   const float* ln_u; const float* ln_c; float ln_eps;
+  const float2* ln_stats; int ln_slots;   // [ln_slots][M] partial (sum, sum of squares) of every A row, written by the producer
+  // producer side of the fold: this GEMM also writes, per output row, the (sum, sum of squares) of the values it stores,
+  // one partial per (N tile, epilogue group) slot: rowstats[slot * M + row]
+  float2* rowstats;
 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 320;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue (two groups of 4)
+constexpr int kMaxStatSlots = 10; // row-statistics slots a LayerNorm-folding GEMM can consume (5 N tiles x 2 epilogue groups)
 
 // MT: M sub-tiles per CTA tile (1 or 2).  MT = 2 (GEMM mode, BN = 128 only) computes a 256 x 128 tile as two 128-row
 // accumulators that share the weight tile in smem: 683 instead of 569 FLOP per byte loaded from L2 for the N = 640 /
@@ -97,7 +105,7 @@ template <int BN, bool RING = false, int MT = 1, bool LNF = false, bool HALO = f
   static constexpr bool kBiasTable = BN >= 160;
   static_assert(!LNF || kBiasTable, "the LayerNorm-folding epilogue reads c and u from the smem tables");
   static constexpr int kTableBytes = kBiasTable ? (LNF ? 4 : 2) * BN * 4 : 0;       // [group][BN] bias (LNF: c), then [group][BN] u
-  static constexpr int kStatBytes = LNF ? 2 * MT * BM * 8 : 0;                        // [acc stage][row] (rstd, -mean * rstd)
+  static constexpr int kStatBytes = 0;
   // dynamic smem is declared __align__(1024) (checked at run time), so no alignment slack is reserved
   static constexpr int kBudget = 227 * 1024 - kNumStg * kStgBytes - kTableBytes - kStatBytes - 256 - kHaloTotal;
   static constexpr int kMaxStages = HALO ? 6 : 8;
@@ -118,13 +126,16 @@ enum : int { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_RESID = 2, EPI_ROWVEC = 3, EPI_AC
 // Ring or not is a compile-time property, so the ring kernels carry no (predicated-off) direct-read instructions.
 template <int BN, int EPI> struct UseRing { static constexpr bool value = (EPI == EPI_RESID) && (BN <= 192); };
 
-// LNF: LayerNorm folded into the GEMM.  Four extra warps (10..13) read every A tile from smem next to the tensor core
-// (row sums and sums of squares; a row of the token matrix is exactly the K extent), publish (rstd, -mean * rstd) per
-// row and accumulator stage, and the epilogue applies  rstd * acc - mean * rstd * u[n] + c[n].  The normalised
-// activations are never written to or read from HBM: the LayerNorm pass (one read + one write of the token matrix per
-// norm, 192 launches and ~13 ms of the 16x512x1024 step) disappears.
+// LNF: LayerNorm folded into the GEMM.  The GEMM that produced the token matrix A wrote, from its epilogue, the partial
+// (sum, sum of squares) of every row it stored (GemmConvParams::rowstats: one slot per N tile and epilogue group, no
+// atomics, so the result is deterministic); the epilogue here adds the slots of its row, forms mean / rstd and applies
+//   rstd * acc - mean * rstd * u[n] + c[n].
+// The normalised activations are never written to or read from HBM: the LayerNorm pass (one read + one write of the
+// token matrix per norm, 192 launches and ~13 ms of the 16x512x1024 step) disappears.  (A first version took the
+// statistics from the A tiles in shared memory with four extra warps; they competed with the epilogue warps for issue
+// slots and the step got 9 ms slower -- see git history / profiles/r02_bench_c3_ln_fold_on.json.)
 template <int BN, int EPI, int MT = 1, bool LNF = false, bool HALO = false>
-__global__ void __launch_bounds__(kThreads + (LNF ? 128 : 0), 1)
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
@@ -139,7 +150,6 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* stg = smem + C::kStages * C::kStageBytes;            // 2 staging buffers (1024-aligned)
   float* sbias = reinterpret_cast<float*>(stg + C::kNumStg * C::kStgBytes);   // [2 groups][BN] (kBiasTable only)
   float* su = sbias + 2 * BN;                                                  // [2 groups][BN] (LNF only)
-  float2* sstat = reinterpret_cast<float2*>(stg + C::kNumStg * C::kStgBytes + C::kTableBytes);   // [2][MT * BM] (LNF only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg + C::kNumStg * C::kStgBytes + C::kTableBytes + C::kStatBytes);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + C::kStages;         // [kStages]
@@ -147,7 +157,6 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty = bars + 2 * C::kStages + 2;// [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
   uint64_t* rbar = bars + 2 * C::kStages + 5;   // [2 groups][4]: residual chunk landed in staging buffer
-  uint64_t* sfull = rbar + 8;                   // [2] (LNF): row statistics of the tile in accumulator stage s published
   uint64_t* afull = rbar + 8;                   // [2] (HALO, never together with LNF): halo tile landed
   uint64_t* aempty = rbar + 10;                 // [2] (HALO): the nine taps that read the halo tile have retired
 
@@ -158,8 +167,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmD);
     if (p.C2 > 0) tma_prefetch_desc(&tmA2);
     if (p.C3 > 0) tma_prefetch_desc(&tmA3);
-    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], LNF ? 5 : 1); }   // LNF: MMA + 4 stats warps
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); if (LNF) mbar_init(&sfull[s], 4); }
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     if (kRing) { for (int s = 0; s < 8; ++s) mbar_init(&rbar[s], 1); tma_prefetch_desc(&tmR); }
     if (HALO) { for (int s = 0; s < kHaloStages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); } }
     fence_barrier_init();
@@ -287,48 +296,6 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else if (LNF && warp >= 10) {
-    // =============================== row statistics (warps 10..13, LNF) ===============================
-    // thread r owns row r (and r + 128 for MT = 2) of every A tile: 8 x 16-byte reads per k block in swizzle order
-    // (lane l of a quarter-warp reads chunk i ^ (r & 7): conflict-free), fp32 sum and sum of squares over the K extent.
-    const int r = (warp - 10) * 32 + lane;
-    const float inv_k = 1.0f / static_cast<float>(p.K);
-    int stage = 0; uint32_t phase = 0;
-    int as = 0; uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      float2 acc[MT][2];
-#pragma unroll
-      for (int m = 0; m < MT; ++m) { acc[m][0] = make_float2(0.f, 0.f); acc[m][1] = make_float2(0.f, 0.f); }
-      for (int kb = 0; kb < p.k_iters; ++kb) {
-        mbar_wait(&full[stage], phase);
-        const uint8_t* sa = smem + stage * C::kStageBytes;
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          const uint8_t* rowp = sa + (m * BM + r) * (BK * 2);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint4 x = *reinterpret_cast<const uint4*>(rowp + ((static_cast<uint32_t>(i) ^ (r & 7)) << 4));
-            const float2 a = unpack_bf16x2(x.x), b = unpack_bf16x2(x.y), c = unpack_bf16x2(x.z), d = unpack_bf16x2(x.w);
-            acc[m][0] = fadd2(acc[m][0], fadd2(fadd2(a, b), fadd2(c, d)));
-            acc[m][1] = ffma2(a, a, ffma2(b, b, ffma2(c, c, ffma2(d, d, acc[m][1]))));
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);      // this warp is done with the stage (the MMA commit is the 5th arrival)
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
-      }
-      mbar_wait(&tempty[as], aphase ^ 1);               // the epilogue that read this statistics slot two tiles ago is done
-#pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        const float mean = (acc[m][0].x + acc[m][0].y) * inv_k;
-        const float var = fmaxf((acc[m][1].x + acc[m][1].y) * inv_k - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + p.ln_eps);
-        sstat[as * (MT * BM) + m * BM + r] = make_float2(rstd, -mean * rstd);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sfull[as]);
-      if (++as == 2) { as = 0; aphase ^= 1; }
-    }
   } else {
     // =============================== epilogue (warps 2..9) ===============================
     // TMEM -> registers -> (bias / temb / activation / residual) -> bf16 -> swizzled smem -> TMA tensor store.
@@ -391,6 +358,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           nu0 = (c0 < p.N) ? p.ln_u[c0] : 0.f;
           nb1 = (gtid + 128 < BN && c0 + 128 < p.N) ? p.ln_c[c0 + 128] : 0.f;
           nu1 = (gtid + 128 < BN && c0 + 128 < p.N) ? p.ln_u[c0 + 128] : 0.f;
+          if (p.rowvec_in_table) {
+            const float* rvp = p.rowvec + static_cast<long long>((((tt / p.n_tiles) * (BM * MT)) / p.rowvec_div) % p.rowvec_mod) * p.rowvec_ld;
+            if (c0 < p.N) nb0 += rvp[c0];
+            if (gtid + 128 < BN && c0 + 128 < p.N) nb1 += rvp[c0 + 128];
+          }
         } else {
           nb0 = (has_bias && c0 < p.N) ? __bfloat162float(p.bias[c0]) : 0.f;
           nb1 = (has_bias && gtid + 128 < BN && c0 + 128 < p.N) ? __bfloat162float(p.bias[c0 + 128]) : 0.f;
@@ -398,6 +370,15 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     };
     if (C::kBiasTable && (has_bias || kGeglu || LNF)) load_bias(blockIdx.x);
+    float2 pst[kMaxStatSlots];                           // LNF: row-statistics slots of my row of the NEXT tile
+    auto load_stats = [&](int tt) {
+      if (!LNF) return;
+      const long long r = (tt < total_tiles) ? static_cast<long long>(tt / p.n_tiles) * (BM * MT) + row_off + row : p.M;
+#pragma unroll
+      for (int sl = 0; sl < kMaxStatSlots; ++sl)
+        pst[sl] = (r < p.M && sl < p.ln_slots) ? __ldg(p.ln_stats + static_cast<long long>(sl) * p.M + r) : make_float2(0.f, 0.f);
+    };
+    load_stats(blockIdx.x);
     int as = 0; uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
@@ -441,17 +422,25 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         named_bar_sync(1 + grp, 128);
         load_bias(t + gridDim.x);                      // lands under this tile's chunks
       }
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
       float2 rstd2 = make_float2(1.f, 1.f), nmr2 = make_float2(0.f, 0.f);     // LNF: rstd and -mean * rstd of my row
       if (LNF) {
-        mbar_wait(&sfull[as], aphase);
-        const float2 st = sstat[as * (MT * BM) + row_off + row];
-        rstd2 = make_float2(st.x, st.x); nmr2 = make_float2(st.y, st.y);
+        // the partial sums of this row were requested one tile ago (a global-load latency per tile on the epilogue's
+        // critical path cost more than the LayerNorm pass saved); the next tile's are requested right away
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < kMaxStatSlots; ++sl) { s1 += pst[sl].x; s2 += pst[sl].y; }
+        load_stats(t + gridDim.x);
+        const float inv_k = 1.0f / static_cast<float>(p.K);
+        const float mean = s1 * inv_k;
+        const float rstd = rsqrtf(fmaxf(s2 * inv_k - mean * mean, 0.f) + p.ln_eps);
+        rstd2 = make_float2(rstd, rstd); nmr2 = make_float2(-mean * rstd, -mean * rstd);
       }
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * C::kAccCols + (MT == 2 ? grp * BN : 0);
       constexpr int n_chunks = kGeglu ? (BN / 2) / CH : BN / CH;
       const int oc0 = kGeglu ? n_blk * (BN / 2) : n_blk * BN;     // first OUTPUT column of this tile
+      float2 rs1 = make_float2(0.f, 0.f), rs2 = make_float2(0.f, 0.f);   // row statistics of the values this thread stores
 
 #pragma unroll 1
       for (int ci = ci_first; ci < n_chunks; ci += kCiStep) {
@@ -587,6 +576,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 16; ++j) f2[j] = fmul2(f2[j], sc);
           }
+          if (!kGeglu && !LNF && p.rowstats != nullptr) {     // producer side of the LayerNorm fold (columns past N are zeros)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { rs1 = fadd2(rs1, f2[j]); rs2 = ffma2(f2[j], f2[j], rs2); }
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const uint4 packed = make_uint4(pack_bf16x2(f2[g * 4 + 0].x, f2[g * 4 + 0].y), pack_bf16x2(f2[g * 4 + 1].x, f2[g * 4 + 1].y),
@@ -621,6 +614,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
+      if (!kGeglu && !LNF && p.rowstats != nullptr && !p.conv && valid) {
+        const int slot = (MT == 2) ? n_blk : n_blk * 2 + grp;
+        p.rowstats[static_cast<long long>(slot) * p.M + orow] = make_float2(rs1.x + rs1.y, rs2.x + rs2.y);
+      }
     }
     if (store_thread) bulk_wait<0>();
   }
@@ -649,7 +646,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms()) grid = num_sms();
   if (grid <= 0) return I360_OK;
-  gemm_conv_kernel<BN, EPI, MT, LNF, HALO><<<grid, kThreads + (LNF ? 128 : 0), C::kSmemBytes, st>>>(a, a2, a3, w, d, rmap, p);
+  gemm_conv_kernel<BN, EPI, MT, LNF, HALO><<<grid, kThreads, C::kSmemBytes, st>>>(a, a2, a3, w, d, rmap, p);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -743,24 +740,40 @@ using namespace i360;
 // rows followed by the BN/2 matching gate rows; i360_gemm_geglu_block(N) returns that BN.
 extern "C" int i360_gemm_geglu_block(int n_total) { return pick_bn(n_total, 1); }
 
-extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* D,
-                              long long ldd, int M, int N, int K, const void* bias,
-                              const void* resid, long long ldr, const float* rowvec, int rowvec_div,
-                              int rowvec_ld, int act, float out_scale, void* stream) {
-  if (!A || !W || !D || M <= 0 || N <= 0 || K <= 0) return I360_ERR_ARG;
-  if ((K % 8) || (lda % 8) || (ldw % 8) || (ldd % 8) || (N % 8)) return I360_ERR_ARG;
-  if (resid && (ldr % 8)) return I360_ERR_ARG;
-  if (act == 1 && (N % 128)) return I360_ERR_ARG;
-  if (act == 1 && (resid || rowvec)) return I360_ERR_UNSUPPORTED;
+// tile plan of a GEMM call: N tile width and whether the 256 x 128 (two M sub-tiles) variant runs
+static void plan_gemm(int M, int N, int K, int act, bool has_rowvec, bool has_resid, float out_scale, int* bn_out, bool* mt2_out) {
   int bn = pick_bn(N, act);
   // 256 x 128 tiles (two M sub-tiles sharing the weight tile) for the L2-bound mid-size projections: N a multiple of
   // 128 but not of 256 (640, 1920), K >= 512, plain / bias / bias + residual epilogues, enough rows to fill the GPU
   // Measured against the 160 / 192-wide tiles on one box: N = 640: -2..-5 % (K = 640 and 2560, with and without the
   // residual ring); N = 1920: -3 % without, +5 % with a residual (3-stage ring) -> not used there.  I360_GEMM_MT2=0 disables.
   static const bool mt2_on = getenv("I360_GEMM_MT2") == nullptr || atoi(getenv("I360_GEMM_MT2")) != 0;
-  const bool mt2 = mt2_on && act == 0 && !rowvec && out_scale == 1.0f && (N % 128 == 0) && (N % 256 != 0) && N >= 640 && K >= 512 &&
-                   M >= 256 * 148 && !(resid && N > 640) && !bn_override(N);
+  const bool mt2 = mt2_on && act == 0 && !has_rowvec && out_scale == 1.0f && (N % 128 == 0) && (N % 256 != 0) && N >= 640 && K >= 512 &&
+                   M >= 256 * 148 && !(has_resid && N > 640) && !bn_override(N);
   if (mt2) bn = 128;
+  *bn_out = bn; *mt2_out = mt2;
+}
+
+// number of row-statistics slots i360_gemm_rowstats_bf16 writes for this problem (the caller allocates slots * M float2)
+extern "C" int i360_gemm_rowstats_slots(int M, int N, int K, int has_resid) {
+  int bn; bool mt2;
+  plan_gemm(M, N, K, 0, false, has_resid != 0, 1.0f, &bn, &mt2);
+  const int n_tiles = (N + bn - 1) / bn;
+  return mt2 ? n_tiles : 2 * n_tiles;
+}
+
+static int gemm_impl(const void* A, long long lda, const void* W, long long ldw, void* D,
+                     long long ldd, int M, int N, int K, const void* bias,
+                     const void* resid, long long ldr, const float* rowvec, int rowvec_div,
+                     int rowvec_ld, int act, float out_scale, float* rowstats, void* stream) {
+  if (!A || !W || !D || M <= 0 || N <= 0 || K <= 0) return I360_ERR_ARG;
+  if ((K % 8) || (lda % 8) || (ldw % 8) || (ldd % 8) || (N % 8)) return I360_ERR_ARG;
+  if (resid && (ldr % 8)) return I360_ERR_ARG;
+  if (act == 1 && (N % 128)) return I360_ERR_ARG;
+  if (act == 1 && (resid || rowvec)) return I360_ERR_UNSUPPORTED;
+  if (rowstats && (act != 0 || rowvec || out_scale != 1.0f)) return I360_ERR_UNSUPPORTED;
+  int bn; bool mt2;
+  plan_gemm(M, N, K, act, rowvec != nullptr, resid != nullptr, out_scale, &bn, &mt2);
   const int bm = mt2 ? 2 * BM : BM;
   GemmConvParams p;
   memset(&p, 0, sizeof(p));
@@ -771,6 +784,7 @@ extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long 
   p.resid = static_cast<const bf16*>(resid); p.ldr = ldr;
   p.rowvec = rowvec; p.rowvec_div = rowvec_div > 0 ? rowvec_div : 1; p.rowvec_ld = rowvec_ld;
   p.act = act; p.out_scale = out_scale; p.n_out = (act == 1) ? N / 2 : N;
+  p.rowstats = reinterpret_cast<float2*>(rowstats);
   CUtensorMap ta, tw;
   uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}; uint64_t sA[1] = {(uint64_t)lda * 2};
   uint32_t bA[2] = {BK, (uint32_t)bm};
@@ -792,6 +806,23 @@ extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long 
     return launch<128, EPI_PLAIN, 2>(ta, ta, ta, tw, td, tr, p, static_cast<cudaStream_t>(stream));
   }
   return dispatch(bn, ta, ta, ta, tw, td, tr, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int i360_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* D,
+                              long long ldd, int M, int N, int K, const void* bias,
+                              const void* resid, long long ldr, const float* rowvec, int rowvec_div,
+                              int rowvec_ld, int act, float out_scale, void* stream) {
+  return gemm_impl(A, lda, W, ldw, D, ldd, M, N, K, bias, resid, ldr, rowvec, rowvec_div, rowvec_ld, act, out_scale, nullptr, stream);
+}
+
+// D = A W^T + bias (+ resid), and additionally rowstats[slot * M + r] = (sum, sum of squares) over the columns of row r
+// this (N tile, epilogue group) slot stored, for slot < i360_gemm_rowstats_slots(M, N, K, resid != NULL): the producer
+// half of the LayerNorm fold (i360_gemm_ln_bf16 consumes it).
+extern "C" int i360_gemm_rowstats_bf16(const void* A, long long lda, const void* W, long long ldw, void* D, long long ldd,
+                                       int M, int N, int K, const void* bias, const void* resid, long long ldr,
+                                       float* rowstats, void* stream) {
+  if (!rowstats) return I360_ERR_ARG;
+  return gemm_impl(A, lda, W, ldw, D, ldd, M, N, K, bias, resid, ldr, nullptr, 1, 0, 0, 1.0f, rowstats, stream);
 }
 
 // HALO mode (fixed 16 x 8 pixel tiles) is used when its padded work is within 4 % of the best free-form pixel box, the
@@ -929,9 +960,9 @@ extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, co
 // (row / rowvec_div) % rowvec_mod -- the temporal module's PE term (LN(x) + pe_f) W^T = LN(x) W^T + (pe W^T)[f].
 // Replaces nn.LayerNorm followed by nn.Linear (animatediff/models/attention.py:463-508, motion_module.py:247-259,:350).
 extern "C" int i360_gemm_ln_bf16(const void* A, long long lda, const void* Wf, long long ldw, void* D, long long ldd, int M,
-                                 int N, int K, const float* u, const float* c, float eps, const float* rowvec,
-                                 int rowvec_div, int rowvec_mod, int rowvec_ld, int act, void* stream) {
-  if (!A || !Wf || !D || !u || !c || M <= 0 || N <= 0 || K <= 0) return I360_ERR_ARG;
+                                 int N, int K, const float* u, const float* c, float eps, const float* rowstats, int slots,
+                                 const float* rowvec, int rowvec_div, int rowvec_mod, int rowvec_ld, int act, void* stream) {
+  if (!A || !Wf || !D || !u || !c || !rowstats || slots <= 0 || slots > kMaxStatSlots || M <= 0 || N <= 0 || K <= 0) return I360_ERR_ARG;
   if ((K % 64) || (lda % 8) || (ldw % 8) || (ldd % 8) || (N % 8)) return I360_ERR_ARG;
   if (act != 0 && act != 1) return I360_ERR_UNSUPPORTED;
   if (act == 1 && ((N % 256) || rowvec)) return I360_ERR_UNSUPPORTED;
@@ -944,7 +975,7 @@ extern "C" int i360_gemm_ln_bf16(const void* A, long long lda, const void* Wf, l
   p.D = static_cast<bf16*>(D); p.ldd = ldd;
   p.rowvec = rowvec; p.rowvec_div = rowvec_div > 0 ? rowvec_div : 1; p.rowvec_ld = rowvec_ld; p.rowvec_mod = rowvec_mod;
   p.act = act; p.out_scale = 1.0f; p.n_out = (act == 1) ? N / 2 : N;
-  p.ln_u = u; p.ln_c = c; p.ln_eps = eps;
+  p.ln_u = u; p.ln_c = c; p.ln_eps = eps; p.ln_stats = reinterpret_cast<const float2*>(rowstats); p.ln_slots = slots;
   CUtensorMap ta, tw, td;
   uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}; uint64_t sA[1] = {(uint64_t)lda * 2};
   uint32_t bA[2] = {BK, (uint32_t)BM};
@@ -957,7 +988,9 @@ extern "C" int i360_gemm_ln_bf16(const void* A, long long lda, const void* Wf, l
   r = get_tmap_bf16(&td, D, 2, dD, sD, bD, 2); if (r) return r;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (act == 1) return launch<256, EPI_GEGLU, 1, true>(ta, ta, ta, tw, td, td, p, st);
-  if (rowvec) {
+  // temporal PE term: when the 128 rows of a tile share one frame the vector rides in the tile's bias table (plain epilogue)
+  p.rowvec_in_table = (rowvec && rowvec_mod > 0 && (p.rowvec_div % BM) == 0) ? 1 : 0;
+  if (rowvec && !p.rowvec_in_table) {
     switch (bn) {
       case 160: return launch<160, EPI_ROWVEC, 1, true>(ta, ta, ta, tw, td, td, p, st);
       case 192: return launch<192, EPI_ROWVEC, 1, true>(ta, ta, ta, tw, td, td, p, st);

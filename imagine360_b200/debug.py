@@ -4,7 +4,7 @@ through plain torch-CUDA math instead of the sm_100a kernels, to localise a nume
     I360_REFERENCE_OPS=attention,groupnorm python ...        # or:  with debug.reference_ops("gemm"): ...
 
 This is a DEBUGGING tool and not a fallback: nothing in the product imports this module, the switch is off unless asked
-for, it still needs the GPU, and it is orders of magnitude slower.  Switchable: gemm, conv3x3, groupnorm, layernorm,
+for, it still needs the GPU, and it is orders of magnitude slower.  Switchable: gemm (with the LayerNorm-folding gemm_ln), conv3x3, groupnorm, layernorm,
 attention, temporal_attention, cfg_ddim_step."""
 from __future__ import annotations
 
@@ -19,7 +19,7 @@ from . import ops
 BF16 = torch.bfloat16
 
 
-def _gemm(a, w, bias=None, resid=None, rowvec=None, rowvec_div=1, act=ops.ACT_NONE, out_scale=1.0, out=None):
+def _gemm(a, w, bias=None, resid=None, rowvec=None, rowvec_div=1, act=ops.ACT_NONE, out_scale=1.0, out=None, rowstats=False):
     y = a.float() @ w.float().t()
     if bias is not None:
         y = y + bias.float()
@@ -36,7 +36,31 @@ def _gemm(a, w, bias=None, resid=None, rowvec=None, rowvec_div=1, act=ops.ACT_NO
         y = F.silu(y)
     if resid is not None:
         y = y + resid.float()
-    y = (y * out_scale).to(BF16)
+    yf = y * out_scale
+    y = yf.to(BF16)
+    if out is not None:
+        out.copy_(y)
+        y = out
+    if rowstats:        # one slot: (sum, sum of squares) of the fp32 values, like the kernel's epilogue
+        return y, ops.RowStats(torch.stack([yf.sum(1), (yf * yf).sum(1)], -1)[None].contiguous(), 1, y)
+    return y
+
+
+def _gemm_ln(a, stats, wf, u, c, eps=1e-5, rowvec=None, rowvec_div=1, rowvec_mod=0, act=ops.ACT_NONE, out=None):
+    """The folded LayerNorm -> Linear with the kernel's own formula: rstd * (a Wf^T - mean * u) + c (+ rowvec)."""
+    s = stats.buf.sum(0)
+    k = a.shape[1]
+    mean = s[:, 0] / k
+    rstd = torch.rsqrt((s[:, 1] / k - mean * mean).clamp_min(0) + eps)
+    y = rstd[:, None] * (a.float() @ wf.float().t() - mean[:, None] * u[None]) + c[None]
+    if rowvec is not None:
+        r = torch.arange(a.shape[0], device=a.device) // rowvec_div
+        y = y + rowvec[r % rowvec_mod if rowvec_mod else r]
+    if act == ops.ACT_GEGLU:
+        bn = ops.geglu_block(wf.shape[0])
+        y = y.view(a.shape[0], -1, 2, bn // 2)
+        y = (y[:, :, 0] * F.gelu(y[:, :, 1])).reshape(a.shape[0], -1)
+    y = y.to(BF16)
     if out is not None:
         out.copy_(y)
         return out
@@ -142,7 +166,7 @@ def _cfg_ddim_step(latent, pred_uncond, pred_cond, guidance, sa, sb, sap, sbp, o
     return y
 
 
-REFERENCE = {"gemm": _gemm, "conv3x3": _conv3x3, "groupnorm": _groupnorm, "layernorm": _layernorm, "attention": _attention,
+REFERENCE = {"gemm": _gemm, "gemm_ln": _gemm_ln, "conv3x3": _conv3x3, "groupnorm": _groupnorm, "layernorm": _layernorm, "attention": _attention,
              "temporal_attention": _temporal_attention, "cfg_ddim_step": _cfg_ddim_step}
 
 
@@ -151,7 +175,7 @@ def reference_ops(*names):
     """Swap the named ops of :mod:`imagine360_b200.ops` for torch math inside the block."""
     saved = {}
     try:
-        for n in names:
+        for n in names + (("gemm_ln",) if "gemm" in names else ()):       # the folded GEMM belongs to the gemm family
             saved[n] = getattr(ops, n)
             setattr(ops, n, REFERENCE[n])
         yield
@@ -162,6 +186,6 @@ def reference_ops(*names):
 
 def install_from_env():
     names = [n for n in os.environ.get("I360_REFERENCE_OPS", "").split(",") if n]
-    for n in names:
+    for n in names + (["gemm_ln"] if "gemm" in names else []):
         setattr(ops, n, REFERENCE[n])
     return names

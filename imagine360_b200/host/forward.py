@@ -65,22 +65,30 @@ def tokens(x):
 
 
 # ------------------------------------------------------------------------------------------------------
-# LayerNorm -> Linear as ONE kernel (ops.gemm_ln): the fold (W * gamma, row sums, W beta + b) is a cached weight packing.
-# EXPERIMENT, off by default (I360_LN_FOLD=1 enables it): it removes 192 of the 220 LayerNorm launches of a 16x512x1024
-# step (13.5 ms of HBM passes), but the four statistics warps it adds to the GEMM CTA need ~2.2 issue slots per A-tile
-# element, recomputed by every N tile of a row block, and take them from the epilogue warps that bound the K = 320 / 640
-# projections: measured on one B200, same box, 317.9 ms per step with the fold against 308.7 ms without.
+# LayerNorm -> Linear as ONE kernel (ops.gemm_ln): the fold (W * gamma, row sums, W beta + b) is a cached weight packing, and
+# the row statistics of the token matrix are written by the epilogue of the GEMM that PRODUCED it (proj_in, to_out + residual,
+# ff.net[2] + residual: ``token_linear`` below), so neither a LayerNorm pass nor a normalised copy of the tokens exists.
+# I360_LN_FOLD=0 restores LayerNorm + GEMM (A/B runs).  History: a first version took the statistics from the A tiles inside the
+# consuming GEMM (four extra warps) and was 9 ms per step SLOWER than the separate pass (profiles/r02_bench_c3_ln_fold_*.json).
 # ------------------------------------------------------------------------------------------------------
-LN_FOLD = os.environ.get("I360_LN_FOLD", "0") not in ("", "0")
+LN_FOLD = os.environ.get("I360_LN_FOLD", "1") not in ("", "0")
 
 
-def ln_linear(t, norm, owner, key, mods, bias_mod=None, act=ops.ACT_NONE, pe=None, pe_div=1, pe_mod=0):
+def token_linear(a, w, bias=None, resid=None):
+    """A projection whose output is the residual stream a LayerNorm reads next: -> (tokens, row statistics | None)."""
+    if LN_FOLD:
+        return ops.gemm(a, w, bias=bias, resid=resid, rowstats=True)
+    return ops.gemm(a, w, bias=bias, resid=resid), None
+
+
+def ln_linear(t, stats, norm, owner, key, mods, bias_mod=None, act=ops.ACT_NONE, pe=None, pe_div=1, pe_mod=0):
     """act(LayerNorm(t) @ cat(W of mods)^T + bias (+ pe @ W^T per row group)).  ``pe`` fp32 [pe_mod, C] is the table
-    the temporal module adds AFTER the norm (motion_module.py:350)."""
+    the temporal module adds AFTER the norm (motion_module.py:350); ``stats`` are the row statistics of ``t`` from
+    :func:`token_linear` (None: separate LayerNorm pass)."""
     ws = [m.weight for m in mods]
     n_total, k = sum(w.shape[0] for w in ws), ws[0].shape[1]
     geglu = act == ops.ACT_GEGLU
-    if LN_FOLD and ops.gemm_ln_supported(n_total, k, act):
+    if stats is not None and ops.gemm_ln_supported(n_total, k, act):
         params = ws + [norm.weight, norm.bias] + ([bias_mod.bias] if bias_mod is not None and bias_mod.bias is not None else [])
 
         def build():
@@ -93,7 +101,7 @@ def ln_linear(t, norm, owner, key, mods, bias_mod=None, act=ops.ACT_NONE, pe=Non
         if pe is not None:
             rv = cached(owner, f"lnpe_{key}_{pe.shape[0]}", ws + [pe],
                         lambda: (pe.float() @ torch.cat([x.to(BF16) for x in ws], 0).float().t()).contiguous())
-        return ops.gemm_ln(t, wf, u, c, norm.eps, rowvec=rv, rowvec_div=pe_div, rowvec_mod=pe_mod if pe is not None else 0, act=act)
+        return ops.gemm_ln(t, stats, wf, u, c, norm.eps, rowvec=rv, rowvec_div=pe_div, rowvec_mod=pe_mod if pe is not None else 0, act=act)
     nrm = ops.layernorm(t, norm.weight, norm.bias, norm.eps, post_add=pe, post_div=pe_div, post_mod=pe_mod if pe is not None else 1)
     if geglu:
         wg, bg = geglu_w(owner)
@@ -201,19 +209,19 @@ def spatial_transformer(x, t3d, ctx: Context, frames: int):
     npix = h * w
     hn = ops.groupnorm(x, t3d.norm.weight, t3d.norm.bias, t3d.groups, 1e-6, False)
     wi, bi = lin_w(t3d.proj_in)
-    t = ops.gemm(tokens(hn), wi, bias=bi)
+    t, st = token_linear(tokens(hn), wi, bi)
     for blk in t3d.transformer_blocks:
         # --- attn1: fused QKV projection, flash attention reading q/k/v as column slices ---
         a1 = blk.attn1
-        qkv = ln_linear(t, blk.norm1, a1, "qkv", [a1.to_q, a1.to_k, a1.to_v])
+        qkv = ln_linear(t, st, blk.norm1, a1, "qkv", [a1.to_q, a1.to_k, a1.to_v])
         o = torch.empty_like(t)
         ops.attention(ops.seq_view(qkv, n, npix, 0), ops.seq_view(qkv, n, npix, c), ops.seq_view(qkv, n, npix, 2 * c),
                       ops.seq_view(o, n, npix), heads, hd, n)
         wo, bo = lin_w(a1.to_out[0])
-        t = ops.gemm(o, wo, bias=bo, resid=t)
+        t, st = token_linear(o, wo, bo, t)
         # --- attn2: text + image-prompt cross attention, outputs summed before to_out (attention.py:148) ---
         a2 = blk.attn2
-        q = ln_linear(t, blk.norm2, a2, "q", [a2.to_q])
+        q = ln_linear(t, st, blk.norm2, a2, "q", [a2.to_q])
         nt, ni = ctx.text.shape[1], ctx.ip.shape[1]
         kv_t = ops.gemm(ctx.text.view(-1, ctx.text.shape[-1]), fused_w(a2, "kv", [a2.to_k, a2.to_v]))
         ip = ctx.ip[..., : a2.image_cross_attention_dim] if a2.image_cross_attention_dim != a2.cross_attention_dim else ctx.ip
@@ -231,18 +239,19 @@ def spatial_transformer(x, t3d, ctx: Context, frames: int):
             ops.attention(qv, ops.seq_view(kv_i, ctx.n_ctx, ni, 0, share_div=frames),
                           ops.seq_view(kv_i, ctx.n_ctx, ni, c, share_div=frames), ov, heads, hd, n, accumulate=True)
         wo, bo = lin_w(a2.to_out[0])
-        t = ops.gemm(o, wo, bias=bo, resid=t)
+        t, st = token_linear(o, wo, bo, t)
         # --- GEGLU feed-forward ---
-        t = feed_forward(t, blk.ff, blk.norm3)
+        t, st = feed_forward(t, st, blk.ff, blk.norm3)
     wo, bo = lin_w(t3d.proj_out)
     return ops.gemm(t, wo, bias=bo, resid=tokens(x)).view(n, h, w, c)
 
 
 @traced("feed_forward")
-def feed_forward(t, ff, norm):
-    g = ln_linear(t, norm, ff, "geglu", [ff.net[0].proj], bias_mod=ff.net[0].proj, act=ops.ACT_GEGLU)
+def feed_forward(t, st, ff, norm):
+    """-> (tokens, row statistics of the result): the next block's first LayerNorm reads them."""
+    g = ln_linear(t, st, norm, ff, "geglu", [ff.net[0].proj], bias_mod=ff.net[0].proj, act=ops.ACT_GEGLU)
     w2, b2 = lin_w(ff.net[2])
-    return ops.gemm(g, w2, bias=b2, resid=t)
+    return token_linear(g, w2, b2, t)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -261,16 +270,16 @@ def temporal_module(x, mm, frames: int):
     d = h * w
     hn = ops.groupnorm(x, tt.norm.weight, tt.norm.bias, tt.groups, 1e-6, False)
     wi, bi = lin_w(tt.proj_in)
-    t = ops.gemm(tokens(hn), wi, bias=bi)
+    t, st = token_linear(tokens(hn), wi, bi)
     for blk in tt.transformer_blocks:
         for att, norm in zip(blk.attention_blocks, blk.norms):
-            qkv = ln_linear(t, norm, att, "qkv", [att.to_q, att.to_k, att.to_v], pe=_pe_table(att, frames, BF16), pe_div=d,
+            qkv = ln_linear(t, st, norm, att, "qkv", [att.to_q, att.to_k, att.to_v], pe=_pe_table(att, frames, BF16), pe_div=d,
                             pe_mod=frames)
             o = torch.empty_like(t)
             ops.temporal_attention(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], o, n // frames, frames, d, tt.heads, tt.dim_head)
             wo, bo = lin_w(att.to_out[0])
-            t = ops.gemm(o, wo, bias=bo, resid=t)
-        t = feed_forward(t, blk.ff, blk.ff_norm)
+            t, st = token_linear(o, wo, bo, t)
+        t, st = feed_forward(t, st, blk.ff, blk.ff_norm)
     wo, bo = lin_w(tt.proj_out)
     return ops.gemm(t, wo, bias=bo, resid=tokens(x)).view(n, h, w, c)
 

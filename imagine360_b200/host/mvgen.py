@@ -130,20 +130,20 @@ class WarpAttn(nn.Module):
         o_e = torch.empty_like(et)
         ops.attention(ops.seq_view(q_e, bf, en), ops.multiview_view(kv_p, clips, views, frames, hw, 0),
                       ops.multiview_view(kv_p, clips, views, frames, hw, c), ops.seq_view(o_e, bf, en), heads, hd, bf, bias=bias_e)
-        e_out = ops.gemm(o_e, wo, bias=bo, resid=et)
+        e_out, e_st = Fw.token_linear(o_e, wo, bo, et)
         # equirect -> perspective
         q_p, kv_e = ops.gemm(pn, wq), ops.gemm(en_, wkv)
         o_p = torch.empty_like(pt)
         ops.attention(ops.multiview_view(q_p, clips, views, frames, hw), ops.seq_view(kv_e, bf, en, 0), ops.seq_view(kv_e, bf, en, c),
                       ops.multiview_view(o_p, clips, views, frames, hw), heads, hd, bf, bias=bias_p)
-        p_out = ops.gemm(o_p, wo, bias=bo, resid=pt)
-        e_out = _warp_ff(e_out, tr)
-        p_out = _warp_ff(p_out, tr)
+        p_out, p_st = Fw.token_linear(o_p, wo, bo, pt)
+        e_out = _warp_ff(e_out, e_st, tr)
+        p_out = _warp_ff(p_out, p_st, tr)
         return p_out.view_as(pers), e_out.view_as(equi)
 
 
-def _warp_ff(t, tr):
-    g = Fw.ln_linear(t, tr.norm2, tr.ff, "geglu", [tr.ff.net[0].proj], bias_mod=tr.ff.net[0].proj, act=ops.ACT_GEGLU)
+def _warp_ff(t, st, tr):
+    g = Fw.ln_linear(t, st, tr.norm2, tr.ff, "geglu", [tr.ff.net[0].proj], bias_mod=tr.ff.net[0].proj, act=ops.ACT_GEGLU)
     w2, b2 = lin_w(tr.ff.net[2])
     return ops.gemm(g, w2, bias=b2, resid=t)
 

@@ -78,9 +78,19 @@ def pack_geglu(weight: torch.Tensor, bias: torch.Tensor | None):
     return w, b
 
 
+class RowStats:
+    """Partial (sum, sum of squares) per row of a token matrix, written by the GEMM that produced it (``gemm(...,
+    rowstats=True)``) and consumed by ``gemm_ln``: fp32 [slots, M, 2]."""
+    __slots__ = ("buf", "slots", "of")
+
+    def __init__(self, buf, slots, of):
+        self.buf, self.slots, self.of = buf, slots, of
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, resid=None, rowvec=None, rowvec_div: int = 1,
-         act: int = ACT_NONE, out_scale: float = 1.0, out: torch.Tensor | None = None) -> torch.Tensor:
-    """out[M, N] = epilogue(a[M, K] @ w[N, K]^T).  a/out may be row-strided 2-D views."""
+         act: int = ACT_NONE, out_scale: float = 1.0, out: torch.Tensor | None = None, rowstats: bool = False):
+    """out[M, N] = epilogue(a[M, K] @ w[N, K]^T).  a/out may be row-strided 2-D views.
+    ``rowstats=True`` (plain / bias / residual epilogues) returns ``(out, RowStats)``."""
     _chk_bf16(a, w, bias, resid, out)
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
     assert a.stride(1) == 1 and w.stride(1) == 1
@@ -94,6 +104,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, resid=None, rowvec=None, r
         assert resid.shape == (M, n_out) and resid.stride(1) == 1
     if rowvec is not None:
         assert rowvec.dtype == torch.float32 and rowvec.stride(-1) == 1
+    if rowstats:
+        assert act == ACT_NONE and rowvec is None and out_scale == 1.0
+        slots = int(lib().i360_gemm_rowstats_slots(c_int(M), c_int(N), c_int(K), c_int(int(resid is not None))))
+        st = torch.empty((slots, M, 2), dtype=torch.float32, device=a.device)
+        rc = lib().i360_gemm_rowstats_bf16(
+            _p(a), c_longlong(a.stride(0)), _p(w), c_longlong(w.stride(0)), _p(out), c_longlong(out.stride(0)),
+            c_int(M), c_int(N), c_int(K), _p(bias), _p(resid), c_longlong(resid.stride(0) if resid is not None else 0),
+            _p(st), _stream())
+        check(rc, "i360_gemm_rowstats_bf16")
+        return out, RowStats(st, slots, out)
     rc = lib().i360_gemm_bf16(
         _p(a), c_longlong(a.stride(0)), _p(w), c_longlong(w.stride(0)), _p(out), c_longlong(out.stride(0)),
         c_int(M), c_int(N), c_int(K), _p(bias), _p(resid),
@@ -127,10 +147,13 @@ def fold_layernorm(weight: torch.Tensor, bias, gamma: torch.Tensor, beta: torch.
     return wf.contiguous(), u.contiguous(), c.contiguous()
 
 
-def gemm_ln(a: torch.Tensor, wf: torch.Tensor, u: torch.Tensor, c: torch.Tensor, eps: float = 1e-5, rowvec=None,
+def gemm_ln(a: torch.Tensor, stats: RowStats, wf: torch.Tensor, u: torch.Tensor, c: torch.Tensor, eps: float = 1e-5, rowvec=None,
             rowvec_div: int = 1, rowvec_mod: int = 0, act: int = ACT_NONE, out: torch.Tensor | None = None) -> torch.Tensor:
     """out[M, N] = act(LayerNorm(a)[M, K] @ W^T + bias (+ rowvec[(r // rowvec_div) % rowvec_mod])) with the LayerNorm folded
-    into the GEMM (see :func:`fold_layernorm`); ``a`` is the UN-normalised token matrix."""
+    into the GEMM (see :func:`fold_layernorm`); ``a`` is the UN-normalised token matrix and ``stats`` the row statistics
+    its producer wrote (``gemm(..., rowstats=True)``)."""
+    assert stats.of is a or (stats.of.data_ptr() == a.data_ptr() and stats.of.shape == a.shape), "row statistics of another tensor"
+    assert stats.buf.shape[1] == a.shape[0]
     _chk_bf16(a, wf, out)
     assert a.dim() == 2 and wf.dim() == 2 and a.shape[1] == wf.shape[1] and a.stride(1) == 1 and wf.stride(1) == 1
     assert u.dtype == torch.float32 and c.dtype == torch.float32 and u.is_contiguous() and c.is_contiguous()
@@ -144,7 +167,7 @@ def gemm_ln(a: torch.Tensor, wf: torch.Tensor, u: torch.Tensor, c: torch.Tensor,
         assert rowvec.dtype == torch.float32 and rowvec.stride(-1) == 1 and rowvec.shape[-1] == N
     rc = lib().i360_gemm_ln_bf16(_p(a), c_longlong(a.stride(0)), _p(wf), c_longlong(wf.stride(0)), _p(out),
                                  c_longlong(out.stride(0)), c_int(M), c_int(N), c_int(K), _p(u), _p(c), c_float(eps),
-                                 _p(rowvec), c_int(rowvec_div), c_int(rowvec_mod),
+                                 _p(stats.buf), c_int(stats.slots), _p(rowvec), c_int(rowvec_div), c_int(rowvec_mod),
                                  c_int(rowvec.stride(0) if rowvec is not None else 0), c_int(act), _stream())
     check(rc, "i360_gemm_ln_bf16")
     return out

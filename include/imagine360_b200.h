@@ -42,16 +42,24 @@ int i360_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, v
                    int K, const void* bias, const void* resid, long long ldr, const float* rowvec, int rowvec_div,
                    int rowvec_ld, int act, float out_scale, void* stream);
 
+/* The same GEMM (bias, residual; no activation) that ALSO writes row statistics of what it stores:
+ * rowstats[(slot * M + r) * 2 + {0, 1}] = (sum, sum of squares) over the columns of row r handled by one (N tile, epilogue
+ * group) slot, for slot < i360_gemm_rowstats_slots(M, N, K, resid != NULL).  No atomics: the consumer adds the slots in a
+ * fixed order, so the result is deterministic.  Producer half of the LayerNorm fold below. */
+int i360_gemm_rowstats_slots(int M, int N, int K, int has_resid);
+int i360_gemm_rowstats_bf16(const void* A, long long lda, const void* W, long long ldw, void* D, long long ldd, int M, int N,
+                            int K, const void* bias, const void* resid, long long ldr, float* rowstats, void* stream);
+
 /* LayerNorm folded into the projection that consumes it: D = act(LN(A; gamma, beta, eps) W^T + bias (+ rowvec)).
- * Wf = W * gamma (bf16, [N, K]); u[n] = sum_k Wf[n,k]; c[n] = sum_k beta[k] W[n,k] + bias[n] (fp32).  Row statistics are
- * taken from the A tiles in shared memory next to the tensor core; the epilogue applies
- * rstd * acc - mean * rstd * u + c, so the normalised activations never travel through HBM.  K = LayerNorm width
- * (multiple of 64).  rowvec fp32 [rowvec_mod, N] is added at row (r / rowvec_div) % rowvec_mod (temporal PE term
- * (LN(x) + pe_f) W^T, motion_module.py:350).  act: 0 or 1 (GEGLU, Wf / u / c packed like the weight).
+ * Wf = W * gamma (bf16, [N, K]); u[n] = sum_k Wf[n,k]; c[n] = sum_k beta[k] W[n,k] + bias[n] (fp32).  The row statistics
+ * of A come from the GEMM that produced it (rowstats / slots as written by i360_gemm_rowstats_bf16); the epilogue applies
+ * rstd * acc - mean * rstd * u + c, so the normalised activations never travel through HBM and no LayerNorm pass runs.
+ * K = LayerNorm width (multiple of 64).  rowvec fp32 [rowvec_mod, N] is added at row (r / rowvec_div) % rowvec_mod (temporal
+ * PE term (LN(x) + pe_f) W^T, motion_module.py:350).  act: 0 or 1 (GEGLU, Wf / u / c packed like the weight).
  * Replaces nn.LayerNorm + nn.Linear (animatediff/models/attention.py:463-508; motion_module.py:247-259). */
 int i360_gemm_ln_bf16(const void* A, long long lda, const void* Wf, long long ldw, void* D, long long ldd, int M, int N,
-                      int K, const float* u, const float* c, float eps, const float* rowvec, int rowvec_div,
-                      int rowvec_mod, int rowvec_ld, int act, void* stream);
+                      int K, const float* u, const float* c, float eps, const float* rowstats, int slots,
+                      const float* rowvec, int rowvec_div, int rowvec_mod, int rowvec_ld, int act, void* stream);
 /* Tile width i360_gemm_ln_bf16 uses for (N, K, act); 0 = unsupported (keep i360_layernorm + i360_gemm_bf16). */
 int i360_gemm_ln_supported(int N, int K, int act);
 

@@ -163,15 +163,44 @@ def test_conv3x3_halo_tiles(B, H, W, Cin, Cout, mode):
     _close(out3, ref.permute(0, 2, 3, 1), f"tap conv {mode} {B}x{H}x{W} {Cin}->{Cout}")
 
 
-@pytest.mark.parametrize("M,N,K,act,pe", [(1000, 960, 320, 0, False), (777, 320, 320, 0, False), (513, 2560, 320, 1, False),
-                                          (300, 3840, 1280, 0, True), (4100, 1920, 640, 0, True), (129, 1280, 1280, 0, False),
-                                          (2000, 5120, 640, 1, False), (64, 960, 320, 0, True)])
-def test_gemm_with_folded_layernorm(M, N, K, act, pe):
-    """i360_gemm_ln_bf16: LayerNorm folded into the consuming projection (row statistics from the A tiles in smem, applied
-    in the epilogue) against fp32 torch LayerNorm -> Linear (-> GEGLU), incl. the temporal-PE row vector."""
+@pytest.mark.parametrize("M,N,K,resid", [(1000, 320, 320, True), (777, 320, 1280, False), (4100, 640, 640, True), (40000, 640, 640, True),
+                                          (38000, 640, 2560, False), (513, 1280, 1280, True), (130, 1280, 5120, False), (64, 320, 320, True)])
+def test_gemm_rowstats(M, N, K, resid):
+    """i360_gemm_rowstats_bf16: the GEMM result is the plain kernel's, and the slots add up to the row sums / sums of
+    squares of what was stored (ring / direct residual epilogues, 160- and 256-wide tiles, the 256 x 128 variant)."""
     from imagine360_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
-    x = (torch.randn(M, K, device="cuda", generator=g) * 1.7 + 0.6 * torch.randn(M, 1, device="cuda", generator=g)).bfloat16()
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g).bfloat16()
+    r = (torch.randn(M, N, device="cuda", generator=g) + 0.5).bfloat16() if resid else None
+    out, st = ops.gemm(a, w, bias=b, resid=r, rowstats=True)
+    plain = ops.gemm(a, w, bias=b, resid=r)
+    assert torch.equal(out, plain)
+    ref = a.float() @ w.float().t() + b.float() + (r.float() if resid else 0)
+    tot = st.buf.sum(0)
+    assert st.buf.shape == (st.slots, M, 2)
+    e1 = (tot[:, 0] - ref.sum(1)).abs().max().item()
+    e2 = ((tot[:, 1] - (ref * ref).sum(1)).abs() / (ref * ref).sum(1)).max().item()
+    assert e1 < 2e-3 * N ** 0.5 and e2 < 1e-4, (e1, e2)
+    out2, st2 = ops.gemm(a, w, bias=b, resid=r, rowstats=True)
+    assert torch.equal(st.buf, st2.buf), "row statistics must be deterministic (no atomics)"
+
+
+@pytest.mark.parametrize("M,N,K,act,pe", [(1000, 960, 320, 0, False), (777, 320, 320, 0, False), (513, 2560, 320, 1, False),
+                                          (300, 3840, 1280, 0, True), (4100, 1920, 640, 0, True), (129, 1280, 1280, 0, False),
+                                          (2000, 5120, 640, 1, False), (64, 960, 320, 0, True), (40000, 640, 640, 0, False)])
+def test_gemm_with_folded_layernorm(M, N, K, act, pe):
+    """i360_gemm_ln_bf16: LayerNorm folded into the consuming projection -- row statistics written by the epilogue of the
+    GEMM that produced the token matrix, applied in the consumer's epilogue -- against fp32 torch LayerNorm -> Linear
+    (-> GEGLU), incl. the temporal-PE row vector."""
+    from imagine360_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    # the token matrix x [M, K] comes out of a producer GEMM (bias + residual, like to_out / ff.net[2]) with a row offset
+    a0 = torch.randn(M, 320, device="cuda", generator=g).bfloat16()
+    w0 = (torch.randn(K, 320, device="cuda", generator=g) * (1.7 / 320 ** 0.5)).bfloat16()
+    r0 = (0.6 * torch.randn(M, 1, device="cuda", generator=g)).expand(M, K).contiguous().bfloat16()
+    x, st = ops.gemm(a0, w0, resid=r0, rowstats=True)
     w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
     b = torch.randn(N, device="cuda", generator=g).bfloat16() if act else None
     gamma = (1 + 0.2 * torch.randn(K, device="cuda", generator=g)).bfloat16()
@@ -181,7 +210,7 @@ def test_gemm_with_folded_layernorm(M, N, K, act, pe):
     Fr, D = 4, 5
     table = torch.randn(Fr, K, device="cuda", generator=g).bfloat16().float() if pe else None
     rv = (table @ w.float().t()).contiguous() if pe else None
-    out = ops.gemm_ln(x, wf, u, c, 1e-5, rowvec=rv, rowvec_div=D, rowvec_mod=Fr if pe else 0, act=act)
+    out = ops.gemm_ln(x, st, wf, u, c, 1e-5, rowvec=rv, rowvec_div=D, rowvec_mod=Fr if pe else 0, act=act)
     y = F.layer_norm(x.float(), (K,), gamma.float(), beta.float(), 1e-5)
     if pe:
         y = y + table[(torch.arange(M, device="cuda") // D) % Fr]
