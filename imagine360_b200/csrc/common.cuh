@@ -323,6 +323,29 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   const float2 h = ffma2(x, make_float2(0.5f, 0.5f), m);                 // max(x, 0) = 0.5 x + 0.5 |x|, exact
   return ffma2(make_float2(-m.x, -m.y), r, h);
 }
+// EXPERIMENT (not the default, see I360_GEGLU_ERF): a cheaper gelu(x) = x * Phi(x) for the GEGLU epilogue (SASS: 304 packed
+// FMA-pipe instructions per 32-column chunk with the A-S 7.1.28 erf above, 19 per output pair):
+// Phi(x) ~= sigmoid(x (c1 + c3 x^2 + c5 x^4)), odd quintic
+// fitted by minimax on the GELU error (tools/fit_gelu_sigmoid.py): max |error| 2.6e-5 on the whole real line in fp32 --
+// two orders of magnitude below the bf16 rounding of the result -- for 6 FMA-pipe instructions and 4 MUFU ops (ex2, rcp)
+// per pair instead of 14 and 2.  The quintic turns around past |x| ~ 11, so its argument is clamped to +-10 (ALU pipe);
+// the result still multiplies the unclamped x.  Constants carry the -log2(e) of exp(-p) = 2^(-p log2 e).
+// Measured: 655 360 x 2560 x 320 LayerNorm-folded GEGLU 1.205 ms with it, 1.215 ms with the erf -- the epilogue is bound by
+// dependency latency (ncu: stall "wait" 27 %, FMA pipe 33 %, tensor 46 %; profiles/r02b_ncu_geglu_ln_k320.txt), not by the
+// FMA pipe, so the 40 % fewer FMA instructions buy nothing and the 100 x more accurate erf stays the default.
+__device__ __forceinline__ float2 gelu_sig2(float2 x) {
+  const float2 xc = make_float2(fminf(fmaxf(x.x, -10.f), 10.f), fminf(fmaxf(x.y, -10.f), 10.f));
+  const float2 x2 = fmul2(xc, xc);
+  float2 p = ffma2(x2, make_float2(1.0142630198970437e-3f, 1.0142630198970437e-3f), make_float2(-0.10677571594715118f, -0.10677571594715118f));
+  p = ffma2(p, x2, make_float2(-2.301121234893799f, -2.301121234893799f));
+  const float2 a = fmul2(p, xc);
+  const float2 d = fadd2(make_float2(fast_exp2(a.x), fast_exp2(a.y)), make_float2(1.f, 1.f));
+  return fmul2(x, make_float2(fast_rcp(d.x), fast_rcp(d.y)));
+}
+#ifndef I360_GEGLU_ERF
+#define I360_GEGLU_ERF 1      // 0: the GEGLU epilogue uses gelu_sig2 (A/B builds)
+#endif
+__device__ __forceinline__ float2 gelu_gate2(float2 x) { return I360_GEGLU_ERF ? gelu_erf2(x) : gelu_sig2(x); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 // Packed SiLU for the HBM-bound GroupNorm+SiLU pass: ONE MUFU op per element (ex2 of -|y|) and the reciprocal of
 // 1 + e in [1, 2] by a linear seed + two Newton steps on the packed FMA pipe (rel. error ~1e-5, far below the bf16

@@ -85,8 +85,10 @@ constexpr int kHaloTxBytes = kHaloRows * BK * 2;               // 23 040
 constexpr int kHaloBytes = 23 * 1024;                          // ... rounded up to the 1024-byte swizzle atom
 constexpr int kHaloStages = 2;                                 // a halo tile lives for 9 taps: double buffering suffices
 
-template <int BN, bool RING = false, int MT = 1, bool LNF = false, bool HALO = false> struct Cfg {
+template <int BN, bool RING = false, int MT = 1, bool LNF = false, bool HALO = false, int NG = 2> struct Cfg {
   static_assert(!HALO || (MT == 1 && !LNF), "HALO is a CONV mode");
+  static_assert(NG == 2 || (NG == 4 && MT == 1 && !RING && !HALO && BN >= 160), "four epilogue groups: GEMM mode, table epilogues");
+  static constexpr int kThreadsTotal = 64 + NG * 128;      // warp0 TMA, warp1 MMA, then NG epilogue groups of four warps
   static constexpr int kABytes = MT * BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = HALO ? kBBytes : kABytes + kBBytes;   // HALO: the ring holds weight tiles only
@@ -97,14 +99,16 @@ template <int BN, bool RING = false, int MT = 1, bool LNF = false, bool HALO = f
   static constexpr int kStgBytes = 128 * CH * 2;
   // RING: the residual tile is TMA-prefetched INTO the staging buffers (added in place, then stored), which needs
   // 4 buffers per group so that a residual chunk can be requested ~3 chunks before it is consumed
-  static constexpr int kBufPerGrp = RING ? 4 : 2;
-  static constexpr int kNumStg = 2 * kBufPerGrp;
+  // (NG = 4: ONE buffer per group -- a group's chunks are four chunks apart, so waiting for its previous store to have read
+  // the buffer costs nothing, and the staging area stays at 32 KB)
+  static constexpr int kBufPerGrp = RING ? 4 : (NG == 4 ? 1 : 2);
+  static constexpr int kNumStg = NG * kBufPerGrp;
   // The epilogue-bound tile shapes (160-wide K=320/640 projections, 256-wide GEGLU) keep the tile's bias as an fp32
   // table in smem -- one copy per epilogue group, filled one tile ahead through registers -- instead of every
   // thread re-loading and unpacking the same bf16 values for every chunk.
   static constexpr bool kBiasTable = BN >= 160;
   static_assert(!LNF || kBiasTable, "the LayerNorm-folding epilogue reads c and u from the smem tables");
-  static constexpr int kTableBytes = kBiasTable ? (LNF ? 4 : 2) * BN * 4 : 0;       // [group][BN] bias (LNF: c), then [group][BN] u
+  static constexpr int kTableBytes = kBiasTable ? (LNF ? 2 : 1) * NG * BN * 4 : 0;   // [group][BN] bias (LNF: c), then [group][BN] u
   static constexpr int kStatBytes = 0;
   // dynamic smem is declared __align__(1024) (checked at run time), so no alignment slack is reserved
   static constexpr int kBudget = 227 * 1024 - kNumStg * kStgBytes - kTableBytes - kStatBytes - 256 - kHaloTotal;
@@ -134,14 +138,14 @@ template <int BN, int EPI> struct UseRing { static constexpr bool value = (EPI =
 // token matrix per norm, 192 launches and ~13 ms of the 16x512x1024 step) disappears.  (A first version took the
 // statistics from the A tiles in shared memory with four extra warps; they competed with the epilogue warps for issue
 // slots and the step got 9 ms slower -- see git history / profiles/r02_bench_c3_ln_fold_on.json.)
-template <int BN, int EPI, int MT = 1, bool LNF = false, bool HALO = false>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int EPI, int MT = 1, bool LNF = false, bool HALO = false, int NG = 2>
+__global__ void __launch_bounds__(64 + NG * 128, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                  const GemmConvParams p) {
   constexpr bool kRing = UseRing<BN, EPI>::value;
-  using C = Cfg<BN, kRing, MT, LNF, HALO>;
+  using C = Cfg<BN, kRing, MT, LNF, HALO, NG>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();   // 128B-swizzled TMA / UMMA tiles need 1024-byte aligned stages
   uint8_t* shalo = smem_raw;                          // HALO: kHaloStages activation tiles in front of the weight ring
@@ -149,7 +153,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t base = smem_u32(smem);
   uint8_t* stg = smem + C::kStages * C::kStageBytes;            // 2 staging buffers (1024-aligned)
   float* sbias = reinterpret_cast<float*>(stg + C::kNumStg * C::kStgBytes);   // [2 groups][BN] (kBiasTable only)
-  float* su = sbias + 2 * BN;                                                  // [2 groups][BN] (LNF only)
+  float* su = sbias + NG * BN;                                                 // [groups][BN] (LNF only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg + C::kNumStg * C::kStgBytes + C::kTableBytes + C::kStatBytes);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + C::kStages;         // [kStages]
@@ -168,7 +172,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.C2 > 0) tma_prefetch_desc(&tmA2);
     if (p.C3 > 0) tma_prefetch_desc(&tmA3);
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4 * NG); }
     if (kRing) { for (int s = 0; s < 8; ++s) mbar_init(&rbar[s], 1); tma_prefetch_desc(&tmR); }
     if (HALO) { for (int s = 0; s < kHaloStages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); } }
     fence_barrier_init();
@@ -296,6 +300,160 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
+  } else if (NG == 4) {
+    // =============================== epilogue, four groups (warps 2..17) ===============================
+    // The K = 320 / 640 GEGLU and QKV projections are bound by their epilogue: with two groups only two warps per SM
+    // sub-partition work on ~35 instructions per output pair (erf-GELU, the LayerNorm fold) and their dependency
+    // latency is exposed -- 6 200 clocks per 128 x 256 GEGLU tile against 2 560 of tensor-core time.  Four groups put four
+    // epilogue warps on every sub-partition; to fit 576 threads (112 registers) a 32-column chunk is computed as two
+    // 16-column halves.  Group g takes chunks g, g + 4, ... and owns ONE staging buffer (see Cfg).  Plain and GEGLU
+    // epilogues with the smem bias table only (bias / LayerNorm-fold constants); nothing per-row but the LN statistics.
+    static_assert(NG != 4 || EPI == EPI_PLAIN || EPI == EPI_GEGLU, "four-group epilogue: plain / GEGLU");
+    constexpr int CH = C::CH;
+    constexpr bool kGeglu = (EPI == EPI_GEGLU);
+    const int ew = warp & 3;                      // TMEM lane quarter of this warp
+    const int grp = (warp - 2) >> 2;
+    const int row = ew * 32 + lane;
+    const int gtid = ((warp - 2) & 3) * 32 + lane;
+    const bool store_thread = (lane == 0) && (((warp - 2) & 3) == 0);
+    const uint32_t swz = (row >> 1) & 3;
+    uint8_t* buf = stg + grp * C::kStgBytes;
+    uint8_t* my = buf + row * (CH * 2);
+    const bool has_bias = p.bias != nullptr;
+    float* tbias_w = sbias + grp * BN;
+    float* tu_w = su + grp * BN;
+    float nb0 = 0.f, nb1 = 0.f, nu0 = 0.f, nu1 = 0.f;
+    auto load_tables = [&](int tt) {
+      if (tt >= total_tiles) return;
+      const int c0 = (tt % p.n_tiles) * BN + gtid;
+      const bool in0 = c0 < p.N, in1 = (gtid + 128 < BN) && (c0 + 128 < p.N);
+      if (LNF) {
+        nb0 = in0 ? p.ln_c[c0] : 0.f; nu0 = in0 ? p.ln_u[c0] : 0.f;
+        nb1 = in1 ? p.ln_c[c0 + 128] : 0.f; nu1 = in1 ? p.ln_u[c0 + 128] : 0.f;
+        if (p.rowvec_in_table) {
+          const float* rvp = p.rowvec + static_cast<long long>((((tt / p.n_tiles) * BM) / p.rowvec_div) % p.rowvec_mod) * p.rowvec_ld;
+          if (in0) nb0 += rvp[c0];
+          if (in1) nb1 += rvp[c0 + 128];
+        }
+      } else {
+        nb0 = (has_bias && in0) ? __bfloat162float(p.bias[c0]) : 0.f;
+        nb1 = (has_bias && in1) ? __bfloat162float(p.bias[c0 + 128]) : 0.f;
+      }
+    };
+    load_tables(blockIdx.x);
+    int as = 0; uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
+      const long long r = static_cast<long long>(m_blk) * BM + row;
+      // this tile's tables (fetched into registers one tile ago).  Everybody of the group is past the previous tile's
+      // last chunk barrier, i.e. done reading the old table.
+      tbias_w[gtid] = nb0;
+      if (gtid + 128 < BN) tbias_w[gtid + 128] = nb1;
+      if (LNF) { tu_w[gtid] = nu0; if (gtid + 128 < BN) tu_w[gtid + 128] = nu1; }
+      named_bar_sync(1 + grp, 128);
+      load_tables(t + gridDim.x);
+      float2 rstd2 = make_float2(1.f, 1.f), nmr2 = make_float2(0.f, 0.f);
+      if (LNF) {      // row statistics: the load latency hides under the wait for the accumulator (the kernel is MMA bound now)
+        float s1 = 0.f, s2 = 0.f;
+        if (r < p.M) {
+          for (int sl = 0; sl < p.ln_slots; ++sl) {
+            const float2 st = __ldg(p.ln_stats + static_cast<long long>(sl) * p.M + r);
+            s1 += st.x; s2 += st.y;
+          }
+        }
+        const float inv_k = 1.0f / static_cast<float>(p.K);
+        const float mean = s1 * inv_k;
+        const float rstd = rsqrtf(fmaxf(s2 * inv_k - mean * mean, 0.f) + p.ln_eps);
+        rstd2 = make_float2(rstd, rstd); nmr2 = make_float2(-mean * rstd, -mean * rstd);
+      }
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * C::kAccCols;
+      constexpr int n_chunks = kGeglu ? (BN / 2) / CH : BN / CH;
+      const int oc0 = kGeglu ? n_blk * (BN / 2) : n_blk * BN;
+      const float* tb = sbias + grp * BN;
+      const float* tuu = su + grp * BN;
+#pragma unroll 1
+      for (int ci = grp; ci < n_chunks; ci += 4) {
+        const int ocol = oc0 + ci * CH;
+        const bool live = ocol < p.n_out;
+        uint32_t pk[16];                                   // the chunk's 32 bf16 outputs of my row
+        if (live) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int cc = ci * CH + h * 16;               // tile column of this half
+            uint32_t v[16];
+            tmem_ld_x16(t_acc + cc, v);
+            if (kGeglu) {
+              uint32_t vg[16];
+              tmem_ld_x16(t_acc + BN / 2 + cc, vg);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {                // 4 columns per step
+                const float4 c4 = *reinterpret_cast<const float4*>(tb + cc + q * 4);
+                const float4 g4 = *reinterpret_cast<const float4*>(tb + BN / 2 + cc + q * 4);
+                float2 ba0 = make_float2(c4.x, c4.y), ba1 = make_float2(c4.z, c4.w);
+                float2 bg0 = make_float2(g4.x, g4.y), bg1 = make_float2(g4.z, g4.w);
+                if (LNF) {
+                  const float4 u4 = *reinterpret_cast<const float4*>(tuu + cc + q * 4);
+                  const float4 w4 = *reinterpret_cast<const float4*>(tuu + BN / 2 + cc + q * 4);
+                  ba0 = ffma2(make_float2(u4.x, u4.y), nmr2, ba0); ba1 = ffma2(make_float2(u4.z, u4.w), nmr2, ba1);
+                  bg0 = ffma2(make_float2(w4.x, w4.y), nmr2, bg0); bg1 = ffma2(make_float2(w4.z, w4.w), nmr2, bg1);
+                }
+                const float2 a0 = make_float2(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]));
+                const float2 a1 = make_float2(__uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                const float2 g0 = make_float2(__uint_as_float(vg[q * 4]), __uint_as_float(vg[q * 4 + 1]));
+                const float2 g1 = make_float2(__uint_as_float(vg[q * 4 + 2]), __uint_as_float(vg[q * 4 + 3]));
+                const float2 val0 = LNF ? ffma2(a0, rstd2, ba0) : fadd2(a0, ba0), val1 = LNF ? ffma2(a1, rstd2, ba1) : fadd2(a1, ba1);
+                const float2 gat0 = LNF ? ffma2(g0, rstd2, bg0) : fadd2(g0, bg0), gat1 = LNF ? ffma2(g1, rstd2, bg1) : fadd2(g1, bg1);
+                const float2 o0 = fmul2(val0, gelu_gate2(gat0)), o1 = fmul2(val1, gelu_gate2(gat1));
+                pk[h * 8 + q * 2] = pack_bf16x2(o0.x, o0.y);
+                pk[h * 8 + q * 2 + 1] = pack_bf16x2(o1.x, o1.y);
+              }
+            } else {
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float2 a0 = make_float2(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]));
+                float2 a1 = make_float2(__uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                if (LNF || has_bias) {
+                  const float4 c4 = *reinterpret_cast<const float4*>(tb + cc + q * 4);
+                  float2 b0 = make_float2(c4.x, c4.y), b1 = make_float2(c4.z, c4.w);
+                  if (LNF) {
+                    const float4 u4 = *reinterpret_cast<const float4*>(tuu + cc + q * 4);
+                    b0 = ffma2(make_float2(u4.x, u4.y), nmr2, b0); b1 = ffma2(make_float2(u4.z, u4.w), nmr2, b1);
+                    a0 = ffma2(a0, rstd2, b0); a1 = ffma2(a1, rstd2, b1);
+                  } else {
+                    a0 = fadd2(a0, b0); a1 = fadd2(a1, b1);
+                  }
+                }
+                pk[h * 8 + q * 2] = pack_bf16x2(a0.x, a0.y);
+                pk[h * 8 + q * 2 + 1] = pack_bf16x2(a1.x, a1.y);
+              }
+            }
+          }
+        }
+        // the group's previous store must have finished READING the buffer before it is overwritten
+        if (store_thread) bulk_wait_read<0>();
+        named_bar_sync(1 + grp, 128);
+        if (live) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(my + ((static_cast<uint32_t>(g) ^ swz) << 4)) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + grp, 128);
+        if (store_thread && live) {
+          tma_store_2d(&tmD, buf, ocol, m_blk * BM);
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (store_thread) bulk_wait<0>();
   } else {
     // =============================== epilogue (warps 2..9) ===============================
     // TMEM -> registers -> (bias / temb / activation / residual) -> bf16 -> swizzled smem -> TMA tensor store.
@@ -495,7 +653,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const float2 ag = make_float2(__uint_as_float(vg[g * 8 + 2 * j]), __uint_as_float(vg[g * 8 + 2 * j + 1]));
                 const float2 val = LNF ? ffma2(av, rstd2, ba[j]) : fadd2(av, ba[j]);
                 const float2 gate = LNF ? ffma2(ag, rstd2, bg[j]) : fadd2(ag, bg[j]);
-                f2[g * 4 + j] = fmul2(val, gelu_erf2(gate));
+                f2[g * 4 + j] = fmul2(val, gelu_gate2(gate));
               }
             }
           } else {
@@ -630,15 +788,15 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-template <int BN, int EPI, int MT = 1, bool LNF = false, bool HALO = false>
+template <int BN, int EPI, int MT = 1, bool LNF = false, bool HALO = false, int NG = 2>
 static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3,
                   const CUtensorMap& w, const CUtensorMap& d, const CUtensorMap& rmap, const GemmConvParams& p,
                   cudaStream_t st) {
-  using C = Cfg<BN, UseRing<BN, EPI>::value, MT, LNF, HALO>;
+  using C = Cfg<BN, UseRing<BN, EPI>::value, MT, LNF, HALO, NG>;
   static_assert(C::kStages >= 3, "weight / operand ring too shallow");
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_conv_kernel<BN, EPI, MT, LNF, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_conv_kernel<BN, EPI, MT, LNF, HALO, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              C::kSmemBytes) != cudaSuccess)
       return I360_ERR_CUDA;
     attr_set = true;
@@ -646,7 +804,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms()) grid = num_sms();
   if (grid <= 0) return I360_OK;
-  gemm_conv_kernel<BN, EPI, MT, LNF, HALO><<<grid, kThreads, C::kSmemBytes, st>>>(a, a2, a3, w, d, rmap, p);
+  gemm_conv_kernel<BN, EPI, MT, LNF, HALO, NG><<<grid, C::kThreadsTotal, C::kSmemBytes, st>>>(a, a2, a3, w, d, rmap, p);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -696,6 +854,16 @@ static int pick_epi(const GemmConvParams& p) {
   return EPI_GENERAL;
 }
 
+// EXPERIMENT, off by default: I360_EPI_GROUPS=4 runs the LayerNorm-folded / GEGLU projections with four epilogue groups
+// (576 threads).  Measured on one B200 (tools/ln_fold_probe.py): folded QKV 655 360 x 960 x 320 0.503 -> 0.451 ms and plain
+// GEGLU x 2560 x 320 1.10 -> 0.99 ms, but folded GEGLU 1.22 -> 1.43 ms (its per-tile preamble -- tables, row statistics, three
+// barriers -- is paid by every group and is as long as the one chunk a group then computes) and N = 320 / 1920 unchanged;
+// step 312.6 / 313.8 ms with four groups against 312.7 / 312.8 ms with two -> the two-group kernels stay.
+static bool four_groups() {
+  static const bool on = getenv("I360_EPI_GROUPS") != nullptr && atoi(getenv("I360_EPI_GROUPS")) == 4;
+  return on;
+}
+
 template <int BN>
 static int dispatch_epi(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3, const CUtensorMap& w,
                         const CUtensorMap& d, const CUtensorMap& r, const GemmConvParams& p, cudaStream_t st) {
@@ -710,7 +878,9 @@ static int dispatch_epi(const CUtensorMap& a, const CUtensorMap& a2, const CUten
   }
   switch (pick_epi(p)) {
     case EPI_PLAIN: return launch<BN, EPI_PLAIN>(a, a2, a3, w, d, r, p, st);
-    case EPI_GEGLU: return launch<BN, EPI_GEGLU>(a, a2, a3, w, d, r, p, st);
+    case EPI_GEGLU:
+      if constexpr (BN == 256) { if (four_groups()) return launch<BN, EPI_GEGLU, 1, false, false, 4>(a, a2, a3, w, d, r, p, st); }
+      return launch<BN, EPI_GEGLU>(a, a2, a3, w, d, r, p, st);
     case EPI_RESID: return launch<BN, EPI_RESID>(a, a2, a3, w, d, r, p, st);
     case EPI_ROWVEC: return launch<BN, EPI_ROWVEC>(a, a2, a3, w, d, r, p, st);
     case EPI_ACT: return launch<BN, EPI_ACT>(a, a2, a3, w, d, r, p, st);
@@ -987,7 +1157,10 @@ extern "C" int i360_gemm_ln_bf16(const void* A, long long lda, const void* Wf, l
   uint32_t bD[2] = {32, BM};
   r = get_tmap_bf16(&td, D, 2, dD, sD, bD, 2); if (r) return r;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (act == 1) return launch<256, EPI_GEGLU, 1, true>(ta, ta, ta, tw, td, td, p, st);
+  if (act == 1) {
+    if (four_groups()) return launch<256, EPI_GEGLU, 1, true, false, 4>(ta, ta, ta, tw, td, td, p, st);
+    return launch<256, EPI_GEGLU, 1, true>(ta, ta, ta, tw, td, td, p, st);
+  }
   // temporal PE term: when the 128 rows of a tile share one frame the vector rides in the tile's bias table (plain epilogue)
   p.rowvec_in_table = (rowvec && rowvec_mod > 0 && (p.rowvec_div % BM) == 0) ? 1 : 0;
   if (rowvec && !p.rowvec_in_table) {
@@ -995,6 +1168,12 @@ extern "C" int i360_gemm_ln_bf16(const void* A, long long lda, const void* Wf, l
       case 160: return launch<160, EPI_ROWVEC, 1, true>(ta, ta, ta, tw, td, td, p, st);
       case 192: return launch<192, EPI_ROWVEC, 1, true>(ta, ta, ta, tw, td, td, p, st);
       case 256: return launch<256, EPI_ROWVEC, 1, true>(ta, ta, ta, tw, td, td, p, st);
+    }
+  } else if (four_groups()) {
+    switch (bn) {
+      case 160: return launch<160, EPI_PLAIN, 1, true, false, 4>(ta, ta, ta, tw, td, td, p, st);
+      case 192: return launch<192, EPI_PLAIN, 1, true, false, 4>(ta, ta, ta, tw, td, td, p, st);
+      case 256: return launch<256, EPI_PLAIN, 1, true, false, 4>(ta, ta, ta, tw, td, td, p, st);
     }
   } else {
     switch (bn) {

@@ -48,6 +48,14 @@ if kind == "ln":
     M, C = a
     x = torch.randn(M, C, device="cuda").bfloat16(); g = torch.ones(C, device="cuda").bfloat16(); b = torch.zeros(C, device="cuda").bfloat16()
     fn = lambda: ops.layernorm(x, g, b)
+if kind == "gemmln":      # LayerNorm-folded consumer (the producer GEMM runs once, before the loop)
+    M, N, K = a[:3]; act = a[3] if len(a) > 3 else 0
+    a0 = torch.randn(M, 320, device="cuda").bfloat16(); w0 = torch.randn(K, 320, device="cuda").bfloat16()
+    x, st = ops.gemm(a0, w0, rowstats=True)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16(); bb = torch.randn(N, device="cuda").bfloat16() if act else None
+    wf, u, c = ops.fold_layernorm(w, bb, torch.ones(K, device="cuda").bfloat16(), torch.zeros(K, device="cuda").bfloat16(), geglu=bool(act))
+    out = torch.empty(M, N // 2 if act == 1 else N, device="cuda", dtype=torch.bfloat16)
+    fn = lambda: ops.gemm_ln(x, st, wf, u, c, 1e-5, act=act, out=out)
 for _ in range(4):
     fn()
 torch.cuda.synchronize()
