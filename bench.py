@@ -608,6 +608,67 @@ def kernel_roofline(pipe, inp, size, one_step):
     return roof, breakdown
 
 
+def encoders_block(device, frames=16):
+    """the conditioning encoders of ONE clip -- SAM ViT-B on 2 x F anchor frames in batches of 8
+    (pipeline...dual.py:675-718) and the SD-2.1 CLIP text tower on [uncond, cond] (:227-299) -- through the native kernels,
+    next to the same algorithm on torch-CUDA in fp32, which is how the reference runs both (inference_dual_p2e.py:370-372,
+    :457: the encoders are never cast to bf16).  Random-init weights of the published shapes."""
+    from imagine360_b200.host.encoders import SamImageEncoderNative, wrap_text_encoder
+    from imagine360_b200.host.sam import build_sam_vit_b
+    from oracle import encoders as OE          # torch-CUDA comparator leg only (like gpu_comparator)
+    out = {}
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        return sorted(ts)[len(ts) // 2]
+
+    g = torch.Generator().manual_seed(3)
+    sam = build_sam_vit_b()
+    with torch.no_grad():
+        for n_, p_ in sam.image_encoder.named_parameters():
+            if "rel_pos" in n_ or n_ == "pos_embed":
+                p_.copy_(torch.randn(p_.shape, generator=g) * 0.2)
+    enc = sam.image_encoder.to(device)
+    nat = SamImageEncoderNative(enc)
+    x = torch.randn(8, 3, 1024, 1024, generator=g).to(device)
+    n_batches = 2 * frames // 8
+    ms = timed(lambda: [nat(x) for _ in range(n_batches)])
+    sd = {k: v for k, v in enc.state_dict().items()}
+    ms_t = timed(lambda: [OE.sam_image_encoder_forward(sd, x, 12, 14, (2, 5, 8, 11)) for _ in range(n_batches)], reps=2)
+    tok, c = 4096, 768
+    per_img = 12 * (2 * tok * c * 3 * c + 2 * tok * c * c + 4 * tok * c * 4 * c) + 4 * 4 * tok * tok * c + 8 * 25 * 4 * 196 * 196 * c \
+        + 2 * tok * 768 * 768 + 2 * tok * c * 256 + 2 * tok * 9 * 256 * 256
+    fl = per_img * 8.0 * n_batches
+    out["sam_vit_b"] = {"frames": 8 * n_batches, "ms": ms, "tflops": fl / ms / 1e9, "torch_cuda_fp32_ms": ms_t, "speedup_vs_torch_cuda": ms_t / ms,
+                        "workload": "ImageEncoderViT (768 x 12 blocks, 1024 px, 14 x 14 windows + 4 global blocks), 2 x 16 frames in batches of 8"}
+    del nat, enc, sam, sd, x
+    torch.cuda.empty_cache()
+    try:
+        import transformers
+        cfg = transformers.CLIPTextConfig(hidden_size=1024, intermediate_size=4096, num_hidden_layers=23, num_attention_heads=16,
+                                          vocab_size=49408, max_position_embeddings=77, hidden_act="gelu", projection_dim=512)
+        m = transformers.CLIPTextModel(cfg).eval().to(device)
+        ids = torch.randint(0, 49408, (2, 77), generator=g).to(device)
+        wrapped = wrap_text_encoder(m)
+        with torch.no_grad():
+            ms = timed(lambda: wrapped(ids)[0], reps=5)
+            ms_t = timed(lambda: m(ids)[0], reps=5)
+        out["clip_text"] = {"tokens": 2 * 77, "ms": ms, "torch_cuda_fp32_ms": ms_t, "speedup_vs_torch_cuda": ms_t / ms,
+                            "workload": "CLIPTextModel of SD-2.1 (1024 x 23 layers, 16 heads), [uncond, cond] x 77 tokens; launch-latency bound (154 rows)"}
+    except Exception as ex:      # transformers missing on the box: the SAM half still stands
+        out["clip_text"] = {"error": repr(ex)}
+    return out
+
+
 def preprocess_roofline(device, frames=16, pano_hw=(512, 1024), res=256, cpu=True):
     """SURVEY.md 8(f) row 1: ``process_equi`` (16 frames x 20 views, bicubic BORDER_WRAP remap) on the GPU, HBM bound;
     algorithmic bytes = float frames in + uint8 frames out and in again + float views out + maps.  The CPU figure beside
@@ -794,6 +855,12 @@ def main():
             out["preprocess"] = preprocess_roofline(device, cpu=not args.no_cpu_baseline)
         except Exception as ex:
             out["preprocess"] = {"error": repr(ex)}
+        try:
+            with torch.no_grad():
+                out["encoders"] = encoders_block(device)
+        except Exception as ex:
+            out["encoders"] = {"error": repr(ex)}
+        torch.cuda.empty_cache()
     if not args.no_cpu_baseline and world == 1:
         run, flops, sample = cpu_sample_step()
         sec = run()

@@ -29,6 +29,11 @@ BOUNDARY = {
     # output side (section 8(f) row 3): uint8 conversion of the decoded video on the GPU
     "animatediff.utils.util": {"save_videos_grid": ("imagine360_b200.host.preprocess", "save_videos_grid")},
     "diffusers": {"AutoencoderKL": ("imagine360_b200.host.vae", "AutoencoderKL"), "DDIMScheduler": ("imagine360_b200.host.ddim", "DDIMScheduler")},
+    # conditioning encoders (section 8(f) row 2).  segment_anything is a third-party dependency of the script
+    # (inference_dual_p2e.py:369-370): the registry / predictor it imports resolve to the native ViT, with or without the
+    # package installed.  CLIPTextModel keeps coming from transformers (the pipeline wraps the instance it is handed).
+    "segment_anything": {"sam_model_registry": ("imagine360_b200.host.sam", "sam_model_registry"),
+                         "SamPredictor": ("imagine360_b200.host.pipeline", "SamPredictor")},
 }
 
 

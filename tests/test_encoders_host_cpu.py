@@ -129,3 +129,33 @@ def test_wrappers_leave_unknown_modules_alone():
     assert not SamImageEncoderNative.supports(lin)
     with pytest.raises(TypeError):
         SamImageEncoderNative(lin)
+
+
+def test_segment_anything_mirror_layout_and_dropin():
+    """inference_dual_p2e.py:369-370 `from segment_anything import SamPredictor, sam_model_registry` resolves through the
+    drop-in; the ViT-B container has the published layout (89.67 M parameters, segment_anything parameter names) and no
+    CPU forward."""
+    import sys
+    import imagine360_b200.dropin as dropin
+    had = sys.modules.get("segment_anything")
+    try:
+        done = dropin.install()
+        assert set(done["segment_anything"]) == {"sam_model_registry", "SamPredictor"}
+        from segment_anything import SamPredictor, sam_model_registry
+        sam = sam_model_registry["vit_b"]()
+        enc = sam.image_encoder
+        n = sum(p.numel() for p in enc.parameters())
+        assert n == 89_670_912, n
+        sd = enc.state_dict()
+        assert sd["blocks.2.attn.rel_pos_h"].shape == (127, 64) and sd["blocks.0.attn.rel_pos_h"].shape == (27, 64)
+        assert sd["pos_embed"].shape == (1, 64, 64, 768) and sd["neck.2.weight"].shape == (256, 256, 3, 3)
+        assert [b.window_size for b in enc.blocks] == [14, 14, 0, 14, 14, 0, 14, 14, 0, 14, 14, 0]
+        pred = SamPredictor(sam)
+        assert pred.native_encoder is not None and pred.transform.target_length == 1024
+        with pytest.raises(RuntimeError):
+            enc(torch.zeros(1, 3, 1024, 1024))
+    finally:
+        if had is None:
+            sys.modules.pop("segment_anything", None)
+        else:
+            sys.modules["segment_anything"] = had
