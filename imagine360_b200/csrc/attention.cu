@@ -241,6 +241,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_wait();        // set-up done under the previous kernel's tail; from here on global memory is touched
+  griddep_launch();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;      // O of (head g, column half h) at tO + (g * 2 + h) * HD
 
@@ -426,7 +428,7 @@ static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtenso
       return I360_ERR_CUDA;
     attr_set = true;
   }
-  attention_kernel<HD, BIAS, G><<<dim3(p.q_tiles, heads / G, batch), kAttnThreads, smem, st>>>(q, k, v, b, p);
+  launch_k(attention_kernel<HD, BIAS, G>, dim3(p.q_tiles, heads / G, batch), dim3(kAttnThreads), smem, st, q, k, v, b, p);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -534,6 +536,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_wait();
+  griddep_launch();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -738,7 +742,7 @@ static int launch_attn2(const CUtensorMap& q, const CUtensorMap& k, const CUtens
       return I360_ERR_CUDA;
     attr_set = true;
   }
-  attention2_kernel<<<dim3(p.q_tiles / 2, heads, batch), kAttn2Threads, smem, st>>>(q, k, v, p);
+  launch_k(attention2_kernel, dim3(p.q_tiles / 2, heads, batch), dim3(kAttn2Threads), smem, st, q, k, v, p);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }

@@ -119,6 +119,26 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL) -- an EXPERIMENT that is off by default (tmap.h::pdl_enabled holds the numbers: it made
+// the step 0.4-2 % slower).  With I360_PDL=1 every kernel of the library is launched with the programmatic-stream-serialization
+// attribute (tmap.h::launch_k), executes griddep_wait() BEFORE its first access to global memory that an earlier kernel
+// may have written (or may still be reading), and griddep_launch() right after its own set-up: the next kernel's CTAs are
+// then scheduled onto SMs as this grid's CTAs retire and run THEIR set-up (barrier init, TMEM allocation, descriptor
+// prefetch, ~2-4 us with the launch latency) under this grid's tail instead of after it.  griddep_wait() returns only when
+// the prerequisite grid has completed and its memory operations are visible, so data dependencies are exactly those of
+// plain stream order; without the launch attribute both instructions are no-ops.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef I360_PDL_EARLY_TRIGGER
+#define I360_PDL_EARLY_TRIGGER 1      // 0: no explicit trigger (dependents are released when the CTAs exit)
+#endif
+__device__ __forceinline__ void griddep_launch() {
+#if I360_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+// ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, TMEM loads, fences
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {

@@ -17,6 +17,8 @@ __device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2
 // out [B, 2H, 2*(W + 2*pad_in), C]; out col w' reads in col ((w'/2) - pad_in) mod W
 __global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int B, int H, int W, int C,
                                   int pad_in) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   const int nvec = C >> 3, Wo = 2 * (W + 2 * pad_in), Ho = 2 * H;
   const long long total = static_cast<long long>(B) * Ho * Wo * nvec;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -37,6 +39,8 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__
 // diffusers/models/resnet.py:184); circular != 0: columns wrap instead (pano halo), rows zero-pad
 __global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int B, int H, int W, int C,
                                  int circular, int pad_lo) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   const int nvec = C >> 3, Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(B) * Ho * Wo * 9 * nvec;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -59,6 +63,8 @@ __global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
 
 __global__ void axpby_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, bf16* __restrict__ out, float a,
                              float b, long long n) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     // reference order: (y * b) rounded to bf16, then x + that (add_noise_to_condition, MVGenModel.py:11-14)
@@ -71,6 +77,8 @@ __global__ void axpby_kernel(const bf16* __restrict__ x, const bf16* __restrict_
 __global__ void cfg_ddim_kernel(const bf16* __restrict__ x, const bf16* __restrict__ vu, const bf16* __restrict__ vc,
                                 bf16* __restrict__ out, float guidance, float sa, float sb, float sap, float sbp,
                                 long long n) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float xs = __bfloat162float(x[i]), u = __bfloat162float(vu[i]), c = __bfloat162float(vc[i]);
@@ -83,6 +91,8 @@ __global__ void cfg_ddim_kernel(const bf16* __restrict__ x, const bf16* __restri
 
 // x [B, F, D, C] -> out [B, F/4, D, C], mean over groups of 4 frames
 __global__ void avgpool_frames4_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int B, int F, long long DC) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   const int Fo = F / 4;
   const long long total = static_cast<long long>(B) * Fo * DC;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -101,6 +111,8 @@ __global__ void avgpool_frames4_kernel(const bf16* __restrict__ x, bf16* __restr
 // One thread per output pixel, looping channels (the 4 taps and weights are reused by every channel).
 __global__ void grid_sample_kernel(const float* __restrict__ img, const float* __restrict__ grid, float* __restrict__ out,
                                    int N, int C, int Hi, int Wi, int Ho, int Wo, int nearest) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   const long long total = static_cast<long long>(N) * Ho * Wo;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -148,8 +160,7 @@ using namespace i360;
 extern "C" int i360_upsample2x_nhwc(const void* x, void* out, int B, int H, int W, int C, int pad_in, void* stream) {
   if (!x || !out || (C % 8) || B <= 0 || pad_in < 0 || pad_in > W) return I360_ERR_ARG;
   const long long total = static_cast<long long>(B) * 2 * H * 2 * (W + 2 * pad_in) * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(x), static_cast<bf16*>(out), B, H, W, C, pad_in);
+  launch_k(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x), static_cast<bf16*>(out), B, H, W, C, pad_in);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -158,16 +169,14 @@ extern "C" int i360_im2col3x3_s2_nhwc(const void* x, void* out, int B, int H, in
                                       void* stream) {
   if (!x || !out || (C % 8) || (H % 2) || (W % 2) || B <= 0 || pad_lo < 0 || pad_lo > 1) return I360_ERR_ARG;
   const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * 9 * (C / 8);
-  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(x), static_cast<bf16*>(out), B, H, W, C, circular, pad_lo);
+  launch_k(im2col_s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x), static_cast<bf16*>(out), B, H, W, C, circular, pad_lo);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
 
 extern "C" int i360_axpby_bf16(const void* x, const void* y, void* out, float a, float b, long long n, void* stream) {
   if (!x || !out || n <= 0) return I360_ERR_ARG;
-  axpby_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(x), static_cast<const bf16*>(y), static_cast<bf16*>(out), a, b, n);
+  launch_k(axpby_kernel, dim3(grid_for(n, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x), static_cast<const bf16*>(y), static_cast<bf16*>(out), a, b, n);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -176,8 +185,7 @@ extern "C" int i360_cfg_ddim_step_bf16(const void* latent, const void* pred_unco
                                        float guidance, float sqrt_a_t, float sqrt_1m_a_t, float sqrt_a_prev,
                                        float sqrt_1m_a_prev, long long n, void* stream) {
   if (!latent || !pred_uncond || !pred_cond || !out || n <= 0) return I360_ERR_ARG;
-  cfg_ddim_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(latent), static_cast<const bf16*>(pred_uncond), static_cast<const bf16*>(pred_cond),
+  launch_k(cfg_ddim_kernel, dim3(grid_for(n, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(latent), static_cast<const bf16*>(pred_uncond), static_cast<const bf16*>(pred_cond),
       static_cast<bf16*>(out), guidance, sqrt_a_t, sqrt_1m_a_t, sqrt_a_prev, sqrt_1m_a_prev, n);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
@@ -186,8 +194,7 @@ extern "C" int i360_cfg_ddim_step_bf16(const void* latent, const void* pred_unco
 extern "C" int i360_avgpool_frames4_bf16(const void* x, void* out, int B, int F, long long DC, void* stream) {
   if (!x || !out || B <= 0 || F < 4 || DC <= 0) return I360_ERR_ARG;
   const long long total = static_cast<long long>(B) * (F / 4) * DC;
-  avgpool_frames4_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(x), static_cast<bf16*>(out), B, F, DC);
+  launch_k(avgpool_frames4_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x), static_cast<bf16*>(out), B, F, DC);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -196,7 +203,7 @@ extern "C" int i360_grid_sample_f32(const float* img, const float* grid, float* 
                                     int Ho, int Wo, int nearest, void* stream) {
   if (!img || !grid || !out || N <= 0 || C <= 0) return I360_ERR_ARG;
   const long long total = static_cast<long long>(N) * Ho * Wo;
-  grid_sample_kernel<<<grid_for(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(img, grid, out, N, C, Hi, Wi,
+  launch_k(grid_sample_kernel, dim3(grid_for(total, 128)), dim3(128), 0, static_cast<cudaStream_t>(stream), img, grid, out, N, C, Hi, Wi,
                                                                                            Ho, Wo, nearest);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;

@@ -18,6 +18,8 @@ constexpr int kRelThreads = 256;
 __global__ void __launch_bounds__(kRelThreads)
 relpos_bias_kernel(const bf16* __restrict__ q, long long ldq, int col0, int heads, int hd, int S,
                    const bf16* __restrict__ rel_h, const bf16* __restrict__ rel_w, bf16* __restrict__ bias, int ldb) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int N = S * S, L = 2 * S - 1, pitch = hd + 2;      // 33-word rows for hd 64: consecutive rows hit distinct banks
   bf16* sRel = reinterpret_cast<bf16*>(smem_raw);           // [2][L][pitch]
@@ -114,8 +116,7 @@ extern "C" int i360_relpos_bias_bf16(const void* q, long long ldq, int col0, int
   }
   const dim3 grid((S * S + kRelQB - 1) / kRelQB, heads, items);
   if (grid.y > 65535u || grid.z > 65535u) return I360_ERR_ARG;
-  relpos_bias_kernel<<<grid, kRelThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(q), ldq, col0, heads, hd, S, static_cast<const bf16*>(rel_h), static_cast<const bf16*>(rel_w),
+  launch_k(relpos_bias_kernel, dim3(grid), dim3(kRelThreads), smem, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(q), ldq, col0, heads, hd, S, static_cast<const bf16*>(rel_h), static_cast<const bf16*>(rel_w),
       static_cast<bf16*>(bias), ldb);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;

@@ -181,6 +181,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_wait();        // barriers, TMEM and descriptors were set up under the previous kernel's tail (see common.cuh)
+  griddep_launch();
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -804,7 +806,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms()) grid = num_sms();
   if (grid <= 0) return I360_OK;
-  gemm_conv_kernel<BN, EPI, MT, LNF, HALO, NG><<<grid, C::kThreadsTotal, C::kSmemBytes, st>>>(a, a2, a3, w, d, rmap, p);
+  launch_k(gemm_conv_kernel<BN, EPI, MT, LNF, HALO, NG>, dim3(grid), dim3(C::kThreadsTotal), C::kSmemBytes, st, a, a2, a3, w, d, rmap, p);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }

@@ -51,6 +51,8 @@ constexpr int kGnDepth = 4;
 
 // grid (chunks, B); block = R * nvec threads; dynamic smem = R*C*2 floats
 __global__ void __launch_bounds__(384, 3) gn_stats_kernel(GnSrc s, int groups, int chunk_pixels, double* __restrict__ stats) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   extern __shared__ float sm[];
   const int C = s.C1 + s.C2, nvec = C >> 3, R = blockDim.x / nvec;
   const int Wv = s.Wsrc + 2 * s.pad;
@@ -108,6 +110,8 @@ __global__ void __launch_bounds__(384, 3) gn_stats_kernel(GnSrc s, int groups, i
 __global__ void __launch_bounds__(384, 3) gn_apply_kernel(GnSrc s, int groups, int chunk_pixels, const double* __restrict__ stats,
                                 const bf16* __restrict__ gamma, const bf16* __restrict__ beta, float eps,
                                 int do_silu, double count, bf16* __restrict__ out) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   extern __shared__ float sm[];
   const int C = s.C1 + s.C2, nvec = C >> 3, R = blockDim.x / nvec;
   const int Wv = s.Wsrc + 2 * s.pad;
@@ -170,6 +174,8 @@ layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y
                  float eps, const bf16* __restrict__ pre_add, int pre_div_a, int pre_mod_a,
                  int pre_mul_a, int pre_mod_b,
                  const float* __restrict__ post_add, int post_div, int post_mod) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   constexpr int VPL = 5, RPW = 32 / LPR, PD = 2;
   extern __shared__ uint4 ln_gb[];                 // [nvec] gamma vectors, then [nvec] beta vectors
   const int nvec = C >> 3;
@@ -284,6 +290,8 @@ layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y
 // softmax(scores.float()).type(bf16) on materialised scores (diffusers/models/attention.py:353-367)
 // ---------------------------------------------------------------------------------------------
 __global__ void softmax_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long ld, int N) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   __shared__ float red[32];
   const bf16* xr = x + static_cast<long long>(blockIdx.x) * ld;
   bf16* yr = y + static_cast<long long>(blockIdx.x) * ld;
@@ -327,8 +335,8 @@ using namespace i360;
 
 extern "C" int i360_softmax_rows_bf16(const void* x, void* y, long long ld, long long M, int N, void* stream) {
   if (!x || !y || M <= 0 || N <= 0 || (N % 8) || (ld % 8)) return I360_ERR_ARG;
-  softmax_rows_kernel<<<static_cast<unsigned>(M), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(x), static_cast<bf16*>(y), ld, N);
+  launch_k(softmax_rows_kernel, dim3(static_cast<unsigned>(M)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+           static_cast<const bf16*>(x), static_cast<bf16*>(y), ld, N);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -369,7 +377,7 @@ extern "C" int i360_groupnorm_stats(const void* x1, int C1, const void* x2, int 
   int r = gn_geometry(C, B, npix, &block, &chunk, &chunks); if (r) return r;
   const size_t smem = static_cast<size_t>(block) * 8 * 2 * sizeof(float);
   if (smem > 48 * 1024) return I360_ERR_ARG;
-  gn_stats_kernel<<<dim3(chunks, B), block, smem, st>>>(s, groups, chunk, stats);
+  launch_k(gn_stats_kernel, dim3(chunks, B), dim3(block), smem, st, s, groups, chunk, stats);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -387,7 +395,7 @@ extern "C" int i360_groupnorm_apply(const void* x1, int C1, const void* x2, int 
   const long long npix = static_cast<long long>(H) * (Wsrc + 2 * pad);
   int r = gn_geometry(C, B, npix, &block, &chunk, &chunks); if (r) return r;
   const size_t smem = static_cast<size_t>(C) * 2 * sizeof(float);
-  gn_apply_kernel<<<dim3(chunks, B), block, smem, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(gn_apply_kernel, dim3(chunks, B), dim3(block), smem, static_cast<cudaStream_t>(stream),
       s, groups, chunk, stats, static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), eps, do_silu,
       stats_count, static_cast<bf16*>(out));
   I360_CUDA_CHECK_LAUNCH();
@@ -414,7 +422,7 @@ extern "C" int i360_layernorm(const void* x, long long ldx, void* y, long long l
   const bf16* pa = static_cast<const bf16*>(pre_add);
   bf16* yy = static_cast<bf16*>(y);
   const size_t smem = static_cast<size_t>(nvec) * 2 * sizeof(uint4);
-#define I360_LN_LAUNCH(L) layernorm_kernel<L><<<grid, warps * 32, smem, st>>>(xx, ldx, yy, ldy, M, C, g, b, eps, pa, pre_div_a, pre_mod_a, pre_mul_a, pre_mod_b, post_add, post_div, post_mod)
+#define I360_LN_LAUNCH(L) launch_k(layernorm_kernel<L>, dim3(grid), dim3(warps * 32), smem, st, xx, ldx, yy, ldy, M, C, g, b, eps, pa, pre_div_a, pre_mod_a, pre_mul_a, pre_mod_b, post_add, post_div, post_mod)
   if (lpr == 8) I360_LN_LAUNCH(8);
   else if (lpr == 16) I360_LN_LAUNCH(16);
   else I360_LN_LAUNCH(32);

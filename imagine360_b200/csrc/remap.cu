@@ -39,6 +39,8 @@ __device__ __forceinline__ int wrap_index(int p, int n) {   // borderInterpolate
 
 __global__ void __launch_bounds__(256)
 remap_cubic_wrap_kernel(const RemapParams p) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   const long long hw = static_cast<long long>(p.h) * p.w;
   const int n_out = p.paired ? 1 : p.n_map;
   const long long total = hw * n_out * p.n_img;
@@ -134,6 +136,8 @@ remap_cubic_wrap_kernel(const RemapParams p) {
 __global__ void __launch_bounds__(256)
 frames_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, long long n, long long hw, int back_norm,
                     long long frame_stride, long long chan_stride) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   const long long total = n * hw;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -213,7 +217,7 @@ extern "C" int i360_remap_cubic_wrap_u8(const void* src, int n_img, int H, int W
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
-  remap_cubic_wrap_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  launch_k(remap_cubic_wrap_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
@@ -226,8 +230,7 @@ extern "C" int i360_frames_to_u8_nhwc(const float* x, long long frame_stride, lo
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
-  frames_to_u8_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, static_cast<uint8_t*>(out), n, static_cast<long long>(H) * W, back_norm, frame_stride, chan_stride);
+  launch_k(frames_to_u8_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, static_cast<uint8_t*>(out), n, static_cast<long long>(H) * W, back_norm, frame_stride, chan_stride);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }

@@ -26,6 +26,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 // MODE 0: F <= 16, two lanes per query row (8 keys each).  MODE 1: F <= 32, one lane per row.
 template <int MODE>
 __global__ void temporal_attn_kernel(const TAParams p) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   extern __shared__ __align__(16) uint8_t smem_ta[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int tile_elems = p.F * p.hd;                 // per tensor
@@ -155,6 +157,8 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
 // latency) set its bandwidth: 16 warps x 1 task ahead = 61 KB gave 3.9 TB/s; 3 stages put 2 tasks per warp in flight.
 template <int STAGES>
 __global__ void temporal_attn_mma_kernel(const TAParams p, int hd_pad, int pitch) {
+  griddep_wait();        // PDL: see common.cuh
+  griddep_launch();
   extern __shared__ __align__(16) uint8_t smem_ta[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int stage_elems = 3 * 16 * pitch;
@@ -336,19 +340,19 @@ extern "C" int i360_temporal_attention_bf16(const void* q, long long ldq, const 
       cudaFuncSetAttribute(temporal_attn_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       setm = true;
     }
-    if (three) temporal_attn_mma_kernel<3><<<static_cast<unsigned>(bl), w2 * 32, sm2, st>>>(p, hd_pad, pitch);
-    else       temporal_attn_mma_kernel<2><<<static_cast<unsigned>(bl), w2 * 32, sm2, st>>>(p, hd_pad, pitch);
+    if (three) launch_k(temporal_attn_mma_kernel<3>, dim3(static_cast<unsigned>(bl)), dim3(w2 * 32), sm2, st, p, hd_pad, pitch);
+    else       launch_k(temporal_attn_mma_kernel<2>, dim3(static_cast<unsigned>(bl)), dim3(w2 * 32), sm2, st, p, hd_pad, pitch);
     I360_CUDA_CHECK_LAUNCH();
     return I360_OK;
   }
   if (F <= 16) {
     static bool set0 = false;
     if (!set0) { cudaFuncSetAttribute(temporal_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set0 = true; }
-    temporal_attn_kernel<0><<<static_cast<unsigned>(blocks), warps * 32, smem, st>>>(p);
+    launch_k(temporal_attn_kernel<0>, dim3(static_cast<unsigned>(blocks)), dim3(warps * 32), smem, st, p);
   } else {
     static bool set1 = false;
     if (!set1) { cudaFuncSetAttribute(temporal_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set1 = true; }
-    temporal_attn_kernel<1><<<static_cast<unsigned>(blocks), warps * 32, smem, st>>>(p);
+    launch_k(temporal_attn_kernel<1>, dim3(static_cast<unsigned>(blocks)), dim3(warps * 32), smem, st, p);
   }
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;

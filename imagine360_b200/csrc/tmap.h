@@ -2,6 +2,7 @@
 // The driver entry point is fetched through the runtime (cudaGetDriverEntryPoint) so the shared
 // library has no link-time dependency on libcuda and loads on a GPU-less build box.
 #pragma once
+#include <stdlib.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -106,6 +107,30 @@ inline int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+// EXPERIMENT, off by default: I360_PDL=1 launches every kernel with the programmatic-dependent-launch attribute (without it
+// the griddepcontrol instructions in the kernels are no-ops).  Measured on one B200, CUDA-graphed 16x512x1024 step, same box,
+// two alternating repetitions: 319.3 / 319.3 ms with the early trigger, 313.8 / 313.9 ms with the attribute but no explicit
+// trigger (-DI360_PDL_EARLY_TRIGGER=0), 312.5 / 312.6 ms without PDL; the 24x768x1536 step 1380-1389 vs 1360 ms, the
+// 16x256x512 single-branch step 23.6-23.8 vs 23.5-23.9 ms.  Inside a graph the kernel-to-kernel gap is already small, and
+// the early-launched CTAs (resident next to the primary grid whenever their shared memory fits, e.g. the normalisation
+// kernels next to a GEMM) take more from the running grid than their hidden set-up gives back.
+inline bool pdl_enabled() {
+  static const bool on = getenv("I360_PDL") != nullptr && atoi(getenv("I360_PDL")) != 0;
+  return on;
+}
+
+// <<<grid, block, smem, stream>>> with the PDL attribute (see common.cuh)
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface through cudaGetLastError()
 }
 
 #define I360_CUDA_CHECK_LAUNCH()                         \

@@ -151,6 +151,8 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_wait();
+  griddep_launch();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -332,7 +334,7 @@ extern "C" int i360_cross_attention_text_ip_bf16(const void* q, long long ldq, v
   }
   const long long sms = num_sms();
   const int grid = static_cast<int>(p.total_tiles < sms ? p.total_tiles : sms);
-  xattn_kernel<<<grid, kXThreads, kXSmem, static_cast<cudaStream_t>(stream)>>>(tq, tkt, tki, p);
+  launch_k(xattn_kernel, dim3(grid), dim3(kXThreads), kXSmem, static_cast<cudaStream_t>(stream), tq, tkt, tki, p);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }
