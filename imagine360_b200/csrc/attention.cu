@@ -201,7 +201,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   static_assert(G == 1 || G == 2, "heads per CTA");
   static_assert(128 + G * 2 * HD <= C::kTmemCols, "accumulators of all heads must fit next to S");
   extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if ((smem_u32(smem) & 1023u) != 0) i360_device_fail("dynamic shared memory is not 1024-byte aligned (128B-swizzled TMA / UMMA tiles)");
   uint8_t* sQ = smem;                        // G query tiles (one per head)
   uint8_t* sK = sQ + G * C::kQBytes;         // 2 stages
   uint8_t* sV = sK + 2 * C::kKVBytes;        // 2 stages
@@ -491,7 +491,7 @@ __device__ __forceinline__ void mbar_wait_fast(uint64_t* bar, uint32_t parity) {
         "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (++spins > I360_SPIN_LIMIT) __trap();
+    if (++spins > I360_SPIN_LIMIT) i360_device_fail("mbarrier test_wait exceeded the spin limit");
   } while (!ok);
 #else
   mbar_wait(bar, parity);
@@ -505,7 +505,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   using C = AttnCfg<HD>;
   constexpr int NS = kAttn2Stages;
   extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if ((smem_u32(smem) & 1023u) != 0) i360_device_fail("dynamic shared memory is not 1024-byte aligned (128B-swizzled TMA / UMMA tiles)");
   uint8_t* sQ = smem;                              // 2 query tiles
   uint8_t* sK = sQ + 2 * C::kQBytes;               // NS stages
   uint8_t* sV = sK + NS * C::kKVBytes;             // NS stages

@@ -53,6 +53,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// A failed invariant inside a kernel traps (a device printf in these register-tight kernels costs stack frames and spills:
+// measured with ptxas -v).  The two invariants are: dynamic shared memory 1024-byte aligned (128B-swizzled TMA / UMMA tiles),
+// and no mbarrier wait longer than I360_SPIN_LIMIT polls (pipeline deadlock guard).  The host names the failing entry point
+// (tmap.h::I360_CUDA_CHECK_LAUNCH) when the sticky error surfaces.
+#define i360_device_fail(what) __trap()
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -67,7 +72,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > I360_SPIN_LIMIT) { __trap(); }
+    if (++spins > I360_SPIN_LIMIT) i360_device_fail("mbarrier wait exceeded the spin limit (pipeline deadlock guard)");
   }
 }
 

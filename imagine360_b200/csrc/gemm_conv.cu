@@ -147,7 +147,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr bool kRing = UseRing<BN, EPI>::value;
   using C = Cfg<BN, kRing, MT, LNF, HALO, NG>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();   // 128B-swizzled TMA / UMMA tiles need 1024-byte aligned stages
+  if ((smem_u32(smem_raw) & 1023u) != 0) i360_device_fail("dynamic shared memory is not 1024-byte aligned (128B-swizzled TMA / UMMA tiles)");
   uint8_t* shalo = smem_raw;                          // HALO: kHaloStages activation tiles in front of the weight ring
   uint8_t* smem = smem_raw + C::kHaloTotal;
   const uint32_t base = smem_u32(smem);

@@ -2,6 +2,7 @@
 // The driver entry point is fetched through the runtime (cudaGetDriverEntryPoint) so the shared
 // library has no link-time dependency on libcuda and loads on a GPU-less build box.
 #pragma once
+#include <stdio.h>
 #include <stdlib.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -91,7 +92,9 @@ inline int get_tmap_bf16(CUtensorMap* out, const void* ptr, uint32_t rank, const
   if (r != CUDA_SUCCESS) return I360_ERR_TMAP;
   {
     std::lock_guard<std::mutex> g(mu);
-    if (cache.size() > 200000) cache.clear();
+    // bounded: a denoising run re-uses a few thousand (pointer, shape) pairs; long-lived processes that keep allocating new
+    // buffers (eager mode, many resolutions) restart the cache instead of growing without limit (encode costs ~1 us)
+    if (cache.size() > 32768) cache.clear();
     cache.emplace(key, m);
   }
   *out = m;
@@ -133,10 +136,16 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface through cudaGetLastError()
 }
 
-#define I360_CUDA_CHECK_LAUNCH()                         \
-  do {                                                   \
-    cudaError_t e__ = cudaGetLastError();                \
-    if (e__ != cudaSuccess) return i360::I360_ERR_CUDA;  \
+// launch errors (and sticky errors of an earlier kernel, e.g. a device assertion) are named on stderr: the reference's
+// script swallows exceptions around the pipeline call (inference_dual_p2e.py:596-597)
+#define I360_CUDA_CHECK_LAUNCH()                                                                          \
+  do {                                                                                                    \
+    cudaError_t e__ = cudaGetLastError();                                                                 \
+    if (e__ != cudaSuccess) {                                                                             \
+      fprintf(stderr, "imagine360_b200: CUDA error '%s' after a launch in %s (a trap = a kernel invariant failed: "    \
+              "smem alignment or an mbarrier wait past the deadlock guard)\n", cudaGetErrorString(e__), __func__);       \
+      return i360::I360_ERR_CUDA;                                                                         \
+    }                                                                                                     \
   } while (0)
 
 }  // namespace i360

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kXThreads, 1)
 xattn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKt,
              const __grid_constant__ CUtensorMap tmKi, const XAttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if ((smem_u32(smem) & 1023u) != 0) i360_device_fail("dynamic shared memory is not 1024-byte aligned (128B-swizzled TMA / UMMA tiles)");
   uint8_t* sK = smem;
   uint8_t* sV = sK + kXKVBytes;
   uint8_t* sQ = sV + kXKVBytes;

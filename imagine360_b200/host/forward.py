@@ -74,11 +74,19 @@ def tokens(x):
 LN_FOLD = os.environ.get("I360_LN_FOLD", "1") not in ("", "0")
 
 
-def token_linear(a, w, bias=None, resid=None):
+def token_linear(a, w, bias=None, resid=None, want_stats=True):
     """A projection whose output is the residual stream a LayerNorm reads next: -> (tokens, row statistics | None)."""
-    if LN_FOLD:
+    if LN_FOLD and want_stats:
         return ops.gemm(a, w, bias=bias, resid=resid, rowstats=True)
     return ops.gemm(a, w, bias=bias, resid=resid), None
+
+
+def fold_pays(k: int, act: int) -> bool:
+    """Measured per consumer inside the 16x512x1024 step (profiles/r02b_ln_fold_per_shape_ab.txt, bench breakdowns): the
+    folded GEGLU projection costs +0.18 ms at K = 320 and +0.07 ms at K = 640 -- its epilogue is the bottleneck there and the
+    fold adds to it -- against LayerNorm passes of 0.14 / 0.07 ms, so those two keep the separate LayerNorm; everything else
+    (QKV, to_q, GEGLU at K = 1280) folds."""
+    return not (act == ops.ACT_GEGLU and k < 1280)
 
 
 def ln_linear(t, stats, norm, owner, key, mods, bias_mod=None, act=ops.ACT_NONE, pe=None, pe_div=1, pe_mod=0):
@@ -88,7 +96,7 @@ def ln_linear(t, stats, norm, owner, key, mods, bias_mod=None, act=ops.ACT_NONE,
     ws = [m.weight for m in mods]
     n_total, k = sum(w.shape[0] for w in ws), ws[0].shape[1]
     geglu = act == ops.ACT_GEGLU
-    if stats is not None and ops.gemm_ln_supported(n_total, k, act):
+    if stats is not None and fold_pays(k, act) and ops.gemm_ln_supported(n_total, k, act):
         params = ws + [norm.weight, norm.bias] + ([bias_mod.bias] if bias_mod is not None and bias_mod.bias is not None else [])
 
         def build():
@@ -239,7 +247,7 @@ def spatial_transformer(x, t3d, ctx: Context, frames: int):
             ops.attention(qv, ops.seq_view(kv_i, ctx.n_ctx, ni, 0, share_div=frames),
                           ops.seq_view(kv_i, ctx.n_ctx, ni, c, share_div=frames), ov, heads, hd, n, accumulate=True)
         wo, bo = lin_w(a2.to_out[0])
-        t, st = token_linear(o, wo, bo, t)
+        t, st = token_linear(o, wo, bo, t, want_stats=fold_pays(c, ops.ACT_GEGLU))
         # --- GEGLU feed-forward ---
         t, st = feed_forward(t, st, blk.ff, blk.norm3)
     wo, bo = lin_w(t3d.proj_out)
@@ -272,13 +280,15 @@ def temporal_module(x, mm, frames: int):
     wi, bi = lin_w(tt.proj_in)
     t, st = token_linear(tokens(hn), wi, bi)
     for blk in tt.transformer_blocks:
-        for att, norm in zip(blk.attention_blocks, blk.norms):
+        n_att = len(blk.attention_blocks)
+        for ai, (att, norm) in enumerate(zip(blk.attention_blocks, blk.norms)):
             qkv = ln_linear(t, st, norm, att, "qkv", [att.to_q, att.to_k, att.to_v], pe=_pe_table(att, frames, BF16), pe_div=d,
                             pe_mod=frames)
             o = torch.empty_like(t)
             ops.temporal_attention(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], o, n // frames, frames, d, tt.heads, tt.dim_head)
             wo, bo = lin_w(att.to_out[0])
-            t, st = token_linear(o, wo, bo, t)
+            # the last attention block's output is read by ff_norm -> GEGLU, the others by the next block's norm -> QKV
+            t, st = token_linear(o, wo, bo, t, want_stats=ai + 1 < n_att or fold_pays(c, ops.ACT_GEGLU))
         t, st = feed_forward(t, st, blk.ff, blk.ff_norm)
     wo, bo = lin_w(tt.proj_out)
     return ops.gemm(t, wo, bias=bo, resid=tokens(x)).view(n, h, w, c)

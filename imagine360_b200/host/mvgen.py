@@ -130,13 +130,13 @@ class WarpAttn(nn.Module):
         o_e = torch.empty_like(et)
         ops.attention(ops.seq_view(q_e, bf, en), ops.multiview_view(kv_p, clips, views, frames, hw, 0),
                       ops.multiview_view(kv_p, clips, views, frames, hw, c), ops.seq_view(o_e, bf, en), heads, hd, bf, bias=bias_e)
-        e_out, e_st = Fw.token_linear(o_e, wo, bo, et)
+        e_out, e_st = Fw.token_linear(o_e, wo, bo, et, want_stats=Fw.fold_pays(c, ops.ACT_GEGLU))
         # equirect -> perspective
         q_p, kv_e = ops.gemm(pn, wq), ops.gemm(en_, wkv)
         o_p = torch.empty_like(pt)
         ops.attention(ops.multiview_view(q_p, clips, views, frames, hw), ops.seq_view(kv_e, bf, en, 0), ops.seq_view(kv_e, bf, en, c),
                       ops.multiview_view(o_p, clips, views, frames, hw), heads, hd, bf, bias=bias_p)
-        p_out, p_st = Fw.token_linear(o_p, wo, bo, pt)
+        p_out, p_st = Fw.token_linear(o_p, wo, bo, pt, want_stats=Fw.fold_pays(c, ops.ACT_GEGLU))
         e_out = _warp_ff(e_out, e_st, tr)
         p_out = _warp_ff(p_out, p_st, tr)
         return p_out.view_as(pers), e_out.view_as(equi)
