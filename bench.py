@@ -589,10 +589,15 @@ def kernel_roofline(pipe, inp, size, one_step):
     if tj and size is SIZES["c3"]:
         with open(tj) as f:
             t = json.load(f)
-        if t.get("launches") == gc_n:
+        # the profiled step is the first step of a clip (it also runs the adapter's ~67 GEMMs, which the steady step has cached):
+        # accept the capture when the engine launch counts agree to 10 % and say so
+        if abs(t.get("launches", 0) - gc_n) <= 0.1 * gc_n:
             roof["traffic"] = t["dram_bytes_per_launch"]
             roof["traffic_source"] = t["source"]
-            roof["alg_bytes_note"] = "tensor-bound kernel: achieved/peak are FLOP-based; traffic is DRAM bytes per launch (cold cache, ncu)"
+            roof["traffic_launches"] = t["launches"]
+            roof["traffic_share_of_step_kernel_time"] = t.get("share_of_step_kernel_time")
+            roof["alg_bytes_note"] = ("tensor-bound kernel: achieved/peak are FLOP-based; traffic is DRAM bytes per launch (cold cache, ncu, "
+                                      "one eager step incl. the per-clip adapter GEMMs)")
     breakdown = {n: {"launches": c, "ms": round(ms, 3)} for n, (c, ms) in sorted(per.items(), key=lambda kv: -kv[1][1])}
     agg = {}
     for kind, M, N, K, act, idx in shapes:
