@@ -856,15 +856,19 @@ static int pick_epi(const GemmConvParams& p) {
   return EPI_GENERAL;
 }
 
-// EXPERIMENT, off by default: I360_EPI_GROUPS=4 runs the LayerNorm-folded / GEGLU projections with four epilogue groups
-// (576 threads).  Measured on one B200 (tools/ln_fold_probe.py): folded QKV 655 360 x 960 x 320 0.503 -> 0.451 ms and plain
-// GEGLU x 2560 x 320 1.10 -> 0.99 ms, but folded GEGLU 1.22 -> 1.43 ms (its per-tile preamble -- tables, row statistics, three
-// barriers -- is paid by every group and is as long as the one chunk a group then computes) and N = 320 / 1920 unchanged;
-// step 312.6 / 313.8 ms with four groups against 312.7 / 312.8 ms with two -> the two-group kernels stay.
-static bool four_groups() {
-  static const bool on = getenv("I360_EPI_GROUPS") != nullptr && atoi(getenv("I360_EPI_GROUPS")) == 4;
-  return on;
+// Epilogue groups of the LayerNorm-folded / GEGLU projections.  Measured on one B200 (tools/ln_fold_probe.py): with four
+// groups (576 threads) the folded QKV projection 655 360 x 960 x 320 goes 0.503 -> 0.451 ms and the plain GEGLU x 2560 x 320
+// 1.10 -> 0.99 ms, but the folded GEGLU 1.22 -> 1.43 ms (its per-tile preamble -- tables, row statistics, three barriers -- is
+// paid by every group and is as long as the one chunk a group then computes) and N = 320 / 1920 are unchanged; with four
+// groups everywhere the step was 312.6 / 313.8 ms against 312.7 / 312.8 ms with two, with four groups for the folded PLAIN
+// projections only 305.6 ms against 304.7 / 305.8 ms: no gain inside the step -> the two-group kernels (which prefetch the row
+// statistics one tile ahead) stay the default.  I360_EPI_GROUPS=4 selects four groups everywhere, =3 for the plain ones only.
+static int epi_groups_env() {
+  static const int v = getenv("I360_EPI_GROUPS") ? atoi(getenv("I360_EPI_GROUPS")) : 0;
+  return v;
 }
+static bool four_groups() { return epi_groups_env() == 4; }                 // GEGLU kernels
+static bool four_groups_plain() { return epi_groups_env() >= 3; }           // LayerNorm-folded plain projections
 
 template <int BN>
 static int dispatch_epi(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& a3, const CUtensorMap& w,
@@ -1171,7 +1175,7 @@ extern "C" int i360_gemm_ln_bf16(const void* A, long long lda, const void* Wf, l
       case 192: return launch<192, EPI_ROWVEC, 1, true>(ta, ta, ta, tw, td, td, p, st);
       case 256: return launch<256, EPI_ROWVEC, 1, true>(ta, ta, ta, tw, td, td, p, st);
     }
-  } else if (four_groups()) {
+  } else if (four_groups_plain()) {
     switch (bn) {
       case 160: return launch<160, EPI_PLAIN, 1, true, false, 4>(ta, ta, ta, tw, td, td, p, st);
       case 192: return launch<192, EPI_PLAIN, 1, true, false, 4>(ta, ta, ta, tw, td, td, p, st);
