@@ -43,6 +43,11 @@ struct GemmConvParams {
   int n_wt, n_ht, n_bt;
   int Cin, C2, C3;    // channels of the 3x3 source and of up to two extra 1x1 sources
   int halo;           // CONV through the halo-tile kernels (TW = 8, TH = 16, TB = 1)
+  // CONV tap list (tap-by-tap mode): n_taps shifted boxes (dh, dw) per channel block, weights tap-major.  3x3: the nine
+  // (kh-1, kw-1); the sub-pixel form of nearest-upsample + 3x3 has four taps per output parity (i360_conv_upsample2x_bf16)
+  int n_taps; signed char tap_dh[9]; signed char tap_dw[9];
+  // direct (cropped) stores into a strided output lattice: element offsets of one step in w / h / image (0 = dense)
+  long long os_w, os_h, os_b;
   int crop;           // output columns cropped on each side (pano halo)
   int xoff;           // column offset applied to the extra 1x1 sources (= -crop: they are stored un-padded)
   int Hout, Wout;
@@ -235,8 +240,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         } else if (!p.conv) {
           for (int kb = 0; kb < p.k_iters; ++kb) issue(&tmA, kb * BK, 0, 0, kb * BK);
         } else {
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+          for (int tap = 0; tap < p.n_taps; ++tap) {
+            const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
             for (int c0 = 0; c0 < p.Cin; c0 += BK) issue(&tmA, c0, dw, dh, tap * p.Cin + c0);
           }
           for (int c0 = 0; c0 < p.C2; c0 += BK) issue(&tmA2, c0, p.xoff, 0, 9 * p.Cin + c0);
@@ -544,6 +549,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
       // ---- row mapping (residual / per-image vector reads, direct stores) ----
       bool valid = true; long long orow = 0; int vec_idx = 0;
+      long long dstr = -1;                     // strided output lattice: element offset of my row (direct stores only)
       int w0 = 0, h0 = 0, b0 = 0;
       if (p.conv) {
         w0 = (m_blk % p.n_wt) * p.TW; h0 = ((m_blk / p.n_wt) % p.n_ht) * p.TH; b0 = (m_blk / (p.n_wt * p.n_ht)) * p.TB;
@@ -552,6 +558,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int w = w0 + tw, h = h0 + th, b = b0 + tb;
           valid = (b < p.B) && (h < p.H) && (w >= p.crop) && (w < p.W - p.crop);
           orow = (static_cast<long long>(b) * p.Hout + h) * p.Wout + (w - p.crop);
+          if (p.os_w != 0) dstr = static_cast<long long>(b) * p.os_b + static_cast<long long>(h) * p.os_h + static_cast<long long>(w - p.crop) * p.os_w;
           vec_idx = b;
         }
       } else {
@@ -562,7 +569,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int rv_row = p.rowvec_mod > 0 ? (vec_idx / p.rowvec_div) % p.rowvec_mod : vec_idx / p.rowvec_div;
       const float* rv = (kRowvec && p.rowvec != nullptr) ? p.rowvec + static_cast<long long>(rv_row) * p.rowvec_ld : nullptr;
       const bf16* rrow = (kResid && !ring_on && p.resid != nullptr && valid) ? p.resid + orow * p.ldr : nullptr;
-      bf16* drow = p.D + orow * p.ldd;
+      bf16* drow = (dstr >= 0 && valid) ? p.D + dstr : p.D + orow * p.ldd;
 
       const float* tbias = sbias + grp * BN;
       const float* tu = su + grp * BN;
@@ -1061,15 +1068,19 @@ extern "C" int i360_conv3x3_uses_halo(int B, int H, int W, int Cin, int has_resi
 // x: NHWC [B,H,W,Cin] (H,W include any materialised halo); Wt: [Cout, 9*Cin + C2 + C3] with the
 // 3x3 part ordered (kh, kw, cin). x2/x3: optional NHWC [B,H,W-2*crop,C2|C3] sources for a fused 1x1
 // (stored WITHOUT the halo, i.e. aligned with the output). Output NHWC [B, H, W-2*crop, Cout].
-extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, const void* x2, int C2,
-                                 const void* x3, int C3, const void* Wt, int Cout, void* D,
-                                 int crop, const void* bias, const void* resid,
-                                 const float* rowvec, int rowvec_div, int rowvec_ld,
-                                 float out_scale, void* stream) {
+// Output placement of a convolution: dense NHWC [B, H, Wo, Cout] (lattice == nullptr), or a strided lattice inside a larger
+// NHWC tensor (the parity sub-lattices of the 2x-upsampled output): element strides of one step in w / h / image.
+struct OutLattice { long long s_w, s_h, s_b; };
+
+static int conv_impl(const void* x, int B, int H, int W, int Cin, const void* x2, int C2, const void* x3, int C3, const void* Wt,
+                     int Cout, void* D, const OutLattice* lattice, int crop, const void* bias, const void* resid, const float* rowvec,
+                     int rowvec_div, int rowvec_ld, float out_scale, int n_taps, const signed char* tap_dh, const signed char* tap_dw,
+                     void* stream) {
   if (!x || !Wt || !D || B <= 0 || H <= 0 || W <= 0) return I360_ERR_ARG;
   if ((Cin % 8) || (Cout % 8) || (C2 % 8) || (C3 % 8) || crop < 0 || 2 * crop >= W)
     return I360_ERR_ARG;
   if ((C2 > 0 && !x2) || (C3 > 0 && !x3)) return I360_ERR_ARG;
+  const bool is3x3 = (n_taps == 9);          // the halo kernels hard-wire the nine (kh-1, kw-1) taps
   // K segments need no 64-alignment: channels past a source's extent are zero-filled by TMA, so whatever
   // weight columns a partial K block overlaps are multiplied by zeros.
   // choose the pixel box minimising padded work
@@ -1077,21 +1088,24 @@ extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, co
   best_box(B, H, W, &bestTW, &bestTH, &bestTB, &bestw);
   GemmConvParams p;
   memset(&p, 0, sizeof(p));
-  p.halo = use_halo(H, W, Cin, resid != nullptr, rowvec != nullptr, C2 + C3 > 0, bestw + 1e-6 * bestTW);
+  p.halo = is3x3 && !lattice && use_halo(H, W, Cin, resid != nullptr, rowvec != nullptr, C2 + C3 > 0, bestw + 1e-6 * bestTW);
   if (p.halo) { bestTW = kHaloTW; bestTH = kHaloTH; bestTB = 1; }
   p.conv = 1; p.B = B; p.H = H; p.W = W; p.TW = bestTW; p.TH = bestTH; p.TB = bestTB;
   p.n_wt = (W + p.TW - 1) / p.TW; p.n_ht = (H + p.TH - 1) / p.TH; p.n_bt = (B + p.TB - 1) / p.TB;
   p.Cin = Cin; p.C2 = C2; p.C3 = C3; p.crop = crop; p.xoff = -crop; p.Hout = H; p.Wout = W - 2 * crop;
   p.N = Cout; p.M = p.n_wt * p.n_ht * p.n_bt * BM;
+  p.n_taps = n_taps;
+  for (int t = 0; t < n_taps; ++t) { p.tap_dh[t] = tap_dh[t]; p.tap_dw[t] = tap_dw[t]; }
   const int bn = pick_bn(Cout, 0);
   p.m_tiles = p.n_wt * p.n_ht * p.n_bt; p.n_tiles = (Cout + bn - 1) / bn;
-  p.k_iters = 9 * ((Cin + BK - 1) / BK) + (C2 + BK - 1) / BK + (C3 + BK - 1) / BK;
+  p.k_iters = n_taps * ((Cin + BK - 1) / BK) + (C2 + BK - 1) / BK + (C3 + BK - 1) / BK;
   p.D = static_cast<bf16*>(D); p.ldd = Cout;
   p.bias = static_cast<const bf16*>(bias);
   p.resid = static_cast<const bf16*>(resid); p.ldr = Cout;
   p.rowvec = rowvec; p.rowvec_div = rowvec_div > 0 ? rowvec_div : 1; p.rowvec_ld = rowvec_ld;
   p.act = 0; p.out_scale = out_scale; p.n_out = Cout;
-  const long long Ktot = 9LL * Cin + C2 + C3;
+  if (lattice) { p.os_w = lattice->s_w; p.os_h = lattice->s_h; p.os_b = lattice->s_b; }
+  const long long Ktot = static_cast<long long>(n_taps) * Cin + C2 + C3;
   CUtensorMap ta, ta2, ta3, tw;
   auto act_map = [&](CUtensorMap* m, const void* ptr, int C, int Wt_) {
     uint64_t d[4] = {(uint64_t)C, (uint64_t)Wt_, (uint64_t)H, (uint64_t)B};
@@ -1120,14 +1134,54 @@ extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, co
     const int Wo = W - 2 * crop;
     uint64_t d[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)H, (uint64_t)B};
     uint64_t s[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, (uint64_t)H * Wo * Cout * 2};
+    if (lattice) { s[0] = (uint64_t)lattice->s_w * 2; s[1] = (uint64_t)lattice->s_h * 2; s[2] = (uint64_t)lattice->s_b * 2; }
     uint32_t b[4] = {32, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
     r = get_tmap_bf16(&td, D, 4, d, s, b, 2); if (r) return r;
     tr = td;
-    if (resid) { r = get_tmap_bf16(&tr, resid, 4, d, s, b, 2); if (r) return r; }
+    if (resid) {
+      if (lattice) return I360_ERR_UNSUPPORTED;
+      r = get_tmap_bf16(&tr, resid, 4, d, s, b, 2); if (r) return r;
+    }
   }
   return dispatch(bn, ta, ta2, ta3, tw, td, tr, p, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, const void* x2, int C2,
+                                 const void* x3, int C3, const void* Wt, int Cout, void* D,
+                                 int crop, const void* bias, const void* resid,
+                                 const float* rowvec, int rowvec_div, int rowvec_ld,
+                                 float out_scale, void* stream) {
+  static const signed char dh[9] = {-1, -1, -1, 0, 0, 0, 1, 1, 1}, dw[9] = {-1, 0, 1, -1, 0, 1, -1, 0, 1};
+  return conv_impl(x, B, H, W, Cin, x2, C2, x3, C3, Wt, Cout, D, nullptr, crop, bias, resid, rowvec, rowvec_div, rowvec_ld,
+                   out_scale, 9, dh, dw, stream);
+}
+
+// Nearest 2x upsample followed by a 3x3 / pad 1 convolution, WITHOUT the upsampled tensor and with 4/9 of the multiply-adds:
+// output pixel (2i + a, 2j + b) reads input rows {i-1, i} (a = 0) or {i, i+1} (a = 1) and likewise for columns, so each of the
+// four output parities is a 2x2-tap convolution of the LOW-resolution input whose weights are sums of the 3x3 taps that fall
+// on the same input pixel (a = 0: {w[0], w[1] + w[2]}, a = 1: {w[0] + w[1], w[2]}; the caller pre-sums in fp32 and rounds once:
+// ops.pack_upsample_conv).  x: NHWC [B, H, W, Cin] low resolution (W includes `crop` circular halo columns per side);
+// Weff: [4 parities (a*2+b)][Cout][4 taps (dr*2+dc) * Cin]; D: NHWC [B, 2H, 2(W - 2 crop), Cout].  Zero padding of the
+// upsampled image coincides with TMA's zero fill of the low-resolution box.  Replaces Upsample3D.forward = F.interpolate(
+// scale_factor=2, mode="nearest") + InflatedConv3d (animatediff/models/resnet.py:86-114; with pad_pano(1) / unpad_pano(2) of
+// MVGenModel.py:449-456 as crop = 1) and the VAE's Upsample2D (diffusers/models/resnet.py:108-143).
+extern "C" int i360_conv_upsample2x_bf16(const void* x, int B, int H, int W, int Cin, const void* Weff, int Cout, void* D,
+                                         int crop, const void* bias, void* stream) {
+  if (!x || !Weff || !D) return I360_ERR_ARG;
+  const int Wo = W - 2 * crop;
+  const OutLattice lat = {2LL * Cout, 2LL * (2LL * Wo) * Cout, (2LL * H) * (2LL * Wo) * Cout};
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      const signed char dh[4] = {static_cast<signed char>(a - 1), static_cast<signed char>(a - 1), static_cast<signed char>(a), static_cast<signed char>(a)};
+      const signed char dw[4] = {static_cast<signed char>(b - 1), static_cast<signed char>(b), static_cast<signed char>(b - 1), static_cast<signed char>(b)};
+      const bf16* wp = static_cast<const bf16*>(Weff) + static_cast<long long>(a * 2 + b) * Cout * (4LL * Cin);
+      bf16* dp = static_cast<bf16*>(D) + (static_cast<long long>(a) * (2LL * Wo) + b) * Cout;
+      const int r = conv_impl(x, B, H, W, Cin, nullptr, 0, nullptr, 0, wp, Cout, dp, &lat, crop, bias, nullptr, nullptr, 1, 0, 1.0f,
+                              4, dh, dw, stream);
+      if (r) return r;
+    }
+  return I360_OK;
+}
 
 // LayerNorm folded into the projection that consumes it:  D = act( LN(A; gamma, beta, eps) W^T + bias (+ rowvec) ).
 // Wf: [N, K] = W * gamma (bf16);  u[n] = sum_k Wf[n,k] (fp32, from the bf16-rounded Wf);  c[n] = sum_k beta[k] W[n,k] + bias[n]

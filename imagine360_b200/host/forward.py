@@ -14,7 +14,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import ops
-from .unet3d import BF16, cached, conv_w, fused_w, geglu_w, lin_w, pad8
+from .unet3d import BF16, cached, conv_w, fused_w, geglu_w, lin_w, pad8, upsample_conv_w
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -188,9 +188,22 @@ def downsample(x, d, circular: bool):
     return y.view(n, h // 2, w // 2, -1)
 
 
+# I360_UPSAMPLE_SUBPIXEL=0: materialise the upsampled tensor and run the plain 3x3 conv on it (A/B runs)
+SUBPIXEL = os.environ.get("I360_UPSAMPLE_SUBPIXEL", "1") not in ("", "0")
+
+
 @traced("upsample")
 def upsample(x, u, circular: bool):
-    """Upsample3D (resnet.py:86-114); circular: pad_pano(1) -> x2 -> conv -> unpad_pano(2) (MVGenModel.py:449-456)."""
+    """Upsample3D (resnet.py:86-114); circular: pad_pano(1) -> x2 -> conv -> unpad_pano(2) (MVGenModel.py:449-456).
+    Sub-pixel form: four 2x2-tap convolutions of the low-resolution tensor (one per output parity) with pre-summed weights --
+    no upsampled tensor, 4/9 of the multiply-adds; the circular halo is one low-resolution column per side, cropped by the
+    kernel (the only copy is that small padded low-resolution tensor)."""
+    if SUBPIXEL:
+        weff, b = upsample_conv_w(u.conv)
+        if circular:
+            xp = torch.cat([x[:, :, -1:], x, x[:, :, :1]], dim=2)
+            return ops.conv_upsample2x(xp, weff, b, crop=1)
+        return ops.conv_upsample2x(x, weff, b)
     wp, b = conv_w(u.conv)
     if circular:
         return ops.conv3x3(ops.upsample2x(x, pad_in=1), wp, bias=b, crop=2)

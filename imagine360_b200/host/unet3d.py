@@ -128,6 +128,14 @@ def conv_w(conv: nn.Conv2d, shortcut: nn.Conv2d | None = None, cin_pad: int | No
     return cached(conv, f"w{cin_pad}_{cout_pad}", params, build)
 
 
+def upsample_conv_w(conv: nn.Conv2d):
+    """Pre-summed sub-pixel weights [4, Cout, 4 * Cin] + bias of an upsampler's 3x3 conv (ops.pack_upsample_conv)."""
+    def build():
+        b = conv.bias.to(BF16) if conv.bias is not None else None
+        return ops.pack_upsample_conv(conv.weight), b
+    return cached(conv, "w_subpixel", [conv.weight, conv.bias], build)
+
+
 # ------------------------------------------------------------------------------------------------------
 # parameter containers (names == reference)
 # ------------------------------------------------------------------------------------------------------

@@ -15,8 +15,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
+from . import forward as Fw
 from .forward import tokens
-from .unet3d import BF16, cached, conv_w, lin_w, pad8
+from .unet3d import BF16, cached, conv_w, lin_w, pad8, upsample_conv_w
 
 
 class ResnetBlock2D(nn.Module):
@@ -269,8 +270,12 @@ class AutoencoderKL(nn.Module):
             for r in blk.resnets:
                 y = _resnet(y, r, g)
             if blk.upsamplers is not None:
-                wu, bu = conv_w(blk.upsamplers[0].conv)
-                y = ops.conv3x3(ops.upsample2x(y), wu, bias=bu)
+                if Fw.SUBPIXEL:          # nearest x2 + conv3x3 as four 2x2-tap convolutions of the low-resolution tensor
+                    wu, bu = upsample_conv_w(blk.upsamplers[0].conv)
+                    y = ops.conv_upsample2x(y, wu, bu)
+                else:
+                    wu, bu = conv_w(blk.upsamplers[0].conv)
+                    y = ops.conv3x3(ops.upsample2x(y), wu, bias=bu)
         y = ops.groupnorm(y, d.conv_norm_out.weight, d.conv_norm_out.bias, g, d.conv_norm_out.eps, True)
         w, b = conv_w(d.conv_out, cout_pad=pad8(d.conv_out.out_channels))
         y = ops.conv3x3(y, w, bias=b)

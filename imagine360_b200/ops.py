@@ -210,6 +210,38 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias=None, x2=None, x3=None
     return out
 
 
+def pack_upsample_conv(weight: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> [4, Cout, 4 * Cin] bf16: the pre-summed 2x2-tap weights of the four output parities of
+    "nearest x2 upsample -> conv3x3" (see i360_conv_upsample2x_bf16); sums in fp32, one rounding."""
+    w = weight.detach().float()
+    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}          # parity -> (taps on input row i + a - 1, taps on input row i + a)
+    out = []
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = []
+            for dr in (0, 1):
+                for dc in (0, 1):
+                    t = sum(w[:, :, kh, kw] for kh in rows[a][dr] for kw in rows[b][dc])      # [Cout, Cin]
+                    taps.append(t)
+            out.append(torch.cat(taps, dim=1))
+    return torch.stack(out).to(BF16).contiguous()
+
+
+def conv_upsample2x(x: torch.Tensor, w_eff: torch.Tensor, bias=None, crop: int = 0) -> torch.Tensor:
+    """nearest x2 upsample + 3x3 conv of NHWC ``x`` [B, H, W, Cin] (``crop`` circular halo columns per side included in W)
+    -> [B, 2H, 2(W - 2 crop), Cout], in sub-pixel form (no upsampled tensor, 4/9 of the FLOPs)."""
+    _chk_bf16(x, w_eff, bias)
+    assert x.dim() == 4 and x.is_contiguous()
+    B, H, W, Cin = x.shape
+    Cout = w_eff.shape[1]
+    assert w_eff.shape == (4, Cout, 4 * Cin) and w_eff.is_contiguous()
+    out = torch.empty((B, 2 * H, 2 * (W - 2 * crop), Cout), dtype=BF16, device=x.device)
+    rc = lib().i360_conv_upsample2x_bf16(_p(x), c_int(B), c_int(H), c_int(W), c_int(Cin), _p(w_eff), c_int(Cout), _p(out),
+                                         c_int(crop), _p(bias), _stream())
+    check(rc, "i360_conv_upsample2x_bf16")
+    return out
+
+
 def conv3x3_uses_halo(B: int, H: int, W: int, Cin: int, resid: bool = False, rowvec: bool = False, extra: bool = False) -> bool:
     return bool(lib().i360_conv3x3_uses_halo(c_int(B), c_int(H), c_int(W), c_int(Cin), c_int(int(resid)), c_int(int(rowvec)),
                                              c_int(int(extra))))

@@ -75,6 +75,16 @@ int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, const void* x
                       const void* Wt, int Cout, void* D, int crop, const void* bias, const void* resid,
                       const float* rowvec, int rowvec_div, int rowvec_ld, float out_scale, void* stream);
 
+/* Nearest 2x upsample + 3x3 / pad 1 convolution in sub-pixel form: no upsampled tensor, 4/9 of the multiply-adds.  Each output
+ * parity (a, b) = (row % 2, col % 2) is a 2x2-tap convolution of the LOW-resolution input with pre-summed weights
+ * Weff[a*2+b][Cout][(dr*2+dc)*Cin + c] (a = 0: rows {w[0], w[1]+w[2]}, a = 1: {w[0]+w[1], w[2]}, same for columns; summed in
+ * fp32 and rounded once to bf16).  x: NHWC [B, H, W, Cin] (W includes `crop` circular halo columns per side), D: NHWC
+ * [B, 2H, 2(W - 2 crop), Cout].  Replaces Upsample3D.forward (F.interpolate nearest x2 + InflatedConv3d,
+ * animatediff/models/resnet.py:86-114; pad_pano(1) / unpad_pano(2) of MVGenModel.py:449-456 as crop = 1) and the VAE's
+ * Upsample2D (diffusers/models/resnet.py:108-143). */
+int i360_conv_upsample2x_bf16(const void* x, int B, int H, int W, int Cin, const void* Weff, int Cout, void* D, int crop,
+                              const void* bias, void* stream);
+
 /* 1 when i360_conv3x3_bf16 runs this problem through its halo-tile variant (16 x 8 pixel tiles whose 18 x 10 halo is
  * loaded once per 64-channel block and shared by the nine taps), 0 for the tap-by-tap variant.  Informational. */
 int i360_conv3x3_uses_halo(int B, int H, int W, int Cin, int has_resid, int has_rowvec, int has_extra_sources);

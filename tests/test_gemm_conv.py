@@ -183,6 +183,29 @@ def test_conv3x3_halo_tiles(B, H, W, Cin, Cout, mode):
     _close(out3, ref.permute(0, 2, 3, 1), f"tap conv {mode} {B}x{H}x{W} {Cin}->{Cout}")
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,crop", [(2, 16, 16, 64, 64, 0), (3, 32, 32, 640, 640, 0), (2, 32, 66, 320, 320, 1), (1, 8, 22, 1280, 1280, 1),
+                                                 (1, 128, 272, 512, 512, 0), (2, 5, 7, 72, 40, 0), (1, 16, 34, 64, 8, 1), (40, 4, 4, 1280, 1280, 0)])
+def test_conv_upsample2x_subpixel(B, H, W, Cin, Cout, crop):
+    """i360_conv_upsample2x_bf16: nearest x2 upsample + conv3x3 as four 2x2-tap convolutions of the low-resolution tensor with
+    pre-summed weights, against fp32 torch interpolate -> conv2d (incl. the circular-halo crop of the panorama branch, partial
+    channel blocks, H / W tails).  The pre-summed weights are rounded once to bf16 (<= 2^-9 relative per merged tap)."""
+    from imagine360_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B + H * 3 + W * 5 + Cin + Cout)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda", generator=g).bfloat16()
+    out = ops.conv_upsample2x(x, ops.pack_upsample_conv(w), bias, crop=crop)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, w.float(), bias.float(), padding=1)
+    if crop:
+        ref = ref[..., 2 * crop:-2 * crop]
+    assert out.shape == (B, 2 * H, 2 * (W - 2 * crop), Cout)
+    _close(out, ref.permute(0, 2, 3, 1), f"subpixel upsample conv {B}x{H}x{W} {Cin}->{Cout} crop {crop}")
+    # and against the materialised path it replaces (same kernels, exact bf16 weights): within the weight-rounding noise
+    two = ops.conv3x3(ops.upsample2x(x, pad_in=0), ops.pack_conv3x3(w), bias=bias, crop=2 * crop)
+    _close(out, two, "subpixel vs upsample + conv3x3", rtol=1.0 / 64, atol_scale=6e-3)
+
+
 @pytest.mark.parametrize("M,N,K,resid", [(1000, 320, 320, True), (777, 320, 1280, False), (4100, 640, 640, True), (40000, 640, 640, True),
                                           (38000, 640, 2560, False), (513, 1280, 1280, True), (130, 1280, 5120, False), (64, 320, 320, True)])
 def test_gemm_rowstats(M, N, K, resid):
