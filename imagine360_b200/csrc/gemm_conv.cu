@@ -48,6 +48,8 @@ struct GemmConvParams {
   int n_taps; signed char tap_dh[9]; signed char tap_dw[9];
   // direct (cropped) stores into a strided output lattice: element offsets of one step in w / h / image (0 = dense)
   long long os_w, os_h, os_b;
+  int in_stride;      // CONV: input pixel = in_stride * output pixel + tap offset (2: the stride-2 downsample convs, whose
+                      // activation boxes are TMA boxes with traversal stride 2 -- no im2col buffer)
   int crop;           // output columns cropped on each side (pano halo)
   int xoff;           // column offset applied to the extra 1x1 sources (= -crop: they are stored un-padded)
   int Hout, Wout;
@@ -211,7 +213,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
           mbar_expect_tx(&full[stage], C::kStageBytes);
-          if (p.conv) tma_load_4d(sa, ma, &full[stage], c0, w0 + dw, h0 + dh, b0);
+          if (p.conv) tma_load_4d(sa, ma, &full[stage], c0, p.in_stride * w0 + dw, p.in_stride * h0 + dh, b0);
           else        tma_load_2d(sa, ma, &full[stage], c0, m_blk * (BM * MT));
           tma_load_2d(sb, &tmW, &full[stage], kcoord, n0);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -1075,7 +1077,9 @@ struct OutLattice { long long s_w, s_h, s_b; };
 static int conv_impl(const void* x, int B, int H, int W, int Cin, const void* x2, int C2, const void* x3, int C3, const void* Wt,
                      int Cout, void* D, const OutLattice* lattice, int crop, const void* bias, const void* resid, const float* rowvec,
                      int rowvec_div, int rowvec_ld, float out_scale, int n_taps, const signed char* tap_dh, const signed char* tap_dw,
-                     void* stream) {
+                     void* stream, int in_stride = 1, int Hin = 0, int Win = 0) {
+  // H, W: the OUTPUT domain that is tiled (before the crop); Hin, Win: the input tensor when in_stride != 1
+  if (in_stride == 1) { Hin = H; Win = W; }
   if (!x || !Wt || !D || B <= 0 || H <= 0 || W <= 0) return I360_ERR_ARG;
   if ((Cin % 8) || (Cout % 8) || (C2 % 8) || (C3 % 8) || crop < 0 || 2 * crop >= W)
     return I360_ERR_ARG;
@@ -1088,7 +1092,9 @@ static int conv_impl(const void* x, int B, int H, int W, int Cin, const void* x2
   best_box(B, H, W, &bestTW, &bestTH, &bestTB, &bestw);
   GemmConvParams p;
   memset(&p, 0, sizeof(p));
-  p.halo = is3x3 && !lattice && use_halo(H, W, Cin, resid != nullptr, rowvec != nullptr, C2 + C3 > 0, bestw + 1e-6 * bestTW);
+  p.halo = is3x3 && !lattice && in_stride == 1 && use_halo(H, W, Cin, resid != nullptr, rowvec != nullptr, C2 + C3 > 0, bestw + 1e-6 * bestTW);
+  p.in_stride = in_stride;
+  if (in_stride != 1 && (C2 > 0 || C3 > 0)) return I360_ERR_UNSUPPORTED;
   if (p.halo) { bestTW = kHaloTW; bestTH = kHaloTH; bestTB = 1; }
   p.conv = 1; p.B = B; p.H = H; p.W = W; p.TW = bestTW; p.TH = bestTH; p.TB = bestTB;
   p.n_wt = (W + p.TW - 1) / p.TW; p.n_ht = (H + p.TH - 1) / p.TH; p.n_bt = (B + p.TB - 1) / p.TB;
@@ -1119,6 +1125,14 @@ static int conv_impl(const void* x, int B, int H, int W, int Cin, const void* x2
     uint64_t s[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
     uint32_t b[4] = {BK, (uint32_t)kHaloW, (uint32_t)kHaloH, 1u};
     r = get_tmap_bf16(&ta, x, 4, d, s, b, 3);
+  } else if (in_stride != 1) {
+    // traversal stride along w and h: the box spans in_stride * T input pixels and loads every in_stride-th one
+    uint64_t d[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
+    uint64_t s[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+    uint32_t b[4] = {BK, (uint32_t)(p.TW * in_stride), (uint32_t)(p.TH * in_stride), (uint32_t)p.TB};
+    uint32_t es[4] = {1u, (uint32_t)in_stride, (uint32_t)in_stride, 1u};
+    if (b[1] > 256 || b[2] > 256) return I360_ERR_UNSUPPORTED;
+    r = get_tmap_bf16(&ta, x, 4, d, s, b, 3, es);
   } else {
     r = act_map(&ta, x, Cin, W);
   }
@@ -1154,6 +1168,20 @@ extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, co
   static const signed char dh[9] = {-1, -1, -1, 0, 0, 0, 1, 1, 1}, dw[9] = {-1, 0, 1, -1, 0, 1, -1, 0, 1};
   return conv_impl(x, B, H, W, Cin, x2, C2, x3, C3, Wt, Cout, D, nullptr, crop, bias, resid, rowvec, rowvec_div, rowvec_ld,
                    out_scale, 9, dh, dw, stream);
+}
+
+// 3x3 / stride 2 convolution as an implicit GEMM: the activation box of tap (kh, kw) is a TMA box with traversal stride 2
+// starting at (2 w0 + kw - pad_lo, 2 h0 + kh - pad_lo); rows / columns outside the image are zero-filled = the conv's padding
+// (pad_lo = 1: symmetric pad 1 of Downsample3D, animatediff/models/resnet.py:117-140; pad_lo = 0: the VAE's asymmetric
+// F.pad(0, 1, 0, 1), diffusers/models/resnet.py:184).  x: NHWC [B, Hin, Win, Cin] (Win includes 2 * crop circular halo
+// columns per side), D: NHWC [B, Hin / 2, Win / 2 - 2 crop, Cout].  Replaces the im2col buffer + GEMM of round 1.
+extern "C" int i360_conv3x3_s2_bf16(const void* x, int B, int Hin, int Win, int Cin, const void* Wt, int Cout, void* D,
+                                    int pad_lo, int crop, const void* bias, void* stream) {
+  if (pad_lo < 0 || pad_lo > 1 || (Hin % 2) || (Win % 2)) return I360_ERR_ARG;
+  signed char dh[9], dw[9];
+  for (int t = 0; t < 9; ++t) { dh[t] = static_cast<signed char>(t / 3 - pad_lo); dw[t] = static_cast<signed char>(t % 3 - pad_lo); }
+  return conv_impl(x, B, Hin / 2, Win / 2, Cin, nullptr, 0, nullptr, 0, Wt, Cout, D, nullptr, crop, bias, nullptr, nullptr, 1, 0, 1.0f,
+                   9, dh, dw, stream, 2, Hin, Win);
 }
 
 // Nearest 2x upsample followed by a 3x3 / pad 1 convolution, WITHOUT the upsampled tensor and with 4/9 of the multiply-adds:

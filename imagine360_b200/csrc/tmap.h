@@ -47,6 +47,7 @@ struct TmapKey {
   uint64_t dim[4];
   uint64_t stride[3];  // bytes, dims 1..3
   uint32_t box[4];
+  uint32_t estride[4];  // traversal ("element") strides: box[i] elements are traversed, every estride[i]-th is loaded
   uint32_t rank;
   uint32_t swizzle;
   bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
@@ -63,13 +64,14 @@ struct TmapKeyHash {
 // bf16 tensor map, rank 2..4. dims/strides innermost-first; strides in BYTES for dims 1..rank-1.
 // swizzle: 0 none, 1 = 32B, 2 = 64B, 3 = 128B (CUtensorMapSwizzle numbering)
 inline int get_tmap_bf16(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* dim,
-                         const uint64_t* stride_bytes, const uint32_t* box, uint32_t swizzle) {
+                         const uint64_t* stride_bytes, const uint32_t* box, uint32_t swizzle,
+                         const uint32_t* elem_stride = nullptr) {
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
   static std::mutex mu;
   TmapKey key;
   memset(&key, 0, sizeof(key));
   key.ptr = ptr; key.rank = rank; key.swizzle = swizzle;
-  for (uint32_t i = 0; i < rank; ++i) { key.dim[i] = dim[i]; key.box[i] = box[i]; }
+  for (uint32_t i = 0; i < rank; ++i) { key.dim[i] = dim[i]; key.box[i] = box[i]; key.estride[i] = elem_stride ? elem_stride[i] : 1; }
   for (uint32_t i = 0; i + 1 < rank; ++i) key.stride[i] = stride_bytes[i];
   {
     std::lock_guard<std::mutex> g(mu);
@@ -80,7 +82,7 @@ inline int get_tmap_bf16(CUtensorMap* out, const void* ptr, uint32_t rank, const
   if (!enc) return I360_ERR_TMAP;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return I360_ERR_ARG;
   cuuint64_t gdim[4]; cuuint64_t gstr[3]; cuuint32_t bx[4]; cuuint32_t es[4];
-  for (uint32_t i = 0; i < rank; ++i) { gdim[i] = dim[i]; bx[i] = box[i]; es[i] = 1; }
+  for (uint32_t i = 0; i < rank; ++i) { gdim[i] = dim[i]; bx[i] = box[i]; es[i] = elem_stride ? elem_stride[i] : 1; }
   for (uint32_t i = 0; i + 1 < rank; ++i) {
     if (stride_bytes[i] % 16 != 0) return I360_ERR_ARG;
     gstr[i] = stride_bytes[i];

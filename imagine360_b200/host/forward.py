@@ -179,13 +179,24 @@ def resnet_block(x, r, temb, frames: int, groups: int, skip=None, halo: int = 0)
     return ops.conv3x3(h, w2, bias=b2, resid=x, crop=halo, out_scale=1.0 / r.output_scale_factor)
 
 
+# I360_CONV_S2_IM2COL=1: the round-1 path (materialised im2col + GEMM) for A/B runs
+S2_IM2COL = os.environ.get("I360_CONV_S2_IM2COL", "0") not in ("", "0")
+
+
 @traced("downsample")
 def downsample(x, d, circular: bool):
-    """Downsample3D (resnet.py:132-140); circular: pad_pano(2) -> conv -> unpad_pano(1) (MVGenModel.py:305-314)."""
+    """Downsample3D (resnet.py:132-140); circular: pad_pano(2) -> conv -> unpad_pano(1) (MVGenModel.py:305-314).
+    Implicit GEMM over TMA boxes with traversal stride 2: no im2col buffer; the circular case materialises the two halo columns
+    per side of the input (one small copy) and crops one output column per side in the kernel."""
     n, h, w, c = x.shape
     wp, b = conv_w(d.conv)
-    y = ops.gemm(ops.im2col_s2(x, circular), wp, bias=b)
-    return y.view(n, h // 2, w // 2, -1)
+    if S2_IM2COL:
+        y = ops.gemm(ops.im2col_s2(x, circular), wp, bias=b)
+        return y.view(n, h // 2, w // 2, -1)
+    if circular:
+        xp = torch.cat([x[:, :, -2:], x, x[:, :, :2]], dim=2)
+        return ops.conv3x3_s2(xp, wp, b, pad_lo=1, crop=1)
+    return ops.conv3x3_s2(x, wp, b, pad_lo=1)
 
 
 # I360_UPSAMPLE_SUBPIXEL=0: materialise the upsampled tensor and run the plain 3x3 conv on it (A/B runs)

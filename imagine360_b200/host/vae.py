@@ -244,7 +244,10 @@ class AutoencoderKL(nn.Module):
             if blk.downsamplers is not None:
                 n, h, ww, c = y.shape
                 wd, bd = conv_w(blk.downsamplers[0].conv)
-                y = ops.gemm(ops.im2col_s2(y, False, pad_lo=0), wd, bias=bd).view(n, h // 2, ww // 2, -1)
+                if Fw.S2_IM2COL:
+                    y = ops.gemm(ops.im2col_s2(y, False, pad_lo=0), wd, bias=bd).view(n, h // 2, ww // 2, -1)
+                else:                    # asymmetric F.pad(0, 1, 0, 1) + stride-2 conv: TMA boxes with traversal stride 2
+                    y = ops.conv3x3_s2(y, wd, bd, pad_lo=0)
         y = _mid(y, e.mid_block, g)
         y = ops.groupnorm(y, e.conv_norm_out.weight, e.conv_norm_out.bias, g, e.conv_norm_out.eps, True)
         w, b = conv_w(e.conv_out, cout_pad=pad8(e.conv_out.out_channels))

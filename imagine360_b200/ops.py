@@ -210,6 +210,21 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias=None, x2=None, x3=None
     return out
 
 
+def conv3x3_s2(x: torch.Tensor, w_packed: torch.Tensor, bias=None, pad_lo: int = 1, crop: int = 0) -> torch.Tensor:
+    """3x3 / stride 2 conv of NHWC ``x`` [B, H, W, Cin] -> [B, H/2, W/2 - 2 crop, Cout] without an im2col buffer (TMA boxes
+    with traversal stride 2); ``pad_lo`` = 1: zero pad 1 all round, 0: pad (0, 1) like the VAE encoder."""
+    _chk_bf16(x, w_packed, bias)
+    assert x.dim() == 4 and x.is_contiguous()
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    assert w_packed.shape[1] == 9 * Cin and w_packed.is_contiguous() and H % 2 == 0 and W % 2 == 0
+    out = torch.empty((B, H // 2, W // 2 - 2 * crop, Cout), dtype=BF16, device=x.device)
+    rc = lib().i360_conv3x3_s2_bf16(_p(x), c_int(B), c_int(H), c_int(W), c_int(Cin), _p(w_packed), c_int(Cout), _p(out),
+                                    c_int(pad_lo), c_int(crop), _p(bias), _stream())
+    check(rc, "i360_conv3x3_s2_bf16")
+    return out
+
+
 def pack_upsample_conv(weight: torch.Tensor) -> torch.Tensor:
     """[Cout, Cin, 3, 3] -> [4, Cout, 4 * Cin] bf16: the pre-summed 2x2-tap weights of the four output parities of
     "nearest x2 upsample -> conv3x3" (see i360_conv_upsample2x_bf16); sums in fp32, one rounding."""

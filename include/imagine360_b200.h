@@ -75,6 +75,14 @@ int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, const void* x
                       const void* Wt, int Cout, void* D, int crop, const void* bias, const void* resid,
                       const float* rowvec, int rowvec_div, int rowvec_ld, float out_scale, void* stream);
 
+/* 3x3 / stride 2 convolution as an implicit GEMM over TMA boxes with traversal stride 2 (no im2col buffer).  pad_lo = 1:
+ * symmetric zero pad 1 (Downsample3D, animatediff/models/resnet.py:117-140; with pad_pano(2) / unpad_pano(1) of
+ * MVGenModel.py:305-314 as a materialised 2-column circular halo and crop = 1); pad_lo = 0: the VAE encoder's asymmetric
+ * F.pad(0, 1, 0, 1) (diffusers/models/resnet.py:184).  x: NHWC [B, Hin, Win, Cin], D: NHWC [B, Hin/2, Win/2 - 2 crop, Cout],
+ * Wt: [Cout, 9*Cin] taps (kh, kw, cin). */
+int i360_conv3x3_s2_bf16(const void* x, int B, int Hin, int Win, int Cin, const void* Wt, int Cout, void* D, int pad_lo,
+                         int crop, const void* bias, void* stream);
+
 /* Nearest 2x upsample + 3x3 / pad 1 convolution in sub-pixel form: no upsampled tensor, 4/9 of the multiply-adds.  Each output
  * parity (a, b) = (row % 2, col % 2) is a 2x2-tap convolution of the LOW-resolution input with pre-summed weights
  * Weff[a*2+b][Cout][(dr*2+dc)*Cin + c] (a = 0: rows {w[0], w[1]+w[2]}, a = 1: {w[0]+w[1], w[2]}, same for columns; summed in

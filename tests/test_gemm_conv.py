@@ -206,6 +206,33 @@ def test_conv_upsample2x_subpixel(B, H, W, Cin, Cout, crop):
     _close(out, two, "subpixel vs upsample + conv3x3", rtol=1.0 / 64, atol_scale=6e-3)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,pad_lo,crop", [(2, 16, 16, 64, 64, 1, 0), (3, 32, 32, 320, 320, 1, 0), (2, 32, 72, 320, 320, 1, 1),
+                                                        (1, 8, 24, 1280, 1280, 1, 1), (2, 64, 128, 128, 128, 0, 0), (2, 6, 10, 72, 40, 1, 0),
+                                                        (1, 256, 512, 128, 128, 0, 0), (40, 8, 8, 1280, 1280, 1, 0)])
+def test_conv3x3_stride2_implicit(B, H, W, Cin, Cout, pad_lo, crop):
+    """i360_conv3x3_s2_bf16: stride-2 conv through TMA boxes with traversal stride 2 (no im2col), against fp32 torch conv2d:
+    symmetric pad 1 (Downsample3D), the VAE's pad (0, 1), the panorama branch's circular halo + crop, tails, partial K blocks;
+    and bit-for-bit sane against the im2col + GEMM path it replaces."""
+    from imagine360_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B + H * 3 + W * 5 + Cin + Cout + pad_lo)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda", generator=g).bfloat16()
+    wp = ops.pack_conv3x3(w)
+    out = ops.conv3x3_s2(x, wp, bias, pad_lo=pad_lo, crop=crop)
+    xin = x.float().permute(0, 3, 1, 2)
+    if pad_lo == 0:
+        xin = F.pad(xin, (0, 1, 0, 1))
+    ref = F.conv2d(xin, w.float(), bias.float(), stride=2, padding=pad_lo)
+    if crop:
+        ref = ref[..., crop:-crop]
+    assert out.shape == (B, H // 2, W // 2 - 2 * crop, Cout)
+    _close(out, ref.permute(0, 2, 3, 1), f"stride-2 conv {B}x{H}x{W} {Cin}->{Cout} pad_lo {pad_lo} crop {crop}")
+    if crop == 0:
+        two = ops.gemm(ops.im2col_s2(x, False, pad_lo=pad_lo), wp, bias=bias).view(B, H // 2, W // 2, Cout)
+        _close(out, two, "implicit vs im2col + GEMM", rtol=1.0 / 128, atol_scale=2e-3)
+
+
 @pytest.mark.parametrize("M,N,K,resid", [(1000, 320, 320, True), (777, 320, 1280, False), (4100, 640, 640, True), (40000, 640, 640, True),
                                           (38000, 640, 2560, False), (513, 1280, 1280, True), (130, 1280, 5120, False), (64, 320, 320, True)])
 def test_gemm_rowstats(M, N, K, resid):
