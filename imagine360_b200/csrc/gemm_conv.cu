@@ -48,6 +48,9 @@ struct GemmConvParams {
   int n_taps; signed char tap_dh[9]; signed char tap_dw[9];
   // direct (cropped) stores into a strided output lattice: element offsets of one step in w / h / image (0 = dense)
   long long os_w, os_h, os_b;
+  // GroupNorm statistics of the OUTPUT, accumulated by the epilogue (CONV, one image per tile, group size 4 / 8 / 16 so that
+  // groups never straddle a 32-column chunk): gn_stats[(image * 32 + group) * 2 + {0, 1}] += (sum, sum of squares), fp64
+  double* gn_stats; int gn_gs;
   int in_stride;      // CONV: input pixel = in_stride * output pixel + tap offset (2: the stride-2 downsample convs, whose
                       // activation boxes are TMA boxes with traversal stride 2 -- no im2col buffer)
   int crop;           // output columns cropped on each side (pano halo)
@@ -116,7 +119,7 @@ template <int BN, bool RING = false, int MT = 1, bool LNF = false, bool HALO = f
   static constexpr bool kBiasTable = BN >= 160;
   static_assert(!LNF || kBiasTable, "the LayerNorm-folding epilogue reads c and u from the smem tables");
   static constexpr int kTableBytes = kBiasTable ? (LNF ? 2 : 1) * NG * BN * 4 : 0;   // [group][BN] bias (LNF: c), then [group][BN] u
-  static constexpr int kStatBytes = 0;
+  static constexpr int kStatBytes = 512;      // [2 epilogue groups][32 GroupNorm groups][sum, sumsq] fp32 partials (gn_stats)
   // dynamic smem is declared __align__(1024) (checked at run time), so no alignment slack is reserved
   static constexpr int kBudget = 227 * 1024 - kNumStg * kStgBytes - kTableBytes - kStatBytes - 256 - kHaloTotal;
   static constexpr int kMaxStages = HALO ? 6 : 8;
@@ -145,6 +148,23 @@ template <int BN, int EPI> struct UseRing { static constexpr bool value = (EPI =
 // token matrix per norm, 192 launches and ~13 ms of the 16x512x1024 step) disappears.  (A first version took the
 // statistics from the A tiles in shared memory with four extra warps; they competed with the epilogue warps for issue
 // slots and the step got 9 ms slower -- see git history / profiles/r02_bench_c3_ln_fold_on.json.)
+// GroupNorm statistics of one 32-column chunk of my row: per group of GS channels (sum, sum of squares), reduced over the
+// 32 rows of the warp by shuffles and added to the CTA's shared-memory partials by lane 0 (see GemmConvParams::gn_stats).
+template <int GS>
+__device__ __forceinline__ void gn_chunk_stats(const float2* f2, bool valid, int first_group, float* acc, int lane) {
+  constexpr int G = 32 / GS, PP = GS / 2;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    float2 a = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < PP; ++j) { a = fadd2(a, f2[g * PP + j]); q = ffma2(f2[g * PP + j], f2[g * PP + j], q); }
+    float s = valid ? a.x + a.y : 0.f, qq = valid ? q.x + q.y : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); qq += __shfl_xor_sync(0xffffffffu, qq, o); }
+    if (lane == 0) { atomicAdd(acc + (first_group + g) * 2, s); atomicAdd(acc + (first_group + g) * 2 + 1, qq); }
+  }
+}
+
 template <int BN, int EPI, int MT = 1, bool LNF = false, bool HALO = false, int NG = 2>
 __global__ void __launch_bounds__(64 + NG * 128, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
@@ -161,6 +181,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* stg = smem + C::kStages * C::kStageBytes;            // 2 staging buffers (1024-aligned)
   float* sbias = reinterpret_cast<float*>(stg + C::kNumStg * C::kStgBytes);   // [2 groups][BN] (kBiasTable only)
   float* su = sbias + NG * BN;                                                 // [groups][BN] (LNF only)
+  float* sgn = reinterpret_cast<float*>(stg + C::kNumStg * C::kStgBytes + C::kTableBytes);     // [2][32][2] (gn_stats)
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg + C::kNumStg * C::kStgBytes + C::kTableBytes + C::kStatBytes);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + C::kStages;         // [kStages]
@@ -546,6 +567,21 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         pst[sl] = (r < p.M && sl < p.ln_slots) ? __ldg(p.ln_stats + static_cast<long long>(sl) * p.M + r) : make_float2(0.f, 0.f);
     };
     load_stats(blockIdx.x);
+    // GroupNorm statistics of the output (gn_stats): this epilogue group's fp32 partials of the image it is working on live in
+    // smem and are flushed (fp64 atomics, 64 per group) when the CTA's tile sequence moves on to the next image and at the end
+    const bool gn_on = !kGeglu && !LNF && p.conv && p.gn_stats != nullptr;
+    float* gacc = sgn + grp * 64;
+    int gn_img = -1;
+    auto gn_flush = [&](int img) {
+      named_bar_sync(1 + grp, 128);                      // every warp's smem atomics of the image have landed
+      if (gtid < 64) {
+        const float v = gacc[gtid];
+        if (v != 0.f) atomicAdd(p.gn_stats + static_cast<long long>(img) * 64 + gtid, static_cast<double>(v));
+        gacc[gtid] = 0.f;
+      }
+      named_bar_sync(1 + grp, 128);
+    };
+    if (gn_on) { if (gtid < 64) gacc[gtid] = 0.f; named_bar_sync(1 + grp, 128); }
     int as = 0; uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
@@ -555,7 +591,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int w0 = 0, h0 = 0, b0 = 0;
       if (p.conv) {
         w0 = (m_blk % p.n_wt) * p.TW; h0 = ((m_blk / p.n_wt) % p.n_ht) * p.TH; b0 = (m_blk / (p.n_wt * p.n_ht)) * p.TB;
-        if (kResid || kRowvec || direct) {
+        if (gn_on && b0 != gn_img) { if (gn_img >= 0) gn_flush(gn_img); gn_img = b0; }
+        if (kResid || kRowvec || direct || gn_on) {
           const int tw = row % p.TW, th = (row / p.TW) % p.TH, tb = row / (p.TW * p.TH);
           const int w = w0 + tw, h = h0 + th, b = b0 + tb;
           valid = (b < p.B) && (h < p.H) && (w >= p.crop) && (w < p.W - p.crop);
@@ -745,6 +782,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 16; ++j) f2[j] = fmul2(f2[j], sc);
           }
+          if (gn_on) {                                          // GroupNorm statistics of what this chunk stores
+            const int fg = ocol / p.gn_gs;
+            if (p.gn_gs == 4) gn_chunk_stats<4>(f2, valid, fg, gacc, lane);
+            else if (p.gn_gs == 8) gn_chunk_stats<8>(f2, valid, fg, gacc, lane);
+            else gn_chunk_stats<16>(f2, valid, fg, gacc, lane);
+          }
           if (!kGeglu && !LNF && p.rowstats != nullptr) {     // producer side of the LayerNorm fold (columns past N are zeros)
 #pragma unroll
             for (int j = 0; j < 16; ++j) { rs1 = fadd2(rs1, f2[j]); rs2 = ffma2(f2[j], f2[j], rs2); }
@@ -788,6 +831,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         p.rowstats[static_cast<long long>(slot) * p.M + orow] = make_float2(rs1.x + rs1.y, rs2.x + rs2.y);
       }
     }
+    if (gn_on && gn_img >= 0) gn_flush(gn_img);
     if (store_thread) bulk_wait<0>();
   }
 
@@ -1045,11 +1089,12 @@ extern "C" void i360_conv3x3_halo_policy(int on, double tol, int allow_extra, in
   if (allow_extra >= 0) hp.allow_extra = allow_extra;
 }
 
-static void best_box(int B, int H, int W, int* TW, int* TH, int* TB, double* waste) {
+static void best_box(int B, int H, int W, int* TW, int* TH, int* TB, double* waste, int max_tb = 128) {
   int bestTW = 16, bestTH = 8, bestTB = 1; double bestw = 1e30;
   for (int tw = 1; tw <= 128; tw *= 2)
     for (int th = 1; tw * th <= 128; th *= 2) {
       const int tb = 128 / (tw * th);
+      if (tb > max_tb) continue;
       if (tw > 1 && tw / 2 >= W) continue;
       if (th > 1 && th / 2 >= H) continue;
       const double w = (double)((W + tw - 1) / tw * tw) * ((H + th - 1) / th * th) *
@@ -1077,7 +1122,7 @@ struct OutLattice { long long s_w, s_h, s_b; };
 static int conv_impl(const void* x, int B, int H, int W, int Cin, const void* x2, int C2, const void* x3, int C3, const void* Wt,
                      int Cout, void* D, const OutLattice* lattice, int crop, const void* bias, const void* resid, const float* rowvec,
                      int rowvec_div, int rowvec_ld, float out_scale, int n_taps, const signed char* tap_dh, const signed char* tap_dw,
-                     void* stream, int in_stride = 1, int Hin = 0, int Win = 0) {
+                     void* stream, int in_stride = 1, int Hin = 0, int Win = 0, double* gn_stats = nullptr, int gn_groups = 0) {
   // H, W: the OUTPUT domain that is tiled (before the crop); Hin, Win: the input tensor when in_stride != 1
   if (in_stride == 1) { Hin = H; Win = W; }
   if (!x || !Wt || !D || B <= 0 || H <= 0 || W <= 0) return I360_ERR_ARG;
@@ -1089,9 +1134,14 @@ static int conv_impl(const void* x, int B, int H, int W, int Cin, const void* x2
   // weight columns a partial K block overlaps are multiplied by zeros.
   // choose the pixel box minimising padded work
   int bestTW, bestTH, bestTB; double bestw;
-  best_box(B, H, W, &bestTW, &bestTH, &bestTB, &bestw);
+  if (gn_stats) {       // one image per tile; groups of 4 / 8 / 16 channels never straddle a 32-column chunk
+    if (gn_groups != 32 || (Cout % 32) || (Cout / 32 != 4 && Cout / 32 != 8 && Cout / 32 != 16) || rowvec) return I360_ERR_UNSUPPORTED;
+    if (static_cast<long long>(H) * W < 128) return I360_ERR_UNSUPPORTED;
+  }
+  best_box(B, H, W, &bestTW, &bestTH, &bestTB, &bestw, gn_stats ? 1 : 128);
   GemmConvParams p;
   memset(&p, 0, sizeof(p));
+  p.gn_stats = gn_stats; p.gn_gs = gn_stats ? Cout / 32 : 0;
   p.halo = is3x3 && !lattice && in_stride == 1 && use_halo(H, W, Cin, resid != nullptr, rowvec != nullptr, C2 + C3 > 0, bestw + 1e-6 * bestTW);
   p.in_stride = in_stride;
   if (in_stride != 1 && (C2 > 0 || C3 > 0)) return I360_ERR_UNSUPPORTED;
@@ -1170,6 +1220,21 @@ extern "C" int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, co
                    out_scale, 9, dh, dw, stream);
 }
 
+// i360_conv3x3_bf16 that ALSO accumulates the GroupNorm statistics of its output (32 groups of 4 / 8 / 16 channels: the VAE's
+// widths) from the epilogue: stats[(image * 32 + group) * 2 + {0, 1}] = (sum, sum of squares) over the image, fp64, zeroed
+// here.  The GroupNorm that reads the output then needs no statistics pass (i360_groupnorm_apply takes the same buffer).
+// Replaces conv -> GroupNorm's first read (diffusers/models/resnet.py:454-496 ResnetBlock2D: norm2 after conv1, the next
+// block's norm1 after conv2 / the up-sampler).
+extern "C" int i360_conv3x3_gnstats_bf16(const void* x, int B, int H, int W, int Cin, const void* x2, int C2, const void* Wt,
+                                         int Cout, void* D, const void* bias, const void* resid, int groups, double* stats,
+                                         void* stream) {
+  if (!stats) return I360_ERR_ARG;
+  if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * 32, static_cast<cudaStream_t>(stream)) != cudaSuccess) return I360_ERR_CUDA;
+  static const signed char dh[9] = {-1, -1, -1, 0, 0, 0, 1, 1, 1}, dw[9] = {-1, 0, 1, -1, 0, 1, -1, 0, 1};
+  return conv_impl(x, B, H, W, Cin, x2, C2, nullptr, 0, Wt, Cout, D, nullptr, 0, bias, resid, nullptr, 1, 0, 1.0f, 9, dh, dw, stream,
+                   1, 0, 0, stats, groups);
+}
+
 // 3x3 / stride 2 convolution as an implicit GEMM: the activation box of tap (kh, kw) is a TMA box with traversal stride 2
 // starting at (2 w0 + kw - pad_lo, 2 h0 + kh - pad_lo); rows / columns outside the image are zero-filled = the conv's padding
 // (pad_lo = 1: symmetric pad 1 of Downsample3D, animatediff/models/resnet.py:117-140; pad_lo = 0: the VAE's asymmetric
@@ -1193,8 +1258,8 @@ extern "C" int i360_conv3x3_s2_bf16(const void* x, int B, int Hin, int Win, int 
 // upsampled image coincides with TMA's zero fill of the low-resolution box.  Replaces Upsample3D.forward = F.interpolate(
 // scale_factor=2, mode="nearest") + InflatedConv3d (animatediff/models/resnet.py:86-114; with pad_pano(1) / unpad_pano(2) of
 // MVGenModel.py:449-456 as crop = 1) and the VAE's Upsample2D (diffusers/models/resnet.py:108-143).
-extern "C" int i360_conv_upsample2x_bf16(const void* x, int B, int H, int W, int Cin, const void* Weff, int Cout, void* D,
-                                         int crop, const void* bias, void* stream) {
+static int upsample2x_impl(const void* x, int B, int H, int W, int Cin, const void* Weff, int Cout, void* D, int crop,
+                           const void* bias, double* stats, int groups, void* stream) {
   if (!x || !Weff || !D) return I360_ERR_ARG;
   const int Wo = W - 2 * crop;
   const OutLattice lat = {2LL * Cout, 2LL * (2LL * Wo) * Cout, (2LL * H) * (2LL * Wo) * Cout};
@@ -1205,10 +1270,24 @@ extern "C" int i360_conv_upsample2x_bf16(const void* x, int B, int H, int W, int
       const bf16* wp = static_cast<const bf16*>(Weff) + static_cast<long long>(a * 2 + b) * Cout * (4LL * Cin);
       bf16* dp = static_cast<bf16*>(D) + (static_cast<long long>(a) * (2LL * Wo) + b) * Cout;
       const int r = conv_impl(x, B, H, W, Cin, nullptr, 0, nullptr, 0, wp, Cout, dp, &lat, crop, bias, nullptr, nullptr, 1, 0, 1.0f,
-                              4, dh, dw, stream);
+                              4, dh, dw, stream, 1, 0, 0, stats, groups);
       if (r) return r;
     }
   return I360_OK;
+}
+
+extern "C" int i360_conv_upsample2x_bf16(const void* x, int B, int H, int W, int Cin, const void* Weff, int Cout, void* D,
+                                         int crop, const void* bias, void* stream) {
+  return upsample2x_impl(x, B, H, W, Cin, Weff, Cout, D, crop, bias, nullptr, 0, stream);
+}
+
+// ... with the GroupNorm statistics of the (2H x 2W) output accumulated by the four parity launches (see
+// i360_conv3x3_gnstats_bf16; the image index of a tile is the same in all four).
+extern "C" int i360_conv_upsample2x_gnstats_bf16(const void* x, int B, int H, int W, int Cin, const void* Weff, int Cout, void* D,
+                                                 const void* bias, int groups, double* stats, void* stream) {
+  if (!stats) return I360_ERR_ARG;
+  if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * 32, static_cast<cudaStream_t>(stream)) != cudaSuccess) return I360_ERR_CUDA;
+  return upsample2x_impl(x, B, H, W, Cin, Weff, Cout, D, 0, bias, stats, groups, stream);
 }
 
 // LayerNorm folded into the projection that consumes it:  D = act( LN(A; gamma, beta, eps) W^T + bias (+ rowvec) ).

@@ -115,16 +115,40 @@ def _to_nhwc(x):
     return y.contiguous()
 
 
-def _resnet(x, r, groups):
-    h = ops.groupnorm(x, r.norm1.weight, r.norm1.bias, groups, r.norm1.eps, True)
+# GroupNorm statistics from the producing conv's epilogue (group sizes 4 / 8 / 16 = the VAE's widths with 32 groups):
+# I360_VAE_GN_FUSED=0 restores the separate statistics pass (A/B runs)
+GN_FUSED = os.environ.get("I360_VAE_GN_FUSED", "1") not in ("", "0")
+
+
+def _gn_ok(c, groups):
+    return GN_FUSED and groups == 32 and c // groups in (4, 8, 16) and c % 32 == 0
+
+
+def _conv_stats(x, w, b, cout, groups):
+    """conv3x3 (+ bias) -> (y, GroupNorm statistics of y | None)"""
+    if _gn_ok(cout, groups):
+        return ops.conv3x3(x, w, bias=b, gn_groups=groups)
+    return ops.conv3x3(x, w, bias=b), None
+
+
+def _resnet(x, r, groups, x_stats=None, want_stats=False):
+    """-> (y, GroupNorm statistics of y | None).  ``x_stats``: statistics of ``x`` from the conv that produced it."""
+    h = ops.groupnorm(x, r.norm1.weight, r.norm1.bias, groups, r.norm1.eps, True, stats=x_stats)
     w1, b1 = conv_w(r.conv1)
-    h = ops.conv3x3(h, w1, bias=b1)
-    h = ops.groupnorm(h, r.norm2.weight, r.norm2.bias, groups, r.norm2.eps, True)
+    co = r.conv1.out_channels
+    if _gn_ok(co, groups):
+        h, st = ops.conv3x3(h, w1, bias=b1, gn_groups=groups)
+    else:
+        h, st = ops.conv3x3(h, w1, bias=b1), None
+    h = ops.groupnorm(h, r.norm2.weight, r.norm2.bias, groups, r.norm2.eps, True, stats=st)
+    gg = groups if (want_stats and _gn_ok(co, groups)) else None
     if r.conv_shortcut is not None:
         w2, b2 = conv_w(r.conv2, shortcut=r.conv_shortcut)
-        return ops.conv3x3(h, w2, bias=b2, x2=x)
-    w2, b2 = conv_w(r.conv2)
-    return ops.conv3x3(h, w2, bias=b2, resid=x)
+        y = ops.conv3x3(h, w2, bias=b2, x2=x, gn_groups=gg)
+    else:
+        w2, b2 = conv_w(r.conv2)
+        y = ops.conv3x3(h, w2, bias=b2, resid=x, gn_groups=gg)
+    return y if gg is not None else (y, None)
 
 
 def _attention(x, a, groups):
@@ -147,10 +171,10 @@ def _attention(x, a, groups):
     return ops.gemm(out.view(-1, c), wo, bias=bo, resid=tokens(x)).view(n, h, w, c)
 
 
-def _mid(x, m, groups):
-    x = _resnet(x, m.resnets[0], groups)
+def _mid(x, m, groups, x_stats=None, want_stats=False):
+    x, _ = _resnet(x, m.resnets[0], groups, x_stats)
     x = _attention(x, m.attentions[0], groups)
-    return _resnet(x, m.resnets[1], groups)
+    return _resnet(x, m.resnets[1], groups, None, want_stats)
 
 
 class DiagonalGaussianDistribution:
@@ -237,19 +261,20 @@ class AutoencoderKL(nn.Module):
         e, g = self.encoder, self.groups
         y = _to_nhwc(x)
         w, b = conv_w(e.conv_in, cin_pad=y.shape[-1])
-        y = ops.conv3x3(y, w, bias=b)
+        y, st = _conv_stats(y, w, b, e.conv_in.out_channels, g)
         for blk in e.down_blocks:
             for r in blk.resnets:
-                y = _resnet(y, r, g)
+                y, st = _resnet(y, r, g, st, True)
             if blk.downsamplers is not None:
+                st = None                # the stride-2 conv has no statistics epilogue: the next norm1 runs its own pass
                 n, h, ww, c = y.shape
                 wd, bd = conv_w(blk.downsamplers[0].conv)
                 if Fw.S2_IM2COL:
                     y = ops.gemm(ops.im2col_s2(y, False, pad_lo=0), wd, bias=bd).view(n, h // 2, ww // 2, -1)
                 else:                    # asymmetric F.pad(0, 1, 0, 1) + stride-2 conv: TMA boxes with traversal stride 2
                     y = ops.conv3x3_s2(y, wd, bd, pad_lo=0)
-        y = _mid(y, e.mid_block, g)
-        y = ops.groupnorm(y, e.conv_norm_out.weight, e.conv_norm_out.bias, g, e.conv_norm_out.eps, True)
+        y, st = _mid(y, e.mid_block, g, st, True)
+        y = ops.groupnorm(y, e.conv_norm_out.weight, e.conv_norm_out.bias, g, e.conv_norm_out.eps, True, stats=st)
         w, b = conv_w(e.conv_out, cout_pad=pad8(e.conv_out.out_channels))
         y = ops.conv3x3(y, w, bias=b)
         y = self._conv1x1(y, self.quant_conv)
@@ -267,19 +292,23 @@ class AutoencoderKL(nn.Module):
         d, g = self.decoder, self.groups
         y = self._conv1x1(_to_nhwc(z), self.post_quant_conv)
         w, b = conv_w(d.conv_in, cin_pad=y.shape[-1])
-        y = ops.conv3x3(y, w, bias=b)
-        y = _mid(y, d.mid_block, g)
+        y, st = _conv_stats(y, w, b, d.conv_in.out_channels, g)
+        y, st = _mid(y, d.mid_block, g, st, True)
         for blk in d.up_blocks:
             for r in blk.resnets:
-                y = _resnet(y, r, g)
+                y, st = _resnet(y, r, g, st, True)
             if blk.upsamplers is not None:
+                co = blk.upsamplers[0].conv.out_channels
                 if Fw.SUBPIXEL:          # nearest x2 + conv3x3 as four 2x2-tap convolutions of the low-resolution tensor
                     wu, bu = upsample_conv_w(blk.upsamplers[0].conv)
-                    y = ops.conv_upsample2x(y, wu, bu)
+                    if _gn_ok(co, g):
+                        y, st = ops.conv_upsample2x(y, wu, bu, gn_groups=g)
+                    else:
+                        y, st = ops.conv_upsample2x(y, wu, bu), None
                 else:
                     wu, bu = conv_w(blk.upsamplers[0].conv)
-                    y = ops.conv3x3(ops.upsample2x(y), wu, bias=bu)
-        y = ops.groupnorm(y, d.conv_norm_out.weight, d.conv_norm_out.bias, g, d.conv_norm_out.eps, True)
+                    y, st = _conv_stats(ops.upsample2x(y), wu, bu, co, g)
+        y = ops.groupnorm(y, d.conv_norm_out.weight, d.conv_norm_out.bias, g, d.conv_norm_out.eps, True, stats=st)
         w, b = conv_w(d.conv_out, cout_pad=pad8(d.conv_out.out_channels))
         y = ops.conv3x3(y, w, bias=b)
         out = y[..., : d.conv_out.out_channels].permute(0, 3, 1, 2).contiguous()

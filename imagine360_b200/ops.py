@@ -184,7 +184,7 @@ def pack_conv3x3(weight: torch.Tensor, *shortcuts: torch.Tensor) -> torch.Tensor
 
 
 def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias=None, x2=None, x3=None, resid=None,
-            rowvec=None, rowvec_div: int = 1, crop: int = 0, out_scale: float = 1.0) -> torch.Tensor:
+            rowvec=None, rowvec_div: int = 1, crop: int = 0, out_scale: float = 1.0, gn_groups: int | None = None):
     """3x3 / stride 1 / zero-pad 1 convolution on NHWC ``x`` [B, H, W, Cin] -> [B, H, W-2*crop, Cout].
 
     ``x2``/``x3`` are optional NHWC sources [B, H, W-2*crop, C] (no halo) of a fused 1x1 convolution whose
@@ -201,6 +201,14 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias=None, x2=None, x3=None
         assert resid.shape == out.shape and resid.is_contiguous()
     if rowvec is not None:
         assert rowvec.dtype == torch.float32 and rowvec.is_contiguous()
+    if gn_groups is not None:
+        # the epilogue also accumulates the GroupNorm statistics of the output -> (out, stats [B, 32, 2] fp64)
+        assert x3 is None and rowvec is None and crop == 0 and out_scale == 1.0
+        stats = torch.empty((B, gn_groups, 2), dtype=torch.float64, device=x.device)
+        rc = lib().i360_conv3x3_gnstats_bf16(_p(x), c_int(B), c_int(H), c_int(W), c_int(Cin), _p(x2), c_int(C2), _p(w_packed),
+                                             c_int(Cout), _p(out), _p(bias), _p(resid), c_int(gn_groups), _p(stats), _stream())
+        check(rc, "i360_conv3x3_gnstats_bf16")
+        return out, stats
     rc = lib().i360_conv3x3_bf16(
         _p(x), c_int(B), c_int(H), c_int(W), c_int(Cin), _p(x2), c_int(C2), _p(x3), c_int(C3),
         _p(w_packed), c_int(Cout), _p(out), c_int(crop), _p(bias), _p(resid), _p(rowvec),
@@ -242,7 +250,7 @@ def pack_upsample_conv(weight: torch.Tensor) -> torch.Tensor:
     return torch.stack(out).to(BF16).contiguous()
 
 
-def conv_upsample2x(x: torch.Tensor, w_eff: torch.Tensor, bias=None, crop: int = 0) -> torch.Tensor:
+def conv_upsample2x(x: torch.Tensor, w_eff: torch.Tensor, bias=None, crop: int = 0, gn_groups: int | None = None):
     """nearest x2 upsample + 3x3 conv of NHWC ``x`` [B, H, W, Cin] (``crop`` circular halo columns per side included in W)
     -> [B, 2H, 2(W - 2 crop), Cout], in sub-pixel form (no upsampled tensor, 4/9 of the FLOPs)."""
     _chk_bf16(x, w_eff, bias)
@@ -251,6 +259,13 @@ def conv_upsample2x(x: torch.Tensor, w_eff: torch.Tensor, bias=None, crop: int =
     Cout = w_eff.shape[1]
     assert w_eff.shape == (4, Cout, 4 * Cin) and w_eff.is_contiguous()
     out = torch.empty((B, 2 * H, 2 * (W - 2 * crop), Cout), dtype=BF16, device=x.device)
+    if gn_groups is not None:
+        assert crop == 0
+        stats = torch.empty((B, gn_groups, 2), dtype=torch.float64, device=x.device)
+        rc = lib().i360_conv_upsample2x_gnstats_bf16(_p(x), c_int(B), c_int(H), c_int(W), c_int(Cin), _p(w_eff), c_int(Cout), _p(out),
+                                                     _p(bias), c_int(gn_groups), _p(stats), _stream())
+        check(rc, "i360_conv_upsample2x_gnstats_bf16")
+        return out, stats
     rc = lib().i360_conv_upsample2x_bf16(_p(x), c_int(B), c_int(H), c_int(W), c_int(Cin), _p(w_eff), c_int(Cout), _p(out),
                                          c_int(crop), _p(bias), _stream())
     check(rc, "i360_conv_upsample2x_bf16")
@@ -273,19 +288,23 @@ def conv3x3_halo_policy(on: int = -1, tol: float = -1.0, allow_extra: int = -1, 
 # normalisation
 # ------------------------------------------------------------------------------------------------
 def groupnorm(x1: torch.Tensor, gamma, beta, groups: int, eps: float, silu: bool, x2=None, pad: int = 0,
-              stats_pad: int | None = None) -> torch.Tensor:
+              stats_pad: int | None = None, stats: torch.Tensor | None = None) -> torch.Tensor:
     """GroupNorm(+SiLU) over the channel concat of NHWC ``x1`` (and ``x2``), circularly padded by ``pad`` columns.
-    Statistics are per image over the padded tensor (``stats_pad`` overrides the pad used for statistics)."""
+    Statistics are per image over the padded tensor (``stats_pad`` overrides the pad used for statistics); ``stats``
+    [B, groups, 2] fp64 from the producing conv's epilogue (``conv3x3(..., gn_groups=)``) skips the statistics pass."""
     _chk_bf16(x1, x2, gamma, beta)
     assert x1.dim() == 4 and x1.is_contiguous() and (x2 is None or (x2.is_contiguous() and x2.shape[:3] == x1.shape[:3]))
     B, H, W, C1 = x1.shape
     C2 = x2.shape[-1] if x2 is not None else 0
     C = C1 + C2
     sp = pad if stats_pad is None else stats_pad
-    stats = torch.empty((B, groups, 2), dtype=torch.float64, device=x1.device)
-    rc = lib().i360_groupnorm_stats(_p(x1), c_int(C1), _p(x2), c_int(C2), c_int(B), c_int(H), c_int(W), c_int(sp),
-                                    c_int(groups), _p(stats), _stream())
-    check(rc, "i360_groupnorm_stats")
+    if stats is None:
+        stats = torch.empty((B, groups, 2), dtype=torch.float64, device=x1.device)
+        rc = lib().i360_groupnorm_stats(_p(x1), c_int(C1), _p(x2), c_int(C2), c_int(B), c_int(H), c_int(W), c_int(sp),
+                                        c_int(groups), _p(stats), _stream())
+        check(rc, "i360_groupnorm_stats")
+    else:
+        assert x2 is None and pad == 0 and sp == 0 and stats.shape == (B, groups, 2) and stats.dtype == torch.float64
     out = torch.empty((B, H, W + 2 * pad, C), dtype=BF16, device=x1.device)
     count = float(H * (W + 2 * sp) * (C // groups)) if sp != pad else 0.0
     rc = lib().i360_groupnorm_apply(_p(x1), c_int(C1), _p(x2), c_int(C2), c_int(B), c_int(H), c_int(W), c_int(pad),

@@ -75,6 +75,15 @@ int i360_conv3x3_bf16(const void* x, int B, int H, int W, int Cin, const void* x
                       const void* Wt, int Cout, void* D, int crop, const void* bias, const void* resid,
                       const float* rowvec, int rowvec_div, int rowvec_ld, float out_scale, void* stream);
 
+/* Convolutions that also accumulate the GroupNorm statistics of their OUTPUT in the epilogue (32 groups of 4 / 8 / 16 channels,
+ * one image per tile): stats[(image * 32 + group) * 2 + {0, 1}] = (sum, sum of squares), fp64, zeroed by the call.  The GroupNorm
+ * reading the output skips its statistics pass (pass the buffer to i360_groupnorm_apply).  Replaces the first read of
+ * nn.GroupNorm after a conv in the VAE's ResnetBlock2D / Upsample2D chain (diffusers/models/resnet.py:454-496,:108-143). */
+int i360_conv3x3_gnstats_bf16(const void* x, int B, int H, int W, int Cin, const void* x2, int C2, const void* Wt, int Cout,
+                              void* D, const void* bias, const void* resid, int groups, double* stats, void* stream);
+int i360_conv_upsample2x_gnstats_bf16(const void* x, int B, int H, int W, int Cin, const void* Weff, int Cout, void* D,
+                                      const void* bias, int groups, double* stats, void* stream);
+
 /* 3x3 / stride 2 convolution as an implicit GEMM over TMA boxes with traversal stride 2 (no im2col buffer).  pad_lo = 1:
  * symmetric zero pad 1 (Downsample3D, animatediff/models/resnet.py:117-140; with pad_pano(2) / unpad_pano(1) of
  * MVGenModel.py:305-314 as a materialised 2-column circular halo and crop = 1); pad_lo = 0: the VAE encoder's asymmetric

@@ -233,6 +233,49 @@ def test_conv3x3_stride2_implicit(B, H, W, Cin, Cout, pad_lo, crop):
         _close(out, two, "implicit vs im2col + GEMM", rtol=1.0 / 128, atol_scale=2e-3)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,mode", [(2, 64, 136, 128, 128, "bias"), (1, 128, 272, 256, 256, "resid"), (3, 32, 40, 512, 512, "resid"),
+                                                 (2, 24, 20, 64, 256, "shortcut"), (2, 16, 24, 8, 512, "bias"), (2, 32, 68, 256, 256, "upsample"),
+                                                 (5, 16, 8, 128, 128, "bias")])
+def test_conv_with_groupnorm_statistics(B, H, W, Cin, Cout, mode):
+    """i360_conv3x3_gnstats_bf16 / i360_conv_upsample2x_gnstats_bf16: the conv result is the plain kernel's and the statistics the
+    epilogue accumulated equal those of the separate pass over the stored tensor (to fp32 partial-sum noise); GroupNorm applied
+    with either agrees.  Group sizes 4 / 8 / 16, halo and tap-by-tap kernels, residual ring, fused shortcut, tails, 5 images."""
+    from imagine360_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B + H * 3 + W * 5 + Cin + Cout)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    x = rn(B, H, W, Cin).bfloat16()
+    w = (rn(Cout, Cin, 3, 3) / (9 * Cin) ** 0.5).bfloat16()
+    bias = (rn(Cout) + 0.5).bfloat16()
+    kw = {}
+    if mode == "upsample":
+        weff = ops.pack_upsample_conv(w)
+        out, st = ops.conv_upsample2x(x, weff, bias, gn_groups=32)
+        plain = ops.conv_upsample2x(x, weff, bias)
+    else:
+        wp = ops.pack_conv3x3(w)
+        if mode == "resid":
+            kw["resid"] = rn(B, H, W, Cout).bfloat16()
+        if mode == "shortcut":
+            x2 = rn(B, H, W, 72).bfloat16()
+            wp = ops.pack_conv3x3(w, (rn(Cout, 72, 1, 1) / 72 ** 0.5).bfloat16())
+            kw["x2"] = x2
+        out, st = ops.conv3x3(x, wp, bias=bias, gn_groups=32, **kw)
+        plain = ops.conv3x3(x, wp, bias=bias, **kw)
+    assert torch.equal(out, plain)
+    gs = Cout // 32
+    v = out.double().view(B, -1, 32, gs)
+    ref = torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], -1)            # statistics of the STORED (bf16) tensor
+    n = v.shape[1] * gs
+    mean_err = ((st[..., 0] - ref[..., 0]).abs() / n).max().item()
+    var = ref[..., 1] / n - (ref[..., 0] / n) ** 2
+    var_fused = st[..., 1] / n - (st[..., 0] / n) ** 2
+    assert mean_err < 2e-3 and ((var_fused - var).abs() / var).max().item() < 5e-3, (mean_err, ((var_fused - var).abs() / var).max().item())
+    gam, bet = (1 + 0.1 * rn(Cout)).bfloat16(), (0.1 * rn(Cout)).bfloat16()
+    a = ops.groupnorm(out, gam, bet, 32, 1e-6, True, stats=st)
+    b_ = ops.groupnorm(out, gam, bet, 32, 1e-6, True)
+    assert (a.float() - b_.float()).abs().max().item() <= 0.04 * b_.float().abs().max().item()
+
+
 @pytest.mark.parametrize("M,N,K,resid", [(1000, 320, 320, True), (777, 320, 1280, False), (4100, 640, 640, True), (40000, 640, 640, True),
                                           (38000, 640, 2560, False), (513, 1280, 1280, True), (130, 1280, 5120, False), (64, 320, 320, True)])
 def test_gemm_rowstats(M, N, K, resid):
