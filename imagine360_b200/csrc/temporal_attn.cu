@@ -155,13 +155,16 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
 // STAGES smem stages per warp: the tasks of the next STAGES-1 iterations are in flight while one is computed.  The kernel
 // is a pure HBM stream with ~4 KB per task, so bytes in flight per SM (Little's law against ~2 us of loaded-HBM
 // latency) set its bandwidth: 16 warps x 1 task ahead = 61 KB gave 3.9 TB/s; 3 stages put 2 tasks per warp in flight.
-template <int STAGES>
-__global__ void temporal_attn_mma_kernel(const TAParams p, int hd_pad, int pitch) {
+// MT = 16-row tiles along the frame axis: 1 for F <= 16, 2 for F <= 32 (the 24-frame configuration; before, F > 16 took the
+// scalar kernel at 0.8 TB/s -- 7.1 ms instead of ~1.4 ms for the 40 x 24 x 2304 x 320 level of the 24x768x1536 step).
+template <int STAGES, int MT>
+__global__ void __launch_bounds__(384) temporal_attn_mma_kernel(const TAParams p, int hd_pad, int pitch) {
   griddep_wait();        // PDL: see common.cuh
   griddep_launch();
+  constexpr int R = 16 * MT;                       // rows (frames, zero padded) of the q / k / v tiles
   extern __shared__ __align__(16) uint8_t smem_ta[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int stage_elems = 3 * 16 * pitch;
+  const int stage_elems = 3 * R * pitch;
   bf16* base = reinterpret_cast<bf16*>(smem_ta) + static_cast<size_t>(warp) * STAGES * stage_elems;
   for (int i = lane; i < STAGES * stage_elems / 8; i += 32) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
   __syncwarp();
@@ -172,16 +175,23 @@ __global__ void temporal_attn_mma_kernel(const TAParams p, int hd_pad, int pitch
 
   // the (frame, 16-byte chunk) pairs this lane copies are the same for every task: the runtime divisions by the
   // chunks-per-row count are done once here instead of ~6 times per task
-  constexpr int kMaxCopies = 10;                         // 16 frames x head_dim 160 / 8 / 32 lanes
-  int cp_smem[kMaxCopies]; int cp_frame[kMaxCopies]; int cp_col[kMaxCopies];
+  constexpr int kMaxCopies = 10 * MT;                    // 16 * MT frames x head_dim 160 / 8 / 32 lanes
+  // MT = 1 keeps the three indices in separate registers (80 registers in all); MT = 2 packs them into one word per copy
+  // -- frame (8 bits) | column (8 bits) | smem element offset (16 bits) -- to stay within 170 registers at 12 warps per CTA
+  constexpr int kIdxWords = (MT == 1) ? 3 : 1;
+  int cp_idx[kMaxCopies][kIdxWords];
   int n_copies = 0;
 #pragma unroll
   for (int k = 0; k < kMaxCopies; ++k) {
     const int c = lane + 32 * k;
     const int f = c / cpr, ch = c - f * cpr;
-    cp_frame[k] = f; cp_col[k] = ch * 8; cp_smem[k] = f * pitch + ch * 8;
+    if (MT == 1) { cp_idx[k][0] = f; cp_idx[k][kIdxWords > 1 ? 1 : 0] = ch * 8; cp_idx[k][kIdxWords > 2 ? 2 : 0] = f * pitch + ch * 8; }
+    else cp_idx[k][0] = (f << 24) | ((ch * 8) << 16) | (f * pitch + ch * 8);
     if (c < nchunks) n_copies = k + 1;
   }
+#define CP_FRAME(k) (MT == 1 ? cp_idx[k][0] : (cp_idx[k][0] >> 24))
+#define CP_COL(k) (MT == 1 ? cp_idx[k][kIdxWords > 1 ? 1 : 0] : ((cp_idx[k][0] >> 16) & 0xff))
+#define CP_SMEM(k) (MT == 1 ? cp_idx[k][kIdxWords > 2 ? 2 : 0] : (cp_idx[k][0] & 0xffff))
   auto issue = [&](long long task, int stage) {
     const int head = static_cast<int>(task % p.heads);
     const long long pix = task / p.heads;
@@ -190,11 +200,11 @@ __global__ void temporal_attn_mma_kernel(const TAParams p, int hd_pad, int pitch
 #pragma unroll
     for (int k = 0; k < kMaxCopies; ++k) {
       if (k < n_copies) {
-        const long long r = row0 + static_cast<long long>(cp_frame[k]) * p.D;
-        const int col = head * p.hd + cp_col[k];
-        cp_async16(sq + cp_smem[k], p.q + r * p.ldq + col);
-        cp_async16(sq + 16 * pitch + cp_smem[k], p.k + r * p.ldk + col);
-        cp_async16(sq + 32 * pitch + cp_smem[k], p.v + r * p.ldv + col);
+        const long long r = row0 + static_cast<long long>(CP_FRAME(k)) * p.D;
+        const int col = head * p.hd + CP_COL(k);
+        cp_async16(sq + CP_SMEM(k), p.q + r * p.ldq + col);
+        cp_async16(sq + R * pitch + CP_SMEM(k), p.k + r * p.ldk + col);
+        cp_async16(sq + 2 * R * pitch + CP_SMEM(k), p.v + r * p.ldv + col);
       }
     }
   };
@@ -215,58 +225,82 @@ __global__ void temporal_attn_mma_kernel(const TAParams p, int hd_pad, int pitch
     asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
     __syncwarp();
     bf16* sQ = base + stage * stage_elems;
-    const bf16* sK = sQ + 16 * pitch;
-    const bf16* sV = sQ + 32 * pitch;
-    // ---- S = Q K^T (16 x 16), two 8-key n-tiles ----
-    float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    for (int k0 = 0; k0 < hd_pad; k0 += 16) {
-      uint32_t a[4];
-      a[0] = *reinterpret_cast<const uint32_t*>(sQ + g * pitch + k0 + q4 * 2);
-      a[1] = *reinterpret_cast<const uint32_t*>(sQ + (g + 8) * pitch + k0 + q4 * 2);
-      a[2] = *reinterpret_cast<const uint32_t*>(sQ + g * pitch + k0 + 8 + q4 * 2);
-      a[3] = *reinterpret_cast<const uint32_t*>(sQ + (g + 8) * pitch + k0 + 8 + q4 * 2);
+    const bf16* sK = sQ + R * pitch;
+    const bf16* sV = sQ + 2 * R * pitch;
+    // ---- S = Q K^T (R x R): MT row tiles x 2 MT 8-key column tiles ----
+    float sc[MT][2 * MT][4];
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sK + (nt * 8 + g) * pitch + k0 + q4 * 2);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sK + (nt * 8 + g) * pitch + k0 + 8 + q4 * 2);
-        mma_bf16_16816(sc[nt], a, b0, b1);
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2 * MT; ++nt) { sc[mt][nt][0] = 0.f; sc[mt][nt][1] = 0.f; sc[mt][nt][2] = 0.f; sc[mt][nt][3] = 0.f; }
+    for (int k0 = 0; k0 < hd_pad; k0 += 16) {
+      uint32_t bk[2 * MT][2];
+#pragma unroll
+      for (int nt = 0; nt < 2 * MT; ++nt) {
+        bk[nt][0] = *reinterpret_cast<const uint32_t*>(sK + (nt * 8 + g) * pitch + k0 + q4 * 2);
+        bk[nt][1] = *reinterpret_cast<const uint32_t*>(sK + (nt * 8 + g) * pitch + k0 + 8 + q4 * 2);
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        uint32_t a[4];
+        a[0] = *reinterpret_cast<const uint32_t*>(sQ + (mt * 16 + g) * pitch + k0 + q4 * 2);
+        a[1] = *reinterpret_cast<const uint32_t*>(sQ + (mt * 16 + g + 8) * pitch + k0 + q4 * 2);
+        a[2] = *reinterpret_cast<const uint32_t*>(sQ + (mt * 16 + g) * pitch + k0 + 8 + q4 * 2);
+        a[3] = *reinterpret_cast<const uint32_t*>(sQ + (mt * 16 + g + 8) * pitch + k0 + 8 + q4 * 2);
+#pragma unroll
+        for (int nt = 0; nt < 2 * MT; ++nt) mma_bf16_16816(sc[mt][nt], a, bk[nt][0], bk[nt][1]);
       }
     }
-    // ---- softmax over keys (row g: sc[.][0..1], row g+8: sc[.][2..3]; a row is spread over the 4 lanes of a quad) ----
-    float mx0 = -INFINITY, mx1 = -INFINITY;
+    // ---- softmax over keys (tile mt: row g in sc[mt][.][0..1], row g+8 in sc[mt][.][2..3]; a row is spread over the 4
+    //      lanes of a quad) and the A fragments of P ----
+    uint32_t pa[MT][MT][4];
+    float inv[MT][2];
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
+    for (int mt = 0; mt < MT; ++mt) {
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const bool ok = (nt * 8 + q4 * 2 + e) < p.F;
-        sc[nt][e] = ok ? sc[nt][e] * p.scale : -INFINITY;
-        sc[nt][2 + e] = ok ? sc[nt][2 + e] * p.scale : -INFINITY;
-        mx0 = fmaxf(mx0, sc[nt][e]); mx1 = fmaxf(mx1, sc[nt][2 + e]);
+      for (int nt = 0; nt < 2 * MT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const bool ok = (nt * 8 + q4 * 2 + e) < p.F;
+          sc[mt][nt][e] = ok ? sc[mt][nt][e] * p.scale : -INFINITY;
+          sc[mt][nt][2 + e] = ok ? sc[mt][nt][2 + e] * p.scale : -INFINITY;
+          mx0 = fmaxf(mx0, sc[mt][nt][e]); mx1 = fmaxf(mx1, sc[mt][nt][2 + e]);
+        }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 2 * MT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          sc[mt][nt][e] = __expf(sc[mt][nt][e] - mx0); sum0 += sc[mt][nt][e];
+          sc[mt][nt][2 + e] = __expf(sc[mt][nt][2 + e] - mx1); sum1 += sc[mt][nt][2 + e];
+        }
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      inv[mt][0] = 1.0f / sum0; inv[mt][1] = 1.0f / sum1;
+#pragma unroll
+      for (int ks = 0; ks < MT; ++ks) {              // 16 keys per k-step = column tiles 2 ks, 2 ks + 1
+        pa[mt][ks][0] = pack_bf16x2(sc[mt][2 * ks][0], sc[mt][2 * ks][1]);
+        pa[mt][ks][1] = pack_bf16x2(sc[mt][2 * ks][2], sc[mt][2 * ks][3]);
+        pa[mt][ks][2] = pack_bf16x2(sc[mt][2 * ks + 1][0], sc[mt][2 * ks + 1][1]);
+        pa[mt][ks][3] = pack_bf16x2(sc[mt][2 * ks + 1][2], sc[mt][2 * ks + 1][3]);
       }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        sc[nt][e] = __expf(sc[nt][e] - mx0); sum0 += sc[nt][e];
-        sc[nt][2 + e] = __expf(sc[nt][2 + e] - mx1); sum1 += sc[nt][2 + e];
-      }
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
-    uint32_t pa[4] = {pack_bf16x2(sc[0][0], sc[0][1]), pack_bf16x2(sc[0][2], sc[0][3]),
-                      pack_bf16x2(sc[1][0], sc[1][1]), pack_bf16x2(sc[1][2], sc[1][3])};
-    __syncwarp();      // all lanes are done reading Q: its tile becomes the output staging area
+    }
     // ---- O = P V, 8 head-dim columns per MMA ----
     for (int n0 = 0; n0 < p.hd; n0 += 8) {
-      uint32_t b0, b1;
-      ldmatrix_x2_trans(b0, b1, sV + (lane & 15) * pitch + n0);
-      float o[4] = {0.f, 0.f, 0.f, 0.f};
-      mma_bf16_16816(o, pa, b0, b1);
-      *reinterpret_cast<uint32_t*>(sQ + g * pitch + n0 + q4 * 2) = pack_bf16x2(o[0] * inv0, o[1] * inv0);
-      *reinterpret_cast<uint32_t*>(sQ + (g + 8) * pitch + n0 + q4 * 2) = pack_bf16x2(o[2] * inv1, o[3] * inv1);
+      uint32_t bv[MT][2];
+#pragma unroll
+      for (int ks = 0; ks < MT; ++ks) ldmatrix_x2_trans(bv[ks][0], bv[ks][1], sV + (ks * 16 + (lane & 15)) * pitch + n0);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < MT; ++ks) mma_bf16_16816(o, pa[mt][ks], bv[ks][0], bv[ks][1]);
+        *reinterpret_cast<uint32_t*>(sQ + (mt * 16 + g) * pitch + n0 + q4 * 2) = pack_bf16x2(o[0] * inv[mt][0], o[1] * inv[mt][0]);
+        *reinterpret_cast<uint32_t*>(sQ + (mt * 16 + g + 8) * pitch + n0 + q4 * 2) = pack_bf16x2(o[2] * inv[mt][1], o[3] * inv[mt][1]);
+      }
     }
     __syncwarp();
     {
@@ -276,17 +310,20 @@ __global__ void temporal_attn_mma_kernel(const TAParams p, int hd_pad, int pitch
 #pragma unroll
       for (int k = 0; k < kMaxCopies; ++k) {
         if (k < n_copies)
-          *reinterpret_cast<uint4*>(p.o + (row0 + static_cast<long long>(cp_frame[k]) * p.D) * p.ldo + head * p.hd + cp_col[k]) =
-              *reinterpret_cast<const uint4*>(sQ + cp_smem[k]);
+          *reinterpret_cast<uint4*>(p.o + (row0 + static_cast<long long>(CP_FRAME(k)) * p.D) * p.ldo + head * p.hd + CP_COL(k)) =
+              *reinterpret_cast<const uint4*>(sQ + CP_SMEM(k));
       }
     }
-    // rows >= F of the staging tile were written with garbage-free zeros only if F == 16; restore the zero padding
-    if (p.F < 16) {
-      for (int c = lane; c < (16 - p.F) * (pitch / 8); c += 32)
+    // rows >= F of the staging tile were written with garbage-free zeros only if F == R; restore the zero padding
+    if (p.F < R) {
+      for (int c = lane; c < (R - p.F) * (pitch / 8); c += 32)
         reinterpret_cast<uint4*>(sQ + p.F * pitch)[c] = make_uint4(0, 0, 0, 0);
     }
     __syncwarp();
   }
+#undef CP_FRAME
+#undef CP_COL
+#undef CP_SMEM
 }
 
 }  // namespace i360
@@ -312,36 +349,40 @@ extern "C" int i360_temporal_attention_bf16(const void* q, long long ldq, const 
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (F <= 16) {
+  if (F <= 32) {
+    const int mt = F <= 16 ? 1 : 2;                     // 16-row tiles along the frame axis
     const int hd_pad = (head_dim + 15) / 16 * 16;
     const int pitch = hd_pad + 8;                       // +16 bytes per row: conflict-free fragment / ldmatrix reads
     // Warps per SM are what buys bandwidth here (each warp keeps one ~4 KB task in flight while it computes another;
     // measured: 16 -> 20 warps per SM = -7.5 % at head_dim 40, 8 -> 10 = -15 % at head_dim 80), so the launch takes as
     // many warps as ~216 KB of smem and 80 registers per thread allow, in one or two CTAs per SM.  A third stage at the
     // cost of warps (12 per SM) was slower (I360_TA_STAGES3 keeps it for experiments).
-    const size_t per_stage = static_cast<size_t>(3) * 16 * pitch * sizeof(bf16);
-    const bool three = getenv("I360_TA_STAGES3") != nullptr && per_stage * 3 * 6 <= 110 * 1024;
+    const size_t per_stage = static_cast<size_t>(3) * 16 * mt * pitch * sizeof(bf16);
+    const bool three = mt == 1 && getenv("I360_TA_STAGES3") != nullptr && per_stage * 3 * 6 <= 110 * 1024;
     const size_t pw = per_stage * (three ? 3 : 2);
     int total_w = static_cast<int>((216 * 1024) / pw);
     if (total_w > 24) total_w = 24;
+    if (mt == 2 && total_w > 12) total_w = 12;          // the two-tile kernel is compiled for <= 384 threads (170 registers)
     if (total_w < 1) return I360_ERR_UNSUPPORTED;
     int ctas = total_w > 12 ? 2 : 1;
     int w2 = total_w / ctas;
     if (const char* e = getenv("I360_TA_WARPS")) { w2 = atoi(e); ctas = (pw * w2 * 2 <= 220 * 1024) ? 2 : 1; }
     if (three) { w2 = 6; ctas = 2; }
     const size_t sm2 = pw * w2;
-    if (sm2 > 227 * 1024 || w2 < 1 || w2 > 32) return I360_ERR_UNSUPPORTED;
+    if (sm2 > 227 * 1024 || w2 < 1 || w2 > 12) return I360_ERR_UNSUPPORTED;       // compiled for <= 384 threads per CTA
     long long bl = (total + w2 - 1) / w2;
     const long long cap2 = static_cast<long long>(num_sms()) * ctas;
     if (bl > cap2) bl = cap2;
     static bool setm = false;
     if (!setm) {
-      cudaFuncSetAttribute(temporal_attn_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(temporal_attn_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(temporal_attn_mma_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(temporal_attn_mma_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(temporal_attn_mma_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       setm = true;
     }
-    if (three) launch_k(temporal_attn_mma_kernel<3>, dim3(static_cast<unsigned>(bl)), dim3(w2 * 32), sm2, st, p, hd_pad, pitch);
-    else       launch_k(temporal_attn_mma_kernel<2>, dim3(static_cast<unsigned>(bl)), dim3(w2 * 32), sm2, st, p, hd_pad, pitch);
+    if (mt == 2)    launch_k(temporal_attn_mma_kernel<2, 2>, dim3(static_cast<unsigned>(bl)), dim3(w2 * 32), sm2, st, p, hd_pad, pitch);
+    else if (three) launch_k(temporal_attn_mma_kernel<3, 1>, dim3(static_cast<unsigned>(bl)), dim3(w2 * 32), sm2, st, p, hd_pad, pitch);
+    else            launch_k(temporal_attn_mma_kernel<2, 1>, dim3(static_cast<unsigned>(bl)), dim3(w2 * 32), sm2, st, p, hd_pad, pitch);
     I360_CUDA_CHECK_LAUNCH();
     return I360_OK;
   }

@@ -203,7 +203,8 @@ def test_warp_attention_with_bias(b, m, Fr, ph, eh, ew, heads):
 
 
 @pytest.mark.parametrize("B,Fr,D,heads,hd", [(2, 16, 50, 8, 40), (1, 16, 33, 8, 80), (2, 8, 20, 8, 160), (1, 24, 10, 8, 40),
-                                            (2, 16, 7, 8, 64), (1, 4, 5, 2, 16)])
+                                            (2, 16, 7, 8, 64), (1, 4, 5, 2, 16), (2, 24, 333, 8, 80), (1, 24, 57, 8, 160),
+                                            (1, 32, 40, 8, 40), (2, 17, 21, 5, 64)])
 def test_temporal_attention(B, Fr, D, heads, hd):
     from imagine360_b200 import ops
     C = heads * hd
