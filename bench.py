@@ -537,8 +537,8 @@ def kernel_roofline(pipe, inp, size, one_step):
     records = []
     orig_gemm, orig_conv = ops.gemm, ops.conv3x3
     L = ops.lib()
-    names = ["i360_gemm_bf16", "i360_gemm_rowstats_bf16", "i360_gemm_ln_bf16", "i360_conv3x3_bf16", "i360_conv_upsample2x_bf16", "i360_conv3x3_s2_bf16", "i360_attention_bf16", "i360_cross_attention_text_ip_bf16", "i360_temporal_attention_bf16", "i360_groupnorm_stats",
-             "i360_groupnorm_apply", "i360_layernorm", "i360_upsample2x_nhwc", "i360_im2col3x3_s2_nhwc", "i360_axpby_bf16",
+    names = ["i360_gemm_bf16", "i360_gemm_rowstats_bf16", "i360_gemm_ln_bf16", "i360_conv3x3_bf16", "i360_conv3x3_chanstats_bf16", "i360_conv_upsample2x_bf16", "i360_conv3x3_s2_bf16", "i360_attention_bf16", "i360_cross_attention_text_ip_bf16", "i360_temporal_attention_bf16", "i360_groupnorm_stats",
+             "i360_groupnorm_apply", "i360_groupnorm_apply_chanstats", "i360_layernorm", "i360_upsample2x_nhwc", "i360_im2col3x3_s2_nhwc", "i360_axpby_bf16",
              "i360_cfg_ddim_step_bf16", "i360_avgpool_frames4_bf16", "i360_grid_sample_f32", "i360_softmax_rows_bf16"]
     timed = {}
 
@@ -583,10 +583,11 @@ def kernel_roofline(pipe, inp, size, one_step):
     def conv(x, wp, *args, **kw):
         b, h, wd, _ = x.shape
         flops["conv"] += 2.0 * b * h * wd * wp.shape[0] * wp.shape[1]
-        shapes.append(("conv", b * h * wd, wp.shape[0], wp.shape[1], 0, ("i360_conv3x3_bf16", len(timed.get("i360_conv3x3_bf16", [])))))
+        cname = "i360_conv3x3_chanstats_bf16" if kw.get("chan_stats") else "i360_conv3x3_bf16"
+        shapes.append(("conv+stats" if kw.get("chan_stats") else "conv", b * h * wd, wp.shape[0], wp.shape[1], 0, (cname, len(timed.get(cname, [])))))
         px = b * h * wd
         extra = sum(t.shape[-1] for t in (kw.get("x2"), kw.get("x3")) if t is not None)
-        bounds.append((("i360_conv3x3_bf16", len(timed.get("i360_conv3x3_bf16", []))), 2.0 * px * wp.shape[0] * wp.shape[1],
+        bounds.append(((cname, len(timed.get(cname, []))), 2.0 * px * wp.shape[0] * wp.shape[1],
                        2.0 * (px * (x.shape[-1] + extra + wp.shape[0] * (2 if kw.get("resid") is not None else 1)) + wp.numel())))
         return orig_conv(x, wp, *args, **kw)
 
@@ -639,7 +640,7 @@ def kernel_roofline(pipe, inp, size, one_step):
         ops.conv_upsample2x, ops.conv3x3_s2 = orig_up, orig_s2
     per = {n: (len(v), sum(a.elapsed_time(b) for a, b in v)) for n, v in timed.items()}
     total = sum(ms for _, ms in per.values())
-    engine = ("i360_gemm_bf16", "i360_gemm_rowstats_bf16", "i360_gemm_ln_bf16", "i360_conv3x3_bf16", "i360_conv_upsample2x_bf16",
+    engine = ("i360_gemm_bf16", "i360_gemm_rowstats_bf16", "i360_gemm_ln_bf16", "i360_conv3x3_bf16", "i360_conv3x3_chanstats_bf16", "i360_conv_upsample2x_bf16",
               "i360_conv3x3_s2_bf16")   # one kernel template
     gc_ms = sum(per.get(n, (0, 0))[1] for n in engine)
     gc_n = sum(per.get(n, (0, 0))[0] * (4 if n == "i360_conv_upsample2x_bf16" else 1) for n in engine)    # 4 launches per call

@@ -51,6 +51,11 @@ struct GemmConvParams {
   // GroupNorm statistics of the OUTPUT, accumulated by the epilogue (CONV, one image per tile, group size 4 / 8 / 16 so that
   // groups never straddle a 32-column chunk): gn_stats[(image * 32 + group) * 2 + {0, 1}] += (sum, sum of squares), fp64
   double* gn_stats; int gn_gs;
+  // ... or, for ANY group size (the UNet's 10 / 20 / 40 channels per group straddle the 32-column chunks): per-CHANNEL statistics
+  // gn_chan[(image * N + channel) * 2 + {0, 1}] += (sum, sum of squares) of the stored bf16 values, fp64 atomics of fp32 warp sums (one coalesced
+  // 32-lane request per warp and chunk after a recursive-halving reduction over the warp's 32 pixel rows); the consuming
+  // GroupNorm folds channels into groups (i360_groupnorm_apply_chanstats)
+  double* gn_chan;
   int in_stride;      // CONV: input pixel = in_stride * output pixel + tap offset (2: the stride-2 downsample convs, whose
                       // activation boxes are TMA boxes with traversal stride 2 -- no im2col buffer)
   int crop;           // output columns cropped on each side (pano halo)
@@ -162,6 +167,24 @@ __device__ __forceinline__ void gn_chunk_stats(const float2* f2, bool valid, int
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); qq += __shfl_xor_sync(0xffffffffu, qq, o); }
     if (lane == 0) { atomicAdd(acc + (first_group + g) * 2, s); atomicAdd(acc + (first_group + g) * 2 + 1, qq); }
+  }
+}
+
+// Per-channel statistics of one 32-column chunk: cs / cq hold my row's 32 values and their squares (zeros for rows outside the
+// image).  Recursive halving over the warp: at offset o every lane keeps the half of its columns selected by its lane bit and
+// receives the partner's partial sums of that half, so after five steps lane l holds column l summed over the warp's 32 rows
+// (31 shuffles per array instead of 32 x 5).
+__device__ __forceinline__ void warp_column_sums(float* cs, float* cq, int lane) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send_s = up ? cs[i] : cs[i + o], keep_s = up ? cs[i + o] : cs[i];
+      const float send_q = up ? cq[i] : cq[i + o], keep_q = up ? cq[i + o] : cq[i];
+      cs[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, o);
+      cq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, o);
+    }
   }
 }
 
@@ -592,7 +615,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (p.conv) {
         w0 = (m_blk % p.n_wt) * p.TW; h0 = ((m_blk / p.n_wt) % p.n_ht) * p.TH; b0 = (m_blk / (p.n_wt * p.n_ht)) * p.TB;
         if (gn_on && b0 != gn_img) { if (gn_img >= 0) gn_flush(gn_img); gn_img = b0; }
-        if (kResid || kRowvec || direct || gn_on) {
+        if (kResid || kRowvec || direct || gn_on || p.gn_chan != nullptr) {
           const int tw = row % p.TW, th = (row / p.TW) % p.TH, tb = row / (p.TW * p.TH);
           const int w = w0 + tw, h = h0 + th, b = b0 + tb;
           valid = (b < p.B) && (h < p.H) && (w >= p.crop) && (w < p.W - p.crop);
@@ -781,6 +804,26 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float2 sc = make_float2(p.out_scale, p.out_scale);
 #pragma unroll
             for (int j = 0; j < 16; ++j) f2[j] = fmul2(f2[j], sc);
+          }
+          if (!kGeglu && !LNF && p.conv && p.gn_chan != nullptr) {     // per-channel GroupNorm statistics of the STORED values
+            float cs[32], cq[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 r = unpack_bf16x2(pack_bf16x2(f2[j].x, f2[j].y));
+              cs[2 * j] = valid ? r.x : 0.f; cs[2 * j + 1] = valid ? r.y : 0.f;
+              cq[2 * j] = cs[2 * j] * cs[2 * j]; cq[2 * j + 1] = cs[2 * j + 1] * cs[2 * j + 1];
+            }
+            warp_column_sums(cs, cq, lane);
+            const int col = ocol + lane;
+            if (col < p.n_out) {
+              // the warp's 32 rows belong to ONE image (host guarantees TW * TH >= 32 pixels of an image per tile)
+              const int img = b0 + (ew * 32) / (p.TW * p.TH);
+              if (img < p.B) {
+                double* dst = p.gn_chan + (static_cast<long long>(img) * p.n_out + col) * 2;
+                atomicAdd(dst, static_cast<double>(cs[0]));       // fp64: the order of the adds does not reach the bf16 result
+                atomicAdd(dst + 1, static_cast<double>(cq[0]));
+              }
+            }
           }
           if (gn_on) {                                          // GroupNorm statistics of what this chunk stores
             const int fg = ocol / p.gn_gs;
@@ -1122,7 +1165,8 @@ struct OutLattice { long long s_w, s_h, s_b; };
 static int conv_impl(const void* x, int B, int H, int W, int Cin, const void* x2, int C2, const void* x3, int C3, const void* Wt,
                      int Cout, void* D, const OutLattice* lattice, int crop, const void* bias, const void* resid, const float* rowvec,
                      int rowvec_div, int rowvec_ld, float out_scale, int n_taps, const signed char* tap_dh, const signed char* tap_dw,
-                     void* stream, int in_stride = 1, int Hin = 0, int Win = 0, double* gn_stats = nullptr, int gn_groups = 0) {
+                     void* stream, int in_stride = 1, int Hin = 0, int Win = 0, double* gn_stats = nullptr, int gn_groups = 0,
+                     double* gn_chan = nullptr) {
   // H, W: the OUTPUT domain that is tiled (before the crop); Hin, Win: the input tensor when in_stride != 1
   if (in_stride == 1) { Hin = H; Win = W; }
   if (!x || !Wt || !D || B <= 0 || H <= 0 || W <= 0) return I360_ERR_ARG;
@@ -1138,10 +1182,13 @@ static int conv_impl(const void* x, int B, int H, int W, int Cin, const void* x2
     if (gn_groups != 32 || (Cout % 32) || (Cout / 32 != 4 && Cout / 32 != 8 && Cout / 32 != 16) || rowvec) return I360_ERR_UNSUPPORTED;
     if (static_cast<long long>(H) * W < 128) return I360_ERR_UNSUPPORTED;
   }
-  best_box(B, H, W, &bestTW, &bestTH, &bestTB, &bestw, gn_stats ? 1 : 128);
+  // per-channel statistics reduce over a warp's 32 tile rows: those must lie in one image (TW * TH >= 32)
+  if (gn_chan && static_cast<long long>(H) * W < 32) return I360_ERR_UNSUPPORTED;
+  best_box(B, H, W, &bestTW, &bestTH, &bestTB, &bestw, gn_stats ? 1 : (gn_chan ? 4 : 128));
   GemmConvParams p;
   memset(&p, 0, sizeof(p));
   p.gn_stats = gn_stats; p.gn_gs = gn_stats ? Cout / 32 : 0;
+  p.gn_chan = gn_chan;
   p.halo = is3x3 && !lattice && in_stride == 1 && use_halo(H, W, Cin, resid != nullptr, rowvec != nullptr, C2 + C3 > 0, bestw + 1e-6 * bestTW);
   p.in_stride = in_stride;
   if (in_stride != 1 && (C2 > 0 || C3 > 0)) return I360_ERR_UNSUPPORTED;
@@ -1233,6 +1280,23 @@ extern "C" int i360_conv3x3_gnstats_bf16(const void* x, int B, int H, int W, int
   static const signed char dh[9] = {-1, -1, -1, 0, 0, 0, 1, 1, 1}, dw[9] = {-1, 0, 1, -1, 0, 1, -1, 0, 1};
   return conv_impl(x, B, H, W, Cin, x2, C2, nullptr, 0, Wt, Cout, D, nullptr, 0, bias, resid, nullptr, 1, 0, 1.0f, 9, dh, dw, stream,
                    1, 0, 0, stats, groups);
+}
+
+// i360_conv3x3_bf16 (same arguments) that also accumulates PER-CHANNEL statistics of its output from the epilogue:
+// chan_stats[(image * Cout + channel) * 2 + {0, 1}] = (sum, sum of squares) of the stored bf16 values over the image, fp64,
+// zeroed here.  Any channel count / group size: the GroupNorm reading the output folds channels into groups
+// (i360_groupnorm_apply_chanstats) and needs no statistics pass.  Replaces the first read of InflatedGroupNorm after a conv in
+// ResnetBlock3D (norm2 after conv1, animatediff/models/resnet.py:243) and of Transformer3DModel.norm after conv2
+// (animatediff/models/attention.py:262).
+extern "C" int i360_conv3x3_chanstats_bf16(const void* x, int B, int H, int W, int Cin, const void* x2, int C2, const void* x3,
+                                           int C3, const void* Wt, int Cout, void* D, int crop, const void* bias,
+                                           const void* resid, const float* rowvec, int rowvec_div, int rowvec_ld, float out_scale,
+                                           double* chan_stats, void* stream) {
+  if (!chan_stats) return I360_ERR_ARG;
+  if (cudaMemsetAsync(chan_stats, 0, sizeof(double) * 2 * B * Cout, static_cast<cudaStream_t>(stream)) != cudaSuccess) return I360_ERR_CUDA;
+  static const signed char dh[9] = {-1, -1, -1, 0, 0, 0, 1, 1, 1}, dw[9] = {-1, 0, 1, -1, 0, 1, -1, 0, 1};
+  return conv_impl(x, B, H, W, Cin, x2, C2, x3, C3, Wt, Cout, D, nullptr, crop, bias, resid, rowvec, rowvec_div, rowvec_ld, out_scale,
+                   9, dh, dw, stream, 1, 0, 0, nullptr, 0, chan_stats);
 }
 
 // 3x3 / stride 2 convolution as an implicit GEMM: the activation box of tap (kh, kw) is a TMA box with traversal stride 2

@@ -107,22 +107,43 @@ __global__ void __launch_bounds__(384, 3) gn_stats_kernel(GnSrc s, int groups, i
 }
 
 // grid (chunks, B); block = R * nvec; dynamic smem = 2*C floats (scale, shift)
+template <bool CHAN>
 __global__ void __launch_bounds__(384, 3) gn_apply_kernel(GnSrc s, int groups, int chunk_pixels, const double* __restrict__ stats,
                                 const bf16* __restrict__ gamma, const bf16* __restrict__ beta, float eps,
-                                int do_silu, double count, bf16* __restrict__ out) {
+                                int do_silu, double count, bf16* __restrict__ out, const double* __restrict__ chan) {
   griddep_wait();        // PDL: see common.cuh
   griddep_launch();
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int C = s.C1 + s.C2, nvec = C >> 3, R = blockDim.x / nvec;
   const int Wv = s.Wsrc + 2 * s.pad;
   const int npix = s.H * Wv;
   const int b = blockIdx.y;
   const int gs = C / groups;
   const double n = count > 0.0 ? count : static_cast<double>(npix) * gs;
+  // chan != nullptr: per-CHANNEL (sum, sumsq) written by the producing conv's epilogue (fp64) are folded into groups here
+  __shared__ double sgd[CHAN ? 128 : 2];         // [groups <= 64][2]
+  if (CHAN) {
+    // coalesced copy of this image's channel sums into sm (reused for scale / shift below), then one thread per group adds its
+    // gs consecutive channels in fp64 (no atomics: contended fp64 shared-memory atomics cost more than the statistics pass saved)
+    const double2* src = reinterpret_cast<const double2*>(chan) + static_cast<long long>(b) * C;
+    double2* stage = reinterpret_cast<double2*>(sm);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) stage[c] = src[c];
+    __syncthreads();
+    if (threadIdx.x < groups) {
+      double a0 = 0.0, a1 = 0.0;
+      const double2* q = stage + threadIdx.x * gs;
+#pragma unroll 4
+      for (int i = 0; i < gs; ++i) { const double2 v = q[i]; a0 += v.x; a1 += v.y; }
+      sgd[threadIdx.x * 2] = a0; sgd[threadIdx.x * 2 + 1] = a1;
+    }
+    __syncthreads();
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / gs;
-    const double m = stats[(static_cast<long long>(b) * groups + g) * 2] / n;
-    double var = stats[(static_cast<long long>(b) * groups + g) * 2 + 1] / n - m * m;
+    const double s0 = CHAN ? sgd[g * 2] : stats[(static_cast<long long>(b) * groups + g) * 2];
+    const double s1 = CHAN ? sgd[g * 2 + 1] : stats[(static_cast<long long>(b) * groups + g) * 2 + 1];
+    const double m = s0 / n;
+    double var = s1 / n - m * m;
     if (var < 0.0) var = 0.0;
     const float rstd = rsqrtf(static_cast<float>(var) + eps);   // mean / variance in fp64, rstd in fp32 (2 ulp)
     const float a = rstd * __bfloat162float(gamma[c]);
@@ -395,9 +416,28 @@ extern "C" int i360_groupnorm_apply(const void* x1, int C1, const void* x2, int 
   const long long npix = static_cast<long long>(H) * (Wsrc + 2 * pad);
   int r = gn_geometry(C, B, npix, &block, &chunk, &chunks); if (r) return r;
   const size_t smem = static_cast<size_t>(C) * 2 * sizeof(float);
-  launch_k(gn_apply_kernel, dim3(chunks, B), dim3(block), smem, static_cast<cudaStream_t>(stream),
+  launch_k(gn_apply_kernel<false>, dim3(chunks, B), dim3(block), smem, static_cast<cudaStream_t>(stream),
       s, groups, chunk, stats, static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), eps, do_silu,
-      stats_count, static_cast<bf16*>(out));
+      stats_count, static_cast<bf16*>(out), static_cast<const double*>(nullptr));
+  I360_CUDA_CHECK_LAUNCH();
+  return I360_OK;
+}
+
+// GroupNorm (+SiLU) of a dense NHWC tensor x [B, H, W, C] whose PER-CHANNEL statistics the producing conv's epilogue already
+// wrote (i360_conv3x3_chanstats_bf16): chan_stats [B, C, 2] fp64 (sum, sum of squares over the image); channels are folded
+// into the `groups` groups here, so no statistics pass over x runs.  out: dense [B, H, W, C].
+extern "C" int i360_groupnorm_apply_chanstats(const void* x, int C, int B, int H, int W, int groups, const double* chan_stats,
+                                              const void* gamma, const void* beta, float eps, int do_silu, void* out,
+                                              void* stream) {
+  if (!x || !chan_stats || !gamma || !beta || !out || (C % 8) || groups <= 0 || groups > 64 || (C % groups)) return I360_ERR_ARG;
+  GnSrc s{static_cast<const bf16*>(x), nullptr, C, 0, H, W, 0};
+  int block, chunk, chunks;
+  const long long npix = static_cast<long long>(H) * W;
+  int r = gn_geometry(C, B, npix, &block, &chunk, &chunks); if (r) return r;
+  const size_t smem = static_cast<size_t>(C) * 2 * sizeof(double);     // the channel sums are staged where scale / shift go later
+  launch_k(gn_apply_kernel<true>, dim3(chunks, B), dim3(block), smem, static_cast<cudaStream_t>(stream),
+           s, groups, chunk, static_cast<const double*>(nullptr), static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), eps,
+           do_silu, 0.0, static_cast<bf16*>(out), chan_stats);
   I360_CUDA_CHECK_LAUNCH();
   return I360_OK;
 }

@@ -67,7 +67,8 @@ def _gemm_ln(a, stats, wf, u, c, eps=1e-5, rowvec=None, rowvec_div=1, rowvec_mod
     return y
 
 
-def _conv3x3(x, w_packed, bias=None, x2=None, x3=None, resid=None, rowvec=None, rowvec_div=1, crop=0, out_scale=1.0):
+def _conv3x3(x, w_packed, bias=None, x2=None, x3=None, resid=None, rowvec=None, rowvec_div=1, crop=0, out_scale=1.0, gn_groups=None,
+             chan_stats=False):
     B, H, W, Cin = x.shape
     Cout = w_packed.shape[0]
     w = w_packed[:, : 9 * Cin].float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
@@ -85,10 +86,17 @@ def _conv3x3(x, w_packed, bias=None, x2=None, x3=None, resid=None, rowvec=None, 
     y = y.permute(0, 2, 3, 1)
     if resid is not None:
         y = y + resid.float()
-    return (y * out_scale).to(BF16).contiguous()
+    y = (y * out_scale).to(BF16).contiguous()
+    if chan_stats or gn_groups is not None:     # the statistics the epilogue leaves: sums of the stored values
+        v = y.double().view(B, -1, Cout) if chan_stats else y.double().view(B, -1, gn_groups, Cout // gn_groups)
+        red = (1,) if chan_stats else (1, 3)
+        st = torch.stack([v.sum(dim=red), (v * v).sum(dim=red)], -1)
+        return y, st
+    return y
 
 
-def _groupnorm(x1, gamma, beta, groups, eps, silu, x2=None, pad=0, stats_pad=None):
+def _groupnorm(x1, gamma, beta, groups, eps, silu, x2=None, pad=0, stats_pad=None, stats=None, chan_stats=None):
+    # ``stats`` / ``chan_stats`` (statistics from the producing conv's epilogue) are recomputed from the tensor here
     x = x1 if x2 is None else torch.cat([x1, x2], -1)
     sp = pad if stats_pad is None else stats_pad
 

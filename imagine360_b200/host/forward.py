@@ -161,22 +161,46 @@ def all_temb_projections(unet, silu_emb):
 # ------------------------------------------------------------------------------------------------------
 # ResnetBlock3D (resnet.py:221-254), optionally on the pano circular halo (MVGenModel.py:276-281)
 # ------------------------------------------------------------------------------------------------------
+# conv -> GroupNorm (opt-in, I360_CONV_GN_STATS=1): the conv epilogue accumulates per-channel statistics of what it stores and the
+# GroupNorm that reads the tensor folds channels into groups instead of running a statistics pass (norm2 after conv1;
+# Transformer3DModel.norm after a block's conv2).  Measured on the C3 step (profiles/r02b_conv_gn_chanstats_ab.txt): the 68
+# statistics passes it removes are 3.3 ms, the conv epilogues pay 1.7 ms and the apply kernels 1.0 ms for it -> -0.4 ms of
+# ~300 ms, inside the run-to-run noise, while the engine's own time (the roofline kernel) grows.  Off by default.
+CONV_GN = os.environ.get("I360_CONV_GN_STATS", "0") not in ("", "0")
+
+
+def _chan_stats_ok(h: int, w: int) -> bool:
+    return CONV_GN and h * w >= 32          # a warp's 32 tile rows must lie in one image
+
+
 @traced("resnet_block")
-def resnet_block(x, r, temb, frames: int, groups: int, skip=None, halo: int = 0):
+def resnet_block(x, r, temb, frames: int, groups: int, skip=None, halo: int = 0, out_stats: bool = False):
     """x [N,H,W,C1] (+ skip [N,H,W,C2] = the torch.cat of the up path) -> [N,H,W,Cout].
     halo > 0: pad_pano(halo) -> block -> unpad_pano(halo): the GroupNorm statistics are taken over the padded tensor
-    (norm2 even over conv1's zero-padded outer columns) exactly as the reference does."""
+    (norm2 even over conv1's zero-padded outer columns) exactly as the reference does.
+    ``out_stats``: also leave the per-channel statistics of the result on it (``_i360_chan_stats``) for the GroupNorm of the
+    Transformer3DModel that follows."""
     eps = r.norm1.eps
     h = ops.groupnorm(x, r.norm1.weight, r.norm1.bias, groups, eps, True, x2=skip, pad=halo)
     w1, b1 = conv_w(r.conv1)
-    h = ops.conv3x3(h, w1, bias=b1, rowvec=temb, rowvec_div=frames)
-    h = ops.groupnorm(h, r.norm2.weight, r.norm2.bias, groups, eps, True)
+    if _chan_stats_ok(h.shape[1], h.shape[2]):
+        h, st = ops.conv3x3(h, w1, bias=b1, rowvec=temb, rowvec_div=frames, chan_stats=True)
+        h = ops.groupnorm(h, r.norm2.weight, r.norm2.bias, groups, eps, True, chan_stats=st)
+    else:
+        h = ops.conv3x3(h, w1, bias=b1, rowvec=temb, rowvec_div=frames)
+        h = ops.groupnorm(h, r.norm2.weight, r.norm2.bias, groups, eps, True)
+    want = out_stats and _chan_stats_ok(x.shape[1], x.shape[2])
     if r.conv_shortcut is not None:
         w2, b2 = conv_w(r.conv2, shortcut=r.conv_shortcut)
-        return ops.conv3x3(h, w2, bias=b2, x2=x, x3=skip, crop=halo, out_scale=1.0 / r.output_scale_factor)
-    assert skip is None
-    w2, b2 = conv_w(r.conv2)
-    return ops.conv3x3(h, w2, bias=b2, resid=x, crop=halo, out_scale=1.0 / r.output_scale_factor)
+        y = ops.conv3x3(h, w2, bias=b2, x2=x, x3=skip, crop=halo, out_scale=1.0 / r.output_scale_factor, chan_stats=want)
+    else:
+        assert skip is None
+        w2, b2 = conv_w(r.conv2)
+        y = ops.conv3x3(h, w2, bias=b2, resid=x, crop=halo, out_scale=1.0 / r.output_scale_factor, chan_stats=want)
+    if want:
+        y, st = y
+        y._i360_chan_stats = st
+    return y
 
 
 # I360_CONV_S2_IM2COL=1: the round-1 path (materialised im2col + GEMM) for A/B runs
@@ -239,7 +263,9 @@ def spatial_transformer(x, t3d, ctx: Context, frames: int):
     n, h, w, c = x.shape
     heads, hd = t3d.heads, t3d.dim_head
     npix = h * w
-    hn = ops.groupnorm(x, t3d.norm.weight, t3d.norm.bias, t3d.groups, 1e-6, False)
+    # statistics of x from the epilogue of the conv that produced it (resnet_block(..., out_stats=True)), when it left them
+    cst = getattr(x, "_i360_chan_stats", None)
+    hn = ops.groupnorm(x, t3d.norm.weight, t3d.norm.bias, t3d.groups, 1e-6, False, chan_stats=cst)
     wi, bi = lin_w(t3d.proj_in)
     t, st = token_linear(tokens(hn), wi, bi)
     for blk in t3d.transformer_blocks:
@@ -356,7 +382,7 @@ def unet_single_forward(unet, sample, timestep, ctx_tokens, fps=None):
     skips = [x]
     for blk in unet.down_blocks:
         for j, r in enumerate(blk.resnets):
-            x = resnet_block(x, r, temb[r], frames, g)
+            x = resnet_block(x, r, temb[r], frames, g, out_stats=blk.has_cross_attention)
             if blk.has_cross_attention:
                 x = spatial_transformer(x, blk.attentions[j], ctx, frames)
             if blk.motion_modules[j] is not None:      # UNet3DConditionModel.forward runs them in every block
@@ -366,7 +392,7 @@ def unet_single_forward(unet, sample, timestep, ctx_tokens, fps=None):
             x = downsample(x, blk.downsamplers[0], False)
             skips.append(x)
     mid = unet.mid_block
-    x = resnet_block(x, mid.resnets[0], temb[mid.resnets[0]], frames, g)
+    x = resnet_block(x, mid.resnets[0], temb[mid.resnets[0]], frames, g, out_stats=True)
     for i, att in enumerate(mid.attentions):
         x = spatial_transformer(x, att, ctx, frames)
         if mid.motion_modules[i] is not None:
@@ -374,7 +400,7 @@ def unet_single_forward(unet, sample, timestep, ctx_tokens, fps=None):
         x = resnet_block(x, mid.resnets[i + 1], temb[mid.resnets[i + 1]], frames, g)
     for blk in unet.up_blocks:
         for j, r in enumerate(blk.resnets):
-            x = resnet_block(x, r, temb[r], frames, g, skip=skips.pop())
+            x = resnet_block(x, r, temb[r], frames, g, skip=skips.pop(), out_stats=blk.has_cross_attention)
             if blk.has_cross_attention:
                 x = spatial_transformer(x, blk.attentions[j], ctx, frames)
             if blk.motion_modules[j] is not None:

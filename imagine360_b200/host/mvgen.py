@@ -343,8 +343,9 @@ class MultiViewBaseModel(nn.Module):
         xs, ys = [x], [y]
         for i, (bp, bq) in enumerate(zip(pu.down_blocks, qu.down_blocks)):
             for j in range(len(bq.resnets)):
-                x = Fw.resnet_block(x, bp.resnets[j], temb_p[bp.resnets[j]], frames, g)
-                y = Fw.resnet_block(y, bq.resnets[j], temb_q[bq.resnets[j]], frames, g, halo=2)
+                ca = bq.has_cross_attention
+                x = Fw.resnet_block(x, bp.resnets[j], temb_p[bp.resnets[j]], frames, g, out_stats=ca)
+                y = Fw.resnet_block(y, bq.resnets[j], temb_q[bq.resnets[j]], frames, g, halo=2, out_stats=ca)
                 if bq.has_cross_attention:
                     x = Fw.spatial_transformer(x, bp.attentions[j], ctx_p, frames)
                     x = Fw.temporal_module(x, bp.motion_modules[j], frames)
@@ -360,8 +361,8 @@ class MultiViewBaseModel(nn.Module):
                 ys.append(y)
                 x, y = warp(self.cp_blocks_encoder[i], x, y)
         mp, mq = pu.mid_block, qu.mid_block
-        x = Fw.resnet_block(x, mp.resnets[0], temb_p[mp.resnets[0]], frames, g)
-        y = Fw.resnet_block(y, mq.resnets[0], temb_q[mq.resnets[0]], frames, g, halo=2)
+        x = Fw.resnet_block(x, mp.resnets[0], temb_p[mp.resnets[0]], frames, g, out_stats=True)
+        y = Fw.resnet_block(y, mq.resnets[0], temb_q[mq.resnets[0]], frames, g, halo=2, out_stats=True)
         for i in range(len(mq.attentions)):
             x = Fw.spatial_transformer(x, mp.attentions[i], ctx_p, frames)
             x = Fw.temporal_module(x, mp.motion_modules[i], frames)
@@ -373,8 +374,9 @@ class MultiViewBaseModel(nn.Module):
         dec = 0
         for bp, bq in zip(pu.up_blocks, qu.up_blocks):
             for j in range(len(bq.resnets)):
-                x = Fw.resnet_block(x, bp.resnets[j], temb_p[bp.resnets[j]], frames, g, skip=xs.pop())
-                y = Fw.resnet_block(y, bq.resnets[j], temb_q[bq.resnets[j]], frames, g, skip=ys.pop(), halo=2)
+                ca = bq.has_cross_attention
+                x = Fw.resnet_block(x, bp.resnets[j], temb_p[bp.resnets[j]], frames, g, skip=xs.pop(), out_stats=ca)
+                y = Fw.resnet_block(y, bq.resnets[j], temb_q[bq.resnets[j]], frames, g, skip=ys.pop(), halo=2, out_stats=ca)
                 if bq.has_cross_attention:
                     x = Fw.spatial_transformer(x, bp.attentions[j], ctx_p, frames)
                     x = Fw.temporal_module(x, bp.motion_modules[j], frames)

@@ -184,7 +184,8 @@ def pack_conv3x3(weight: torch.Tensor, *shortcuts: torch.Tensor) -> torch.Tensor
 
 
 def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias=None, x2=None, x3=None, resid=None,
-            rowvec=None, rowvec_div: int = 1, crop: int = 0, out_scale: float = 1.0, gn_groups: int | None = None):
+            rowvec=None, rowvec_div: int = 1, crop: int = 0, out_scale: float = 1.0, gn_groups: int | None = None,
+            chan_stats: bool = False):
     """3x3 / stride 1 / zero-pad 1 convolution on NHWC ``x`` [B, H, W, Cin] -> [B, H, W-2*crop, Cout].
 
     ``x2``/``x3`` are optional NHWC sources [B, H, W-2*crop, C] (no halo) of a fused 1x1 convolution whose
@@ -201,6 +202,15 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias=None, x2=None, x3=None
         assert resid.shape == out.shape and resid.is_contiguous()
     if rowvec is not None:
         assert rowvec.dtype == torch.float32 and rowvec.is_contiguous()
+    if chan_stats:
+        # the epilogue also accumulates PER-CHANNEL statistics of the output -> (out, stats [B, Cout, 2] fp64); any group size
+        st = torch.empty((B, Cout, 2), dtype=torch.float64, device=x.device)
+        rc = lib().i360_conv3x3_chanstats_bf16(
+            _p(x), c_int(B), c_int(H), c_int(W), c_int(Cin), _p(x2), c_int(C2), _p(x3), c_int(C3),
+            _p(w_packed), c_int(Cout), _p(out), c_int(crop), _p(bias), _p(resid), _p(rowvec),
+            c_int(rowvec_div), c_int(rowvec.shape[-1] if rowvec is not None else 0), c_float(out_scale), _p(st), _stream())
+        check(rc, "i360_conv3x3_chanstats_bf16")
+        return out, st
     if gn_groups is not None:
         # the epilogue also accumulates the GroupNorm statistics of the output -> (out, stats [B, 32, 2] fp64)
         assert x3 is None and rowvec is None and crop == 0 and out_scale == 1.0
@@ -288,7 +298,7 @@ def conv3x3_halo_policy(on: int = -1, tol: float = -1.0, allow_extra: int = -1, 
 # normalisation
 # ------------------------------------------------------------------------------------------------
 def groupnorm(x1: torch.Tensor, gamma, beta, groups: int, eps: float, silu: bool, x2=None, pad: int = 0,
-              stats_pad: int | None = None, stats: torch.Tensor | None = None) -> torch.Tensor:
+              stats_pad: int | None = None, stats: torch.Tensor | None = None, chan_stats: torch.Tensor | None = None) -> torch.Tensor:
     """GroupNorm(+SiLU) over the channel concat of NHWC ``x1`` (and ``x2``), circularly padded by ``pad`` columns.
     Statistics are per image over the padded tensor (``stats_pad`` overrides the pad used for statistics); ``stats``
     [B, groups, 2] fp64 from the producing conv's epilogue (``conv3x3(..., gn_groups=)``) skips the statistics pass."""
@@ -298,6 +308,14 @@ def groupnorm(x1: torch.Tensor, gamma, beta, groups: int, eps: float, silu: bool
     C2 = x2.shape[-1] if x2 is not None else 0
     C = C1 + C2
     sp = pad if stats_pad is None else stats_pad
+    if chan_stats is not None:
+        # per-channel statistics [B, C, 2] fp64 from the producing conv's epilogue (conv3x3(..., chan_stats=True))
+        assert x2 is None and pad == 0 and sp == 0 and chan_stats.shape == (B, C, 2) and chan_stats.dtype == torch.float64
+        out = torch.empty((B, H, W, C), dtype=BF16, device=x1.device)
+        rc = lib().i360_groupnorm_apply_chanstats(_p(x1), c_int(C), c_int(B), c_int(H), c_int(W), c_int(groups), _p(chan_stats),
+                                                  _p(gamma), _p(beta), c_float(eps), c_int(1 if silu else 0), _p(out), _stream())
+        check(rc, "i360_groupnorm_apply_chanstats")
+        return out
     if stats is None:
         stats = torch.empty((B, groups, 2), dtype=torch.float64, device=x1.device)
         rc = lib().i360_groupnorm_stats(_p(x1), c_int(C1), _p(x2), c_int(C2), c_int(B), c_int(H), c_int(W), c_int(sp),

@@ -84,6 +84,18 @@ int i360_conv3x3_gnstats_bf16(const void* x, int B, int H, int W, int Cin, const
 int i360_conv_upsample2x_gnstats_bf16(const void* x, int B, int H, int W, int Cin, const void* Weff, int Cout, void* D,
                                       const void* bias, int groups, double* stats, void* stream);
 
+/* conv -> GroupNorm for ANY group size: i360_conv3x3_bf16 (same arguments) whose epilogue also accumulates per-CHANNEL
+ * statistics of the stored output, chan_stats[(image * Cout + channel) * 2 + {0, 1}] = (sum, sum of squares), fp64, zeroed by
+ * the call; and the GroupNorm (+SiLU) that folds those channels into groups instead of running a statistics pass.  Replaces
+ * the first read of InflatedGroupNorm after a conv: norm2 after conv1 in ResnetBlock3D (animatediff/models/resnet.py:243) and
+ * Transformer3DModel.norm after the block's conv2 (animatediff/models/attention.py:262). */
+int i360_conv3x3_chanstats_bf16(const void* x, int B, int H, int W, int Cin, const void* x2, int C2, const void* x3, int C3,
+                                const void* Wt, int Cout, void* D, int crop, const void* bias, const void* resid,
+                                const float* rowvec, int rowvec_div, int rowvec_ld, float out_scale, double* chan_stats,
+                                void* stream);
+int i360_groupnorm_apply_chanstats(const void* x, int C, int B, int H, int W, int groups, const double* chan_stats,
+                                   const void* gamma, const void* beta, float eps, int do_silu, void* out, void* stream);
+
 /* 3x3 / stride 2 convolution as an implicit GEMM over TMA boxes with traversal stride 2 (no im2col buffer).  pad_lo = 1:
  * symmetric zero pad 1 (Downsample3D, animatediff/models/resnet.py:117-140; with pad_pano(2) / unpad_pano(1) of
  * MVGenModel.py:305-314 as a materialised 2-column circular halo and crop = 1); pad_lo = 0: the VAE encoder's asymmetric

@@ -56,9 +56,13 @@ def load_native(mod, sd_native):
 
 
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("conv_gn", [False, True])
 @pytest.mark.parametrize("cin,cout,halo,skip", [(64, 64, 0, 0), (64, 128, 0, 0), (128, 64, 2, 64), (320, 320, 2, 0), (640, 320, 0, 320)])
-def test_resnet_block(cin, cout, halo, skip):
+def test_resnet_block(cin, cout, halo, skip, conv_gn, monkeypatch):
+    """conv_gn: the opt-in conv -> GroupNorm path (I360_CONV_GN_STATS=1): norm2 from conv1's epilogue statistics, and conv2 leaves
+    the statistics of the block's result for the Transformer3DModel norm that follows."""
     from imagine360_b200.host import forward as Fw
+    monkeypatch.setattr(Fw, "CONV_GN", conv_gn)
     from imagine360_b200.host.unet3d import ResnetBlock3D
     from oracle import geometry as G, unet3d as OU
     from oracle.nn_ops import P
@@ -75,8 +79,14 @@ def test_resnet_block(cin, cout, halo, skip):
     # native
     import torch.nn.functional as F
     tproj = (F.silu(temb).float() @ sd_o["time_emb_proj.weight"].t() + sd_o["time_emb_proj.bias"]).contiguous()
-    out = Fw.resnet_block(nhwc(x), m, tproj, f, 32, skip=nhwc(s) if skip else None, halo=halo)
+    out = Fw.resnet_block(nhwc(x), m, tproj, f, 32, skip=nhwc(s) if skip else None, halo=halo, out_stats=True)
     assert rel_err(ncfhw(out, b), ref) < 2e-2     # 2 convs + 2 norms: ~5 bf16 round-offs
+    st = getattr(out, "_i360_chan_stats", None)
+    assert (st is not None) == conv_gn
+    if conv_gn:
+        v = out.double().view(b * f, -1, cout)
+        want = torch.stack([v.sum(1), (v * v).sum(1)], -1)
+        assert torch.allclose(st, want, rtol=1e-5, atol=1e-4)
 
 
 def test_spatial_transformer_vs_oracle_and_reference():

@@ -276,6 +276,47 @@ def test_conv_with_groupnorm_statistics(B, H, W, Cin, Cout, mode):
     assert (a.float() - b_.float()).abs().max().item() <= 0.04 * b_.float().abs().max().item()
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,mode", [(2, 64, 64, 320, 320, "temb"), (2, 64, 132, 320, 320, "temb_crop"), (4, 32, 32, 320, 640, "shortcut"),
+                                                 (3, 16, 36, 1280, 640, "shortcut_crop"), (5, 8, 8, 1280, 1280, "resid"), (2, 8, 20, 640, 1280, "resid_crop"),
+                                                 (7, 4, 8, 1280, 1280, "temb"), (2, 32, 68, 640, 640, "resid")])
+def test_conv_with_channel_statistics(B, H, W, Cin, Cout, mode):
+    """i360_conv3x3_chanstats_bf16 + i360_groupnorm_apply_chanstats (the UNet's group sizes 10 / 20 / 40): the conv result is
+    the plain kernel's, the per-channel sums equal those of the stored tensor, and GroupNorm applied from them agrees with the
+    statistics pass.  temb rowvec, fused shortcut, residual, pano crop, several images per tile (TB = 2, 4), halo kernels."""
+    from imagine360_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B + H * 3 + W * 5 + Cin + Cout)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    crop = 2 if mode.endswith("_crop") else 0
+    x = rn(B, H, W, Cin).bfloat16()
+    w = (rn(Cout, Cin, 3, 3) / (9 * Cin) ** 0.5).bfloat16()
+    bias = (rn(Cout) + 0.5).bfloat16()
+    kw = {"crop": crop}
+    wp = ops.pack_conv3x3(w)
+    if mode.startswith("temb"):
+        kw["rowvec"] = rn(1, Cout).float().contiguous()
+        kw["rowvec_div"] = B
+    if mode.startswith("resid"):
+        kw["resid"] = rn(B, H, W - 2 * crop, Cout).bfloat16()
+        kw["out_scale"] = 0.5
+    if mode.startswith("shortcut"):
+        x2 = rn(B, H, W - 2 * crop, 200).bfloat16()
+        wp = ops.pack_conv3x3(w, (rn(Cout, 200, 1, 1) / 200 ** 0.5).bfloat16())
+        kw["x2"] = x2
+    out, st = ops.conv3x3(x, wp, bias=bias, chan_stats=True, **kw)
+    plain = ops.conv3x3(x, wp, bias=bias, **kw)
+    assert torch.equal(out, plain)
+    v = out.double().view(B, -1, Cout)
+    ref = torch.stack([v.sum(dim=1), (v * v).sum(dim=1)], -1)                      # statistics of the STORED (bf16) tensor
+    n = v.shape[1]
+    assert ((st[..., 0] - ref[..., 0]).abs() / n).max().item() < 1e-4
+    assert ((st[..., 1] - ref[..., 1]).abs() / ref[..., 1]).max().item() < 1e-4
+    gam, bet = (1 + 0.1 * rn(Cout)).bfloat16(), (0.1 * rn(Cout)).bfloat16()
+    for silu in (True, False):
+        a = ops.groupnorm(out, gam, bet, 32, 1e-5, silu, chan_stats=st)
+        b_ = ops.groupnorm(out, gam, bet, 32, 1e-5, silu)
+        assert (a.float() - b_.float()).abs().max().item() <= 0.02 * b_.float().abs().max().item()
+
+
 @pytest.mark.parametrize("M,N,K,resid", [(1000, 320, 320, True), (777, 320, 1280, False), (4100, 640, 640, True), (40000, 640, 640, True),
                                           (38000, 640, 2560, False), (513, 1280, 1280, True), (130, 1280, 5120, False), (64, 320, 320, True)])
 def test_gemm_rowstats(M, N, K, resid):
