@@ -32,12 +32,11 @@ def sam_1024():
     return StubSam(img_size=1024)
 
 
-def oracle_call(sd_mv, sd_vae, pipe, vb, prompt, negative, steps, dtype, seed_t, seed_p):
+def oracle_call(sd_mv, sd_vae, pipe, vb, prompt, negative, steps, dtype, seed_t, seed_p, dev="cuda"):
     """The reference's __call__ sequence over the oracle functions, in ``dtype`` (fp32 = truth with the production grid /
     PE quantisation; bf16 = what the reference's production path computes through torch's kernels)."""
     from oracle import pipeline as OP
     from oracle import vae as OV
-    dev = "cuda"
     f, m = vb["video_length"], vb["pers_pixel_values"].shape[2]
     cams = vb["cameras"]
     torch.manual_seed(seed_t)
