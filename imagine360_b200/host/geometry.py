@@ -132,7 +132,35 @@ def _normalised_grid(px, py, src_h, src_w, dtype, device):
     return torch.stack([gx, gy], dim=-1).float().contiguous()
 
 
-_grid_cache: dict = {}
+_grid_cache: dict = {}        # key[1] is always the camera set (camera_lists(...)) the entry was built for
+_set_last_use: dict = {}      # camera set -> tick of its last use (prune_cache drops the least recently used sets)
+_tick = [0]
+
+
+def _touch(cams):
+    _tick[0] += 1
+    _set_last_use[cams] = _tick[0]
+
+
+def cached_entries(cameras) -> list:
+    """Every cached table built for this camera set.  A captured step graph keeps this list: the graph reads the tables by
+    address, so they must outlive any pruning of the cache."""
+    cams = camera_lists(cameras)
+    return [v for k, v in _grid_cache.items() if k[1] == cams]
+
+
+def prune_cache(max_sets: int = 4) -> None:
+    """The reference script uses one fixed icosahedron camera set (inference_dual_p2e.py:79-110) and the tables of a set are
+    ~100 MB at 16x512x1024; a caller that varies the cameras per clip would otherwise grow the cache without bound.  Keeps the
+    ``max_sets`` most recently used camera sets."""
+    sets = {k[1] for k in _grid_cache}
+    if len(sets) <= max_sets:
+        return
+    keep = set(sorted(sets, key=lambda c: _set_last_use.get(c, 0))[-max_sets:])
+    for k in [k for k in _grid_cache if k[1] not in keep]:
+        del _grid_cache[k]
+    for c in [c for c in _set_last_use if c not in keep]:
+        del _set_last_use[c]
 
 
 def e2p(e_img, cameras, out_hw, mode="bilinear", grid_dtype=None):
@@ -141,6 +169,7 @@ def e2p(e_img, cameras, out_hw, mode="bilinear", grid_dtype=None):
     m, c, eh, ew = e_img.shape
     gd = grid_dtype or e_img.dtype
     key = ("e2p", cams, eh, ew, out_hw, gd, str(e_img.device))
+    _touch(cams)
     if key not in _grid_cache:
         px, py = e2p_pixel_grid(cams, eh, ew, *out_hw)
         _grid_cache[key] = _normalised_grid(px, py, eh, ew, gd, e_img.device)
@@ -153,6 +182,7 @@ def p2e(p_img, cameras, out_hw, mode="bilinear", theta_offset=0.0, grid_dtype=No
     m, c, ph, pw = p_img.shape
     gd = grid_dtype or p_img.dtype
     key = ("p2e", cams, ph, pw, out_hw, theta_offset, gd, str(p_img.device))
+    _touch(cams)
     if key not in _grid_cache:
         px, py, mask = p2e_pixel_grid(cams, ph, pw, *out_hw, theta_offset=theta_offset)
         _grid_cache[key] = (_normalised_grid(px, py, ph, pw, gd, p_img.device),
@@ -204,6 +234,7 @@ def warp_biases(ph, pw, eh, ew, cameras, device, antipodal: bool, grid_dtype=BF1
     ATen's bf16 grid_sample/conv kernels and is not pinned by anything)."""
     cams = camera_lists(cameras)
     key = ("bias", cams, ph, pw, eh, ew, antipodal, grid_dtype, str(device))
+    _touch(cams)
     if key in _grid_cache:
         return _grid_cache[key]
     m = len(cams[0])
@@ -240,6 +271,7 @@ def spherical_pe_tables(freq_bands, ph, pw, eh, ew, cameras, device, dtype=BF16)
     the reference: -> (pers_pe [m*ph*pw, C], equi_pe [eh*ew, C])."""
     cams = camera_lists(cameras)
     key = ("pe", cams, ph, pw, eh, ew, dtype, str(device), freq_bands.data_ptr(), freq_bands._version)
+    _touch(cams)
     if key in _grid_cache:
         return _grid_cache[key]
     x, y = np.meshgrid(np.linspace(-np.pi, np.pi, ew), np.linspace(np.pi / 2, -np.pi / 2, eh))

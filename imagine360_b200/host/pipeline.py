@@ -112,6 +112,9 @@ class StepGraph:
         with torch.cuda.graph(self.g_step):
             self.pred_pers, self.pred_pano = forward(list(self.slots), adapter_tokens=self.tokens)
         self.kernels_per_replay = _lib.LAUNCHES - n0        # C-ABI launches recorded into the step graph
+        # the graphs read the mask / PE / grid tables of this camera set by address: hold them, so that pruning the geometry cache
+        # (G.prune_cache) can never free what a live graph reads
+        self._geometry = G.cached_entries(self.cams)
 
     @staticmethod
     def key_of(pipe, pano_latent, pers_latent, cond, cameras):
@@ -324,6 +327,7 @@ class AnimationPipeline:
         dev = pano_latent.device
         m = pers_latent.shape[1]
         self.scheduler.set_timesteps(num_inference_steps, device=dev)
+        G.prune_cache()          # bounded when the caller varies the cameras per clip (the reference script never does)
         i0, i1 = step_range if step_range is not None else (0, num_inference_steps)
         if inject is None and dev.type == "cuda" and os.environ.get("I360_CUDA_GRAPH", "1") != "0":
             key = StepGraph.key_of(self, pano_latent, pers_latent, cond, cameras)

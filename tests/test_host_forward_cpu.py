@@ -193,3 +193,31 @@ def test_single_unet_forward_vs_oracle_and_reference():
     rel = lambda a, b: ((a.float() - b.float()).abs().max() / b.float().abs().max()).item()
     assert rel(out, ref) < 5e-2                    # ~60 ops deep with bf16 storage between them
     assert rel(out, g["y"]) < 6e-2                 # the unmodified reference's fp32 output
+
+
+def test_geometry_cache_is_bounded_and_keeps_what_a_graph_holds():
+    """The mask / PE / grid tables are cached per camera set; ``prune_cache`` keeps the most recently used sets and
+    ``cached_entries`` is what a captured step graph holds on to (it reads the tables by address)."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from cpu_ops import cpu_ops
+    from imagine360_b200.host import geometry as G
+    G._grid_cache.clear()
+    G._set_last_use.clear()
+    fb = (2.0 ** torch.arange(4)).to(BF)
+    sets = [dict(FoV=[90, 90], theta=[10.0 * i, 100.0 + i], phi=[5.0, -20.0]) for i in range(6)]
+    with cpu_ops():
+        for c in sets:
+            G.warp_biases(4, 4, 8, 16, c, "cpu", False)
+            G.spherical_pe_tables(fb, 4, 4, 8, 16, c, "cpu")
+        held = G.cached_entries(sets[0])
+        assert len(held) >= 4                                  # e2p grid, p2e grid + mask, bias pair, PE pair
+        G.warp_biases(4, 4, 8, 16, sets[1], "cpu", False)      # set 1 becomes the most recently used
+        G.prune_cache(max_sets=3)
+        alive = {k[1] for k in G._grid_cache}
+        assert alive == {G.camera_lists(c) for c in (sets[1], sets[4], sets[5])}
+        assert G.cached_entries(sets[0]) == [] and all(isinstance(v, (tuple, torch.Tensor)) for v in held)      # still referenced
+        again = G.warp_biases(4, 4, 8, 16, sets[0], "cpu", False)                                              # rebuilt on demand
+        assert torch.equal(again[0], next(v for v in held if isinstance(v, tuple) and v[0].shape == again[0].shape)[0])
+    G._grid_cache.clear()
+    G._set_last_use.clear()

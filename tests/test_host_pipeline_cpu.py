@@ -205,3 +205,44 @@ def test_call_end_to_end_host_wiring_vs_oracle(monkeypatch):
     # bf16 storage between the ops of two steps and a decode against fp32 throughout: measured mean 0.008, max 0.09 of a [0, 1] video;
     # a wrong RNG order, chunking, mask or crop moves the video by O(0.3)
     assert d.mean().item() < 0.02 and d.max().item() < 0.2, (d.mean().item(), d.max().item())
+
+
+def test_step_graph_construction_logic(monkeypatch):
+    """``StepGraph.__init__`` -- static buffers, conditioning load, the two eager warm-up passes (both WarpAttn bias variants of all
+    7 call sites), bias slots frozen, adapter + step captures -- executed on the CPU with torch's CUDA-graph API stubbed out and
+    the kernels emulated: checks the PYTHON of the default GPU path (the graphs themselves are a GPU test:
+    tests/test_pipeline_gpu.py::test_cuda_graph_step_equals_eager_step).  The graph object holds the geometry tables it reads by
+    address, so pruning the geometry cache cannot free them."""
+    import contextlib
+    import types
+    from imagine360_b200.host import geometry as G
+    from imagine360_b200.host import pipeline as PL
+    from imagine360_b200.host.config import SCHEDULER_KWARGS
+    from imagine360_b200.host.ddim import DDIMScheduler
+    from imagine360_b200.host.mvgen import MultiViewBaseModel
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", lambda: types.SimpleNamespace(replay=lambda: None))
+    monkeypatch.setattr(torch.cuda, "graph", lambda g: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+    G._grid_cache.clear()
+    G._set_last_use.clear()
+    g = load("mvgen.pt")
+    mv = MultiViewBaseModel(tiny_unet(), tiny_unet()).to(BF)
+    mv.load_state_dict({k: v.to(BF) for k, v in synth_state(g["shapes"], g["seed"]).items()}, strict=False)
+    f, m = 16, 2
+    mk = lambda shape, seed, scale=1.0: (synth_tensor(shape, seed) * scale).to(BF)      # noqa: E731
+    pano, pers = mk((1, 4, f, 32, 64), 20), mk((1, m, 4, f, 16, 16), 21)
+    cond = PL.Conditioning(mk((2, 5, 32), 24), mk((2 * m, 5, 32), 25), mk((2, f, 4096, 8), 26),
+                           mk((2, 1, f, 4096, 8), 27).expand(-1, m, -1, -1, -1),
+                           torch.tensor([1.0, 1.0, 63.0, 63.0, 128.0, 256.0])[None].repeat(f, 1), torch.linspace(-5, 5, f), 8)
+    pipe = PL.AnimationPipeline(None, None, None, mv.unet, mv.pano_unet, mv, DDIMScheduler(**SCHEDULER_KWARGS))
+    calls = {}
+    with cpu_ops(calls):
+        sg = PL.StepGraph(pipe, pano, pers, cond, g["cams"])
+    assert sg.pred_pano.shape == (2, 4, f, 32, 64) and sg.pred_pers.shape == (2, m, 4, f, 16, 16)
+    assert len(sg.slots) == 7 and calls["grid_sample"] > 0
+    held = sg._geometry
+    assert len(held) > 0 and len(held) == len(G.cached_entries(sg.cams))
+    G._grid_cache.clear()                      # an aggressive prune: the graph's tables stay referenced
+    assert all(v is not None for v in held)
+    G._set_last_use.clear()
